@@ -1,0 +1,169 @@
+/*
+ * glowk.h -- C ABI of the B200 (sm_100a) Glow flow kernels.
+ *
+ * Drop-in boundary for the hot path of corenel/pytorch-glow.
+ * The reference has no FFI of its own: its boundary is the nn.Module surface of
+ * network/module.py + network/model.py, all of which bottoms out in ATen calls.
+ * Each entry point below replaces the ATen call sequence of the cited reference
+ * lines; INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - flow state is contiguous NCHW fp32 exactly as in the reference;
+ *   - "rows" matrices are [P][ld] with P = N*H*W pixels (pixel-major, channel
+ *     contiguous) and are the operands of the coupling-network GEMMs; their
+ *     element type is selected by `act_dtype` (GLOWK_F32 | GLOWK_BF16);
+ *   - `stream` is a cudaStream_t passed as void* (torch's current stream);
+ *   - return value: 0 = ok, otherwise a GLOWK_E* code; glowk_last_error() gives
+ *     the message for the calling thread.  No entry point keeps global mutable
+ *     state, synchronises the device, or changes the current device.
+ */
+#ifndef GLOWK_H_
+#define GLOWK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLOWK_OK 0
+#define GLOWK_EINVAL 1   /* bad shape / argument (reference: Python assert) */
+#define GLOWK_ECUDA 2    /* CUDA launch / runtime error */
+#define GLOWK_EUNSUP 3   /* valid request this build cannot serve */
+
+#define GLOWK_F32 0
+#define GLOWK_BF16 1
+
+/* GEMM epilogues (glowk_gemm) */
+#define GLOWK_EPI_STORE 0        /* out = acc                               */
+#define GLOWK_EPI_ACTNORM_RELU 1 /* out = relu((acc + bias[n]) * exp(f*logs[n])): Conv2d+ActNorm+ReLU, module.py:252-260,315 */
+#define GLOWK_EPI_ACTNORM 2      /* same without the ReLU (stand-alone Conv2d module) */
+#define GLOWK_EPI_ZEROS 3        /* out = (acc + bias[n]) * exp(f*logs[n]): Conv2dZeros, module.py:295-296 */
+#define GLOWK_EPI_RELU_BWD 4     /* g = acc*[y>0]; out = g*exp(f*logs[n]); dlogs[n] += f*sum g*y; dbias[n] += exp(f*logs[n])*sum g */
+
+const char* glowk_last_error(void);
+int glowk_version(void);
+/* 1 if the tcgen05/TMA (bf16) GEMM path is usable on the current device. */
+int glowk_has_tcgen05(void);
+
+/* ---- ActNorm: network/module.py:34-84,122-149 ------------------------------------------
+ * fwd: y = (x + bias[c]) * exp(f*logs[c]);  rev: y = x * exp(-f*logs[c]) - bias[c].
+ * x,y: [N,C,HW] (y may alias x).  The logdet term HW*sum(f*logs) is glowk_logdet_finish's. */
+int glowk_actnorm(const float* x, float* y, const float* bias, const float* logs,
+                  float logscale_factor, int64_t N, int64_t C, int64_t HW, int reverse, void* stream);
+
+/* Data-dependent init, module.py:86-120: bias = -mean_{n,p} x;
+ * logs = log(scale / (sqrt(mean (x+bias)^2) + 1e-6)) / f.  Strided so that both NCHW
+ * (sN=C*HW, sC=HW, sP=1) and pixel-major rows (sN=HW*ld, sC=1, sP=ld) inputs work.
+ * If `relu_after_prev` ... (not used).  Deterministic (one CTA per channel). */
+int glowk_actnorm_init(const void* x, int act_dtype, int64_t N, int64_t C, int64_t HW,
+                       int64_t sN, int64_t sC, int64_t sP, float scale, float logscale_factor,
+                       float* bias_out, float* logs_out, void* stream);
+
+/* ---- Invertible 1x1 conv weight prep: module.py:356-357,365 (torch.det / .inverse) -------
+ * LU with partial pivoting of the CxC matrix W (one CTA, fp64 internally):
+ * logabsdet_out[0] = log|det W|; winv_out (nullable) = W^-1. */
+int glowk_invconv_prepare(const float* w, int64_t C, float* logabsdet_out, float* winv_out, void* stream);
+
+/* LU parameterisation (north_star; the reference raises NotImplementedError, module.py:336-337):
+ * W = P . L . (U + diag(sign_s*exp(log_s))), L unit-lower (strict lower part of l), U strictly
+ * upper part of u.  w_out = W, winv_out (nullable) = W^-1 by two triangular solves,
+ * logabsdet_out[0] = sum(log_s). */
+int glowk_invconv_lu_assemble(const float* p, const float* l, const float* u, const float* sign_s,
+                              const float* log_s, int64_t C, float* w_out, float* winv_out,
+                              float* logabsdet_out, void* stream);
+
+/* ---- Fused ActNorm + channel mix: model.py:94-103 (fwd) / 142-152 (rev) ------------------
+ * fwd: z[n,o,p] = sum_i W[o,i] * ((x[n,i,p] + bias[i]) * exp(f*logs[i]))          (mix)
+ *      z[n,o,p] =               (x[n,idx[o],p] + bias[idx[o]]) * exp(f*logs[idx[o]]) (perm, bit-exact gather)
+ * rev: x[n,o,p] = (sum_i Winv[o,i] z[n,i,p]) * exp(-f*logs[o]) - bias[o]           (w = W^-1 / idx = inverse idx)
+ * Exactly one of w / idx is non-null.  bias/logs null => plain Invertible1x1Conv / Permutation2d. */
+int glowk_actnorm_mix(const float* x, float* z, const float* w, const int64_t* idx,
+                      const float* bias, const float* logs, float logscale_factor,
+                      int64_t N, int64_t C, int64_t HW, int reverse, void* stream);
+
+/* ---- Squeeze2d: module.py:551-591 (bit-exact index map) ---------------------------------
+ * fwd: y[n, c*f*f + fh*f + fw, i, j] = x[n, c, i*f+fh, j*f+fw];  x: [N,C,H,W]. reverse = unsqueeze
+ * with x: [N,C,H,W] -> y: [N, C/f^2, H*f, W*f].  sN = batch stride of x in elements (C*H*W when
+ * contiguous; larger for the channel-sliced view Split2d returns, module.py:111). */
+int glowk_squeeze2d(const float* x, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
+                    int64_t sN, int factor, int reverse, void* stream);
+
+/* ---- rows (pixel-major) <-> NCHW ---------------------------------------------------------
+ * im2col for a SAME-padded kxk conv (k = 1 or 3), module.py:209-212,252:
+ * dst[p][tap*Cin + ci] = src[n, c0+ci, y+ky-pad, x+kx-pad] (0 outside), columns >= k*k*Cin zeroed
+ * up to ld.  sN = batch stride of src in elements (>= (c0+Cin)*H*W).  flip=1 mirrors the taps (transposed conv, used by the backward pass). */
+int glowk_im2col(const float* src, int64_t N, int64_t sN, int64_t c0, int64_t Cin, int64_t H, int64_t W,
+                 int ksize, int flip, void* dst, int act_dtype, int64_t ld, void* stream);
+/* Same gather from a pixel-major fp32 source [P][ld_src] (channels c0..c0+Cin). */
+int glowk_im2col_rows(const float* src, int64_t ld_src, int64_t N, int64_t c0, int64_t Cin, int64_t H,
+                      int64_t W, int ksize, int flip, void* dst, int act_dtype, int64_t ld, void* stream);
+/* dst[n,c,p] = rows[(n*HW+p)*ld + c] for c < C (rows of type act_dtype). */
+int glowk_rows_to_nchw(const void* rows, int act_dtype, int64_t ld, float* dst, int64_t N, int64_t C,
+                       int64_t HW, void* stream);
+/* 3x3 tap gather-sum: dst[n,c0+c,y,x] (+)= sum_tap P[pix(n,y+ky-1,x+kx-1)][tap*C + c], the
+ * second half of a conv computed as nine pointwise GEMMs.  flip=1 mirrors taps. */
+int glowk_tapsum_to_nchw(const float* P, int64_t ldp, float* dst, int64_t N, int64_t Ctot, int64_t c0,
+                         int64_t C, int64_t H, int64_t W, int flip, int accumulate, void* stream);
+
+/* Conv weight packing, fp32 [O][I][k][k] (module.py nn.Conv2d layout) -> GEMM B operands:
+ *   layout 0: dst[o][tap*I + i]      ([O][ld], ld >= k*k*I)   forward, taps folded into K
+ *   layout 1: dst[tap*O + o][i]      ([rows][ld], ld >= I)    forward, taps folded into N
+ *   layout 2: dst[tap*I + i][o]      transpose of layout 0    (dgrad)
+ *   layout 3: dst[i][tap*O + o]      transpose of layout 1    (dgrad)
+ * Padding rows/cols are zeroed: dst has `rows` rows of `ld` elements. */
+int glowk_pack_conv_weight(const float* w, int64_t O, int64_t I, int ksize, int layout,
+                           void* dst, int act_dtype, int64_t rows, int64_t ld, void* stream);
+
+/* ---- GEMM: out[M][N] = epilogue(A[M][K] . B[N][K]^T) --------------------------------------
+ * The coupling network's convs (module.py:300-319) as pixel-major GEMMs.  act_dtype GLOWK_BF16
+ * runs the tcgen05/TMEM/TMA kernel (bf16 operands, fp32 accumulate); GLOWK_F32 runs the fp32
+ * CUDA-core kernel used for strict-parity runs.  A: [M][lda], B: [N][ldb] both K-contiguous.
+ * out_dtype selects the element type of out ([M][ldo]).  bias/logs: fp32 [N] epilogue vectors.
+ * EPI_RELU_BWD additionally reads y ([M][ldy], act_dtype) and accumulates dlogs/dbias (fp32 [N]). */
+int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype,
+               int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
+               float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
+               void* out, int out_dtype, int64_t ldo, void* stream);
+
+/* Weight-gradient GEMM: dW[Mo][No] (+)= A[P][Mo]^T . B[P][No]  (reduction over pixels, fp32 out,
+ * split over CTAs with atomic accumulation).  A: [P][lda], B: [P][ldb] of act_dtype. */
+int glowk_gemm_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype,
+                     int64_t P, int64_t Mo, int64_t No, float* dW, int64_t lddw, void* stream);
+
+/* ---- Coupling: model.py:105-115 (fwd) / 131-140 (rev) --------------------------------------
+ * h[n,co,y,x] = (u + bias3[co]) * exp(f*logs3[co]),  u = 3x3 tap gather-sum of P (ldp floats/row,
+ * column tap*Cout+co), i.e. Conv2dZeros (module.py:295-296).
+ * affine (Cout = C):  shift = h[2j], scale = sigmoid(h[2j+1] + 2);
+ *    fwd z2 = (z2 + shift)*scale, partial += sum log scale ; rev z2 = z2/scale - shift, partial -= ...
+ * additive (Cout = C/2): fwd z2 += h[j]; rev z2 -= h[j].
+ * z: [N,C,H,W], channels C/2.. are updated IN PLACE.  partials: [N][nblk] per-CTA sums of
+ * log(scale) for sample n (nblk = glowk_coupling_nblk(H*W)); summed by glowk_logdet_finish.
+ * h_save (nullable): [P][Cout] fp32 copy of h for the backward pass. */
+int64_t glowk_coupling_nblk(int64_t HW);
+int glowk_coupling(const float* P, int64_t ldp, const float* bias3, const float* logs3,
+                   float logscale_factor, float* z, float* partials, float* h_save,
+                   int64_t N, int64_t C, int64_t H, int64_t W, int affine, int reverse, void* stream);
+
+/* logdet_out[n] = logdet_in[n] + sign * ( HW * (sum_c f*logs[c] + logabsdet[0]) ) + sum_b partials[n][b]
+ * (module.py:77-82, 357-367; model.py:114,140).  logs/logabsdet/partials may each be null.
+ * `sign` = +1 forward, -1 reverse (partials already carry their own sign). */
+int glowk_logdet_finish(const float* logdet_in, float* logdet_out, const float* logs, int64_t C,
+                        float logscale_factor, const float* logabsdet, const float* partials,
+                        int64_t nblk, int64_t HW, float sign, int64_t N, void* stream);
+
+/* ---- Split2d / GaussianDiag: module.py:437-483, 511-536 -----------------------------------
+ * h: [P][ldh] fp32 rows holding Conv2dZeros(z1) (mean = h[2j], logs = h[2j+1], 'cross' split);
+ * x: [N,C,H,W]; z2 = x[:, C/2:].  out[n] = logdet_in[n] + sum_{j,p} -0.5(log2pi + 2 logs + (z2-mean)^2/exp(2 logs)).
+ * h == null => mean = logs = 0 over all C channels of x (the Glow top prior, model.py:435-438). */
+int glowk_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t N, int64_t C, int64_t HW,
+                        int64_t c0, int64_t Cz, const float* logdet_in, float* logdet_out, void* stream);
+/* Reverse: out[:, :C/2] = z1, out[:, C/2:] = mean + exp(logs) * eps   (eps already scaled by eps_std). */
+int glowk_split2d_sample(const float* h, int64_t ldh, const float* z1, const float* eps, float* out,
+                         int64_t N, int64_t Chalf, int64_t HW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOWK_H_ */

@@ -1,0 +1,24 @@
+"""Process-wide knobs of the engine (read at call time, never by the kernels)."""
+from . import _C
+
+# Arithmetic type of the coupling-network GEMM operands:
+#   "bf16": tcgen05/TMEM kernels, bf16 operands, fp32 accumulate (the production path);
+#   "fp32": CUDA-core fp32 kernels, used for the strict 1e-4 parity runs;
+#   "auto": bf16 whenever the layer shape fits the tensor-core tiling, else fp32.
+conv_dtype = "auto"
+
+
+def resolve_conv_dtype(hidden_channels, override=None):
+    mode = override or conv_dtype
+    if mode == "fp32":
+        return _C.F32
+    fits = hidden_channels % 64 == 0
+    if mode == "bf16":
+        if not fits:
+            raise ValueError("conv_dtype='bf16' needs hidden_channels %% 64 == 0 (got %d)" % hidden_channels)
+        if not _C.has_tcgen05():
+            raise _C.GlowkError("conv_dtype='bf16' needs an sm_100 device with the tcgen05 GEMM built")
+        return _C.BF16
+    if mode != "auto":
+        raise ValueError("conv_dtype must be 'auto', 'fp32' or 'bf16'")
+    return _C.BF16 if (fits and _C.has_tcgen05()) else _C.F32

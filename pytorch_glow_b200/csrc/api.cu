@@ -1,0 +1,75 @@
+// C-ABI plumbing: error reporting, device queries, GEMM dispatch.
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace glowk {
+
+static thread_local char g_err[512];
+
+char* last_error_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1, cached = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+}  // namespace glowk
+
+using namespace glowk;
+
+extern "C" const char* glowk_last_error(void) { return last_error_buf(); }
+extern "C" int glowk_version(void) { return 100; }
+extern "C" int glowk_has_tcgen05(void) { return tc_available() ? 1 : 0; }
+
+extern "C" int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype, int64_t M,
+                          int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
+                          float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
+                          void* out, int out_dtype, int64_t ldo, void* stream) {
+  if (M == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(A && B && out, "glowk_gemm: null pointer");
+  GLOWK_CHECK_ARG(M >= 0 && N > 0 && K > 0, "glowk_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  GLOWK_CHECK_ARG(lda >= K && ldb >= K && ldo >= N, "glowk_gemm: leading dimensions too small");
+  GLOWK_CHECK_ARG(out_dtype == GLOWK_F32 || out_dtype == GLOWK_BF16, "glowk_gemm: bad out_dtype");
+  if (epilogue != GLOWK_EPI_STORE) GLOWK_CHECK_ARG(logs, "glowk_gemm: epilogue %d needs logs", epilogue);
+  if (epilogue == GLOWK_EPI_ACTNORM_RELU || epilogue == GLOWK_EPI_ACTNORM || epilogue == GLOWK_EPI_ZEROS)
+    GLOWK_CHECK_ARG(bias, "glowk_gemm: epilogue %d needs bias", epilogue);
+  if (epilogue == GLOWK_EPI_RELU_BWD) GLOWK_CHECK_ARG(y && dlogs && dbias && ldy >= N, "glowk_gemm: RELU_BWD needs y, dlogs, dbias");
+  if (M == 0) return GLOWK_OK;
+  EpiParams ep;
+  ep.bias = bias; ep.logs = logs; ep.f = logscale_factor; ep.y = y; ep.ldy = ldy;
+  ep.y_bf16 = (act_dtype == GLOWK_BF16); ep.dlogs = dlogs; ep.dbias = dbias;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == GLOWK_F32)
+    return gemm_f32((const float*)A, lda, (const float*)B, ldb, M, N, K, epilogue, ep, out, out_dtype, ldo, st);
+  if (act_dtype == GLOWK_BF16)
+    return gemm_bf16_tc(A, lda, B, ldb, M, N, K, epilogue, ep, out, out_dtype, ldo, st);
+  return fail(GLOWK_EINVAL, "glowk_gemm: bad act_dtype %d", act_dtype);
+}
+
+extern "C" int glowk_gemm_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype, int64_t P,
+                                int64_t Mo, int64_t No, float* dW, int64_t lddw, void* stream) {
+  GLOWK_CHECK_ARG(A && B && dW, "glowk_gemm_wgrad: null pointer");
+  GLOWK_CHECK_ARG(P >= 0 && Mo > 0 && No > 0 && lda >= Mo && ldb >= No && lddw >= No, "glowk_gemm_wgrad: bad shape");
+  if (P == 0) return GLOWK_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == GLOWK_F32) return wgrad_simt(A, lda, B, ldb, act_dtype, P, Mo, No, dW, lddw, st);
+  if (act_dtype == GLOWK_BF16) return wgrad_bf16_tc(A, lda, B, ldb, P, Mo, No, dW, lddw, st);
+  return fail(GLOWK_EINVAL, "glowk_gemm_wgrad: bad act_dtype %d", act_dtype);
+}

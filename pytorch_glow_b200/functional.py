@@ -1,0 +1,245 @@
+"""Tensor-level wrappers of the glowk C ABI (one function per entry point).
+
+Everything here takes/returns torch CUDA tensors, allocates outputs with torch's
+caching allocator and launches on torch's current stream.  No arithmetic is done
+in Python/torch: the math lives in pytorch_glow_b200/csrc/*.cu.
+"""
+import torch
+
+from . import _C
+from ._C import F32, BF16, call, ptr, check_cuda
+
+TORCH_DTYPE = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _f32c(t):
+    assert t.dtype == torch.float32, "expected float32, got %s" % t.dtype
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------ ActNorm
+def actnorm(x, bias, logs, logscale_factor=3.0, reverse=False, out=None):
+    """y = (x+bias)*exp(f*logs) / inverse.  network/module.py:34-84."""
+    check_cuda(x, bias, logs)
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    y = torch.empty_like(x) if out is None else out
+    call("glowk_actnorm", ptr(x), ptr(y), ptr(bias), ptr(logs), float(logscale_factor), n, c, h * w,
+         int(bool(reverse)))
+    return y
+
+
+def actnorm_init_nchw(x, scale=1.0, logscale_factor=3.0):
+    """(bias, logs) [C] from a [N,C,H,W] fp32 batch.  network/module.py:86-120."""
+    check_cuda(x)
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    bias = torch.empty(c, device=x.device, dtype=torch.float32)
+    logs = torch.empty_like(bias)
+    call("glowk_actnorm_init", ptr(x), F32, n, c, h * w, c * h * w, h * w, 1, float(scale),
+         float(logscale_factor), ptr(bias), ptr(logs))
+    return bias, logs
+
+
+def actnorm_init_rows(rows, n_cols, scale=1.0, logscale_factor=3.0):
+    """Same statistics over a pixel-major fp32 matrix [P][ld] (columns 0..n_cols-1)."""
+    check_cuda(rows)
+    assert rows.dtype == torch.float32 and rows.dim() == 2 and rows.is_contiguous()
+    p, ld = rows.shape
+    bias = torch.empty(n_cols, device=rows.device, dtype=torch.float32)
+    logs = torch.empty_like(bias)
+    call("glowk_actnorm_init", ptr(rows), F32, 1, n_cols, p, 0, 1, ld, float(scale), float(logscale_factor),
+         ptr(bias), ptr(logs))
+    return bias, logs
+
+
+# ------------------------------------------------------------------ invertible 1x1 conv
+def invconv_prepare(weight, need_inverse):
+    """(log|det W| as a 1-element tensor, W^-1 or None).  network/module.py:357,365."""
+    check_cuda(weight)
+    w = _f32c(weight)
+    c = w.shape[0]
+    logabsdet = torch.empty(1, device=w.device, dtype=torch.float32)
+    winv = torch.empty_like(w) if need_inverse else None
+    call("glowk_invconv_prepare", ptr(w), c, ptr(logabsdet), ptr(winv))
+    return logabsdet, winv
+
+
+def invconv_lu_assemble(p, l, u, sign_s, log_s, need_inverse):
+    """W = P L (U + diag(sign_s exp(log_s))), optional W^-1, sum(log_s)."""
+    check_cuda(p, l, u, sign_s, log_s)
+    c = p.shape[0]
+    w = torch.empty(c, c, device=p.device, dtype=torch.float32)
+    winv = torch.empty_like(w) if need_inverse else None
+    logabsdet = torch.empty(1, device=p.device, dtype=torch.float32)
+    call("glowk_invconv_lu_assemble", ptr(_f32c(p)), ptr(_f32c(l)), ptr(_f32c(u)), ptr(_f32c(sign_s)),
+         ptr(_f32c(log_s)), c, ptr(w), ptr(winv), ptr(logabsdet))
+    return w, winv, logabsdet
+
+
+def actnorm_mix(x, weight=None, indices=None, bias=None, logs=None, logscale_factor=3.0, reverse=False):
+    """Fused ActNorm + 1x1 channel mix (or permutation gather).  model.py:94-103 / 142-152."""
+    check_cuda(x, weight, indices, bias, logs)
+    x = _f32c(x)
+    n, c, h, w = x.shape
+    z = torch.empty_like(x)
+    call("glowk_actnorm_mix", ptr(x), ptr(z), ptr(weight), ptr(indices), ptr(bias), ptr(logs),
+         float(logscale_factor), n, c, h * w, int(bool(reverse)))
+    return z
+
+
+# ------------------------------------------------------------------ squeeze
+def squeeze2d(x, factor=2, reverse=False):
+    """network/module.py:551-591 (bit-exact)."""
+    check_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 4
+    n, c, h, w = x.shape
+    if factor == 1:
+        return x
+    # accept a channel-sliced view (Split2d's z1) without a copy: only the batch stride may differ
+    if not (x.stride(3) == 1 and x.stride(2) == w and x.stride(1) == h * w):
+        x = x.contiguous()
+    sn = x.stride(0) if n > 1 else c * h * w
+    if not reverse:
+        if h % factor or w % factor:
+            raise ValueError("Squeeze2d: H, W = %d, %d not divisible by factor %d" % (h, w, factor))
+        y = torch.empty(n, c * factor * factor, h // factor, w // factor, device=x.device, dtype=x.dtype)
+    else:
+        if c < factor * factor or c % (factor * factor):
+            raise ValueError("Squeeze2d: C = %d not divisible by factor^2" % c)
+        y = torch.empty(n, c // (factor * factor), h * factor, w * factor, device=x.device, dtype=x.dtype)
+    call("glowk_squeeze2d", x.data_ptr(), ptr(y), n, c, h, w, sn, int(factor), int(bool(reverse)))
+    return y
+
+
+# ------------------------------------------------------------------ rows <-> NCHW, weight packing
+def im2col(src, c0, cin, ksize, dtype, ld, flip=False):
+    """rows[p][tap*cin+ci] from channels c0..c0+cin of an NCHW fp32 tensor (SAME zero padding)."""
+    check_cuda(src)
+    assert src.dtype == torch.float32 and src.dim() == 4
+    n, ctot, h, w = src.shape
+    if not (src.stride(3) == 1 and src.stride(2) == w and src.stride(1) == h * w):
+        src = src.contiguous()
+    sn = src.stride(0) if n > 1 else ctot * h * w
+    rows = torch.empty(n * h * w, ld, device=src.device, dtype=TORCH_DTYPE[dtype])
+    call("glowk_im2col", src.data_ptr(), n, sn, c0, cin, h, w, int(ksize), int(bool(flip)), ptr(rows), dtype, ld)
+    return rows
+
+
+def im2col_rows(src_rows, n, h, w, c0, cin, ksize, dtype, ld, flip=False):
+    check_cuda(src_rows)
+    assert src_rows.dtype == torch.float32 and src_rows.dim() == 2 and src_rows.is_contiguous()
+    rows = torch.empty(n * h * w, ld, device=src_rows.device, dtype=TORCH_DTYPE[dtype])
+    call("glowk_im2col_rows", ptr(src_rows), src_rows.shape[1], n, c0, cin, h, w, int(ksize), int(bool(flip)),
+         ptr(rows), dtype, ld)
+    return rows
+
+
+def rows_to_nchw(rows, n, c, h, w):
+    check_cuda(rows)
+    dt = BF16 if rows.dtype == torch.bfloat16 else F32
+    out = torch.empty(n, c, h, w, device=rows.device, dtype=torch.float32)
+    call("glowk_rows_to_nchw", ptr(rows), dt, rows.shape[1], ptr(out), n, c, h * w)
+    return out
+
+
+def tapsum_to_nchw(p_rows, dst, c0, c, flip=False, accumulate=False):
+    check_cuda(p_rows, dst)
+    n, ctot, h, w = dst.shape
+    assert dst.is_contiguous() and p_rows.dtype == torch.float32
+    call("glowk_tapsum_to_nchw", ptr(p_rows), p_rows.shape[1], ptr(dst), n, ctot, c0, c, h, w, int(bool(flip)),
+         int(bool(accumulate)))
+    return dst
+
+
+def pack_conv_weight(weight, layout, dtype, rows, ld):
+    """fp32 [O][I][k][k] -> GEMM B operand (see include/glowk.h for the four layouts)."""
+    check_cuda(weight)
+    w = _f32c(weight)
+    o, i, k, _ = w.shape
+    dst = torch.empty(rows, ld, device=w.device, dtype=TORCH_DTYPE[dtype])
+    call("glowk_pack_conv_weight", ptr(w), o, i, k, int(layout), ptr(dst), dtype, rows, ld)
+    return dst
+
+
+# ------------------------------------------------------------------ GEMMs
+def gemm(a, b, n, k, epilogue=_C.EPI_STORE, bias=None, logs=None, logscale_factor=3.0, y=None,
+         dlogs=None, dbias=None, out_dtype=F32, ldo=None, out=None):
+    """out[M][n] = epilogue(a[M][:k] . b[:n][:k]^T).  a, b: 2-D row-major, same dtype."""
+    check_cuda(a, b)
+    assert a.dim() == 2 and b.dim() == 2 and a.dtype == b.dtype
+    dt = BF16 if a.dtype == torch.bfloat16 else F32
+    m = a.shape[0]
+    ldo = n if ldo is None else ldo
+    if out is None:
+        out = torch.empty(m, ldo, device=a.device, dtype=TORCH_DTYPE[out_dtype])
+    call("glowk_gemm", ptr(a), a.shape[1], ptr(b), b.shape[1], dt, m, n, k, int(epilogue), ptr(bias), ptr(logs),
+         float(logscale_factor), ptr(y), 0 if y is None else y.shape[1], ptr(dlogs), ptr(dbias), ptr(out),
+         out_dtype, ldo)
+    return out
+
+
+def gemm_wgrad(a, b, mo, no, dw):
+    """dw[mo][no] += a[P][:mo]^T . b[P][:no]  (fp32 accumulate into dw)."""
+    check_cuda(a, b, dw)
+    assert a.dtype == b.dtype and dw.dtype == torch.float32 and dw.is_contiguous()
+    dt = BF16 if a.dtype == torch.bfloat16 else F32
+    call("glowk_gemm_wgrad", ptr(a), a.shape[1], ptr(b), b.shape[1], dt, a.shape[0], mo, no, ptr(dw),
+         dw.shape[-1] if dw.dim() == 2 else no)
+    return dw
+
+
+# ------------------------------------------------------------------ coupling / logdet / prior
+def coupling(p_rows, bias3, logs3, z, affine, reverse, logscale_factor=3.0, save_h=False):
+    """In-place coupling on z[:, C/2:] from the tap-GEMM output p_rows.  model.py:105-115 / 131-140.
+
+    Returns (partials [N][nblk] or None, h rows or None)."""
+    check_cuda(p_rows, bias3, logs3, z)
+    assert z.is_contiguous() and z.dtype == torch.float32 and p_rows.dtype == torch.float32
+    n, c, h, w = z.shape
+    cout = c if affine else c // 2
+    nblk = _C.coupling_nblk(h * w)
+    partials = torch.empty(n, nblk, device=z.device, dtype=torch.float32) if affine else None
+    hs = torch.empty(n * h * w, cout, device=z.device, dtype=torch.float32) if save_h else None
+    call("glowk_coupling", ptr(p_rows), p_rows.shape[1], ptr(bias3), ptr(logs3), float(logscale_factor), ptr(z),
+         ptr(partials), ptr(hs), n, c, h, w, int(bool(affine)), int(bool(reverse)))
+    return partials, hs
+
+
+def logdet_finish(logdet_in, n, hw, logs=None, logabsdet=None, partials=None, logscale_factor=3.0, sign=1.0,
+                  device=None):
+    """logdet_out[n] = logdet_in[n] + sign*HW*(sum f*logs + log|det W|) + sum_b partials[n][b]."""
+    dev = device if device is not None else (logdet_in.device if logdet_in is not None else logs.device)
+    out = torch.empty(n, device=dev, dtype=torch.float32)
+    c = 0 if logs is None else logs.numel()
+    nblk = 0 if partials is None else partials.shape[1]
+    call("glowk_logdet_finish", ptr(logdet_in), ptr(out), ptr(logs), c, float(logscale_factor), ptr(logabsdet),
+         ptr(partials), nblk, hw, float(sign), n)
+    return out
+
+
+def gaussian_logp(h_rows, x, c0, cz, logdet_in=None):
+    """logdet_in + sum_{c,p} log N(x[:, c0:c0+cz]; mean, exp(logs)) with (mean, logs) = cross-split of h_rows
+    (None => standard normal).  network/module.py:437-467."""
+    check_cuda(h_rows, x, logdet_in)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty(n, device=x.device, dtype=torch.float32)
+    call("glowk_gaussian_logp", ptr(h_rows), 0 if h_rows is None else h_rows.shape[1], ptr(x), n, c, h * w, c0, cz,
+         ptr(logdet_in), ptr(out))
+    return out
+
+
+def split2d_sample(h_rows, z1, eps):
+    """cat(z1, mean + exp(logs)*eps).  network/module.py:482-483, 532-536."""
+    check_cuda(h_rows, z1, eps)
+    z1 = _f32c(z1)
+    eps = _f32c(eps)
+    n, ch, h, w = z1.shape
+    out = torch.empty(n, 2 * ch, h, w, device=z1.device, dtype=torch.float32)
+    call("glowk_split2d_sample", ptr(h_rows), h_rows.shape[1], ptr(z1), ptr(eps), ptr(out), n, ch, h * w)
+    return out

@@ -1,0 +1,291 @@
+"""Host-side mirror of pytorch-glow's FlowStep / FlowModel / Glow (network/model.py).
+
+`FlowModel` is what BASELINE.json's north_star calls "FlowNet":
+``forward(x) -> (z, logdet)`` / ``reverse(z) -> x``.  Class names, constructor
+arguments, call conventions, ``output_shapes`` and ``state_dict()`` keys follow the
+reference; every flow layer executes as fused sm_100a kernels from libglowk.so.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _C, module, ops
+from . import functional as K
+from .module import _logdet_in, _logdet_out
+
+
+class FlowStep(nn.Module):
+    """One step of flow: ActNorm -> {1x1 conv | permutation} -> coupling (network/model.py:10-173)."""
+
+    flow_permutation_list = ['invconv', 'reverse', 'shuffle']
+    flow_coupling_list = ['additive', 'affine']
+
+    def __init__(self, in_channels, hidden_channels, permutation='invconv', coupling='additive',
+                 actnorm_scale=1., lu_decomposition=False):
+        super().__init__()
+        assert permutation in self.flow_permutation_list, 'Unsupported flow permutation: {}'.format(permutation)
+        assert coupling in self.flow_coupling_list, 'Unsupported flow coupling: {}'.format(coupling)
+        self.permutation = permutation
+        self.coupling = coupling
+        self.in_channels = in_channels
+        self.conv_dtype = None      # per-step override of config.conv_dtype ("fp32" | "bf16" | None)
+
+        self.actnorm = module.ActNorm(num_channels=in_channels, scale=actnorm_scale)
+        if permutation == 'invconv':
+            self.invconv = module.Invertible1x1Conv(num_channels=in_channels, lu_decomposition=lu_decomposition)
+        elif permutation == 'reverse':
+            self.reverse = module.Permutation2d(num_channels=in_channels, shuffle=False)
+        else:
+            self.shuffle = module.Permutation2d(num_channels=in_channels, shuffle=True)
+        if coupling == 'additive':
+            self.f = module.f(in_channels // 2, hidden_channels, in_channels // 2)
+        else:
+            self.f = module.f(in_channels // 2, hidden_channels, in_channels)
+
+    # -- helpers ---------------------------------------------------------------------------------
+    @property
+    def perm_module(self):
+        return None if self.permutation == 'invconv' else getattr(self, self.permutation)
+
+    def _mix_args(self, device, reverse):
+        """(weight, indices, log|det W| or None) for glowk_actnorm_mix in the given direction."""
+        if self.permutation == 'invconv':
+            w, winv, ld = self.invconv.prepared(need_inverse=reverse)
+            return (winv if reverse else w), None, ld
+        return None, self.perm_module.device_indices(device, reverse), None
+
+    # -- forward (model.py:82-117) ------------------------------------------------------------------
+    def normal_flow(self, x, logdet=None):
+        _C.check_cuda(x)
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import flowstep_autograd
+            return flowstep_autograd(self, x, logdet)
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        an = self.actnorm
+        if an.needs_init:
+            an.initialize_from_nchw(x)
+        wmat, idx, logabsdet = self._mix_args(x.device, False)
+        # (1) ActNorm + 1x1 mix / permutation, one pass over x
+        z = K.actnorm_mix(x, wmat, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
+                          an.logscale_factor, reverse=False)
+        # (2) coupling network on z1 as three GEMMs (conv3 left in tap form)
+        p3 = self.f.tap_rows(z, self.conv_dtype)
+        # (3) tap gather-sum + Conv2dZeros scale + coupling, in place on z2, per-CTA logdet partials
+        c3 = self.f[4]
+        affine = self.coupling == 'affine'
+        partials, _ = K.coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), z, affine, False,
+                                 c3.logscale_factor)
+        vec, scalar_like = _logdet_in(logdet, n, x.device)
+        if vec is None:
+            return z, None
+        if affine and vec.shape[0] == 1 and n != 1:
+            vec, scalar_like = vec.expand(n).contiguous(), False
+        out = K.logdet_finish(vec, vec.shape[0], h * w, logs=an.logs.detach().reshape(-1), logabsdet=logabsdet,
+                              partials=partials, logscale_factor=an.logscale_factor, sign=1.0)
+        return z, _logdet_out(out, scalar_like and not affine)
+
+    # -- reverse (model.py:119-154); like the reference it clobbers z2 of its input --------
+    def reverse_flow(self, x, logdet=None):
+        _C.check_cuda(x)
+        x = x.contiguous()
+        n, c, h, w = x.shape
+        an = self.actnorm
+        c3 = self.f[4]
+        affine = self.coupling == 'affine'
+        p3 = self.f.tap_rows(x, self.conv_dtype)
+        partials, _ = K.coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, affine, True,
+                                 c3.logscale_factor)
+        wmat, idx, logabsdet = self._mix_args(x.device, True)
+        out_x = K.actnorm_mix(x, wmat, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
+                              an.logscale_factor, reverse=True)
+        vec, scalar_like = _logdet_in(logdet, n, x.device)
+        if vec is None:
+            return out_x, None
+        if affine and vec.shape[0] == 1 and n != 1:
+            vec, scalar_like = vec.expand(n).contiguous(), False
+        out = K.logdet_finish(vec, vec.shape[0], h * w, logs=an.logs.detach().reshape(-1), logabsdet=logabsdet,
+                              partials=partials, logscale_factor=an.logscale_factor, sign=-1.0)
+        return out_x, _logdet_out(out, scalar_like and not affine)
+
+    def forward(self, x, logdet=None, reverse=False):
+        assert x.shape[1] % 2 == 0
+        if not reverse:
+            return self.normal_flow(x, logdet)
+        return self.reverse_flow(x, logdet)
+
+
+class FlowModel(nn.Module):
+    """Multi-scale flow (network/model.py:176-314): [Squeeze2d, FlowStep x K, Split2d] x (L-1),
+    Squeeze2d, FlowStep x K."""
+
+    def __init__(self, in_shape, hidden_channels, K, L, permutation='invconv', coupling='additive',
+                 actnorm_scale=1., lu_decomposition=False):
+        super().__init__()
+        self.K = K
+        self.L = L
+        assert len(in_shape) == 3
+        assert in_shape[2] == 1 or in_shape[2] == 3
+        nh, nw, nc = in_shape
+        self.layers = nn.ModuleList()
+        self.output_shapes = []
+        for i in range(L):
+            self.layers.append(module.Squeeze2d(factor=2))
+            nc, nh, nw = nc * 4, nh // 2, nw // 2
+            self.output_shapes.append([-1, nc, nh, nw])
+            for _ in range(K):
+                self.layers.append(FlowStep(in_channels=nc, hidden_channels=hidden_channels,
+                                            permutation=permutation, coupling=coupling,
+                                            actnorm_scale=actnorm_scale, lu_decomposition=lu_decomposition))
+                self.output_shapes.append([-1, nc, nh, nw])
+            if i < L - 1:
+                self.layers.append(module.Split2d(num_channels=nc))
+                nc = nc // 2
+                self.output_shapes.append([-1, nc, nh, nw])
+
+    def set_conv_dtype(self, mode):
+        """'fp32' | 'bf16' | None for every FlowStep (see config.conv_dtype)."""
+        for layer in self.layers:
+            if isinstance(layer, FlowStep):
+                layer.conv_dtype = mode
+
+    def adopt_permutations(self, other):
+        """Copy the (unsaved, numpy-RNG) channel permutations from another FlowModel-like object."""
+        for mine, theirs in zip(self.layers, other.layers):
+            if isinstance(mine, FlowStep) and mine.permutation != 'invconv':
+                mine.perm_module.set_indices(getattr(theirs, mine.permutation).indices)
+
+    def encode(self, z, logdet=0.):
+        for layer in self.layers:
+            z, logdet = layer(z, logdet, reverse=False)
+        return z, logdet
+
+    def decode(self, z, eps_std=None, eps_list=None):
+        """model.py:278-294.  `eps_list` optionally supplies the Split2d noise (deepest split first)."""
+        k = 0
+        for layer in reversed(self.layers):
+            if isinstance(layer, module.Split2d):
+                e = None if eps_list is None else eps_list[k]
+                k += 1
+                z, logdet = layer(z, logdet=0., reverse=True, eps_std=eps_std, eps=e)
+            else:
+                z, logdet = layer(z, logdet=0., reverse=True)
+        return z
+
+    def forward(self, z, logdet=0., eps_std=None, reverse=False):
+        if not reverse:
+            return self.encode(z, logdet)
+        return self.decode(z, eps_std)
+
+
+FlowNet = FlowModel   # the name BASELINE.json's north_star uses
+
+
+class Glow(nn.Module):
+    """network/model.py:317-550: dequantisation, objective, top prior, bits/dim; thin caller of FlowModel."""
+
+    bce_criterion = nn.BCEWithLogitsLoss()
+    ce_criterion = nn.CrossEntropyLoss()
+
+    def __init__(self, hps):
+        super().__init__()
+        self.hps = hps
+        self.flow = FlowModel(in_shape=hps.model.image_shape, hidden_channels=hps.model.hidden_channels,
+                              K=hps.model.K, L=hps.model.L, permutation=hps.ablation.flow_permutation,
+                              coupling=hps.ablation.flow_coupling, actnorm_scale=hps.model.actnorm_scale,
+                              lu_decomposition=hps.ablation.lu_decomposition)
+        if hps.ablation.learn_top:
+            nc = self.flow.output_shapes[-1][1]
+            self.learn_top = module.Conv2dZeros(in_channels=2 * nc, out_channels=2 * nc)
+        if hps.ablation.y_condition:
+            nc = self.flow.output_shapes[-1][1]
+            self.y_emb = module.LinearZeros(hps.dataset.num_classes, nc * 2)
+            self.classifier = module.LinearZeros(nc, hps.dataset.num_classes)
+        num_device = max(1, len(_graph_devices(hps)))
+        assert hps.optim.num_batch_train % num_device == 0
+        self.register_parameter('h_top', nn.Parameter(torch.zeros(
+            [hps.optim.num_batch_train // num_device, self.flow.output_shapes[-1][1] * 2,
+             self.flow.output_shapes[-1][2], self.flow.output_shapes[-1][3]])))
+
+    @property
+    def batch_h_top(self):
+        return self.h_top.shape[0]
+
+    @property
+    def _plain_top_prior(self):
+        return not (self.hps.ablation.learn_top or self.hps.ablation.y_condition)
+
+    def prior(self, y_onehot=None):
+        nc = self.h_top.shape[1]
+        h = self.h_top.detach().clone()
+        if self.hps.ablation.learn_top:
+            h = self.learn_top(h)
+        if self.hps.ablation.y_condition:
+            assert y_onehot is not None
+            h = h + self.y_emb(y_onehot).view(-1, nc, 1, 1)
+        return ops.split_channel(h, 'simple')
+
+    def normal_flow(self, x, y_onehot, noise=None):
+        """model.py:409-452.  `noise` (U(0, 1/n_bins), same shape as x) may be supplied for parity runs."""
+        n_bins = 2 ** self.hps.model.n_bits_x
+        if noise is None:
+            noise = torch.nn.init.uniform_(torch.empty(*x.shape, device=x.device), 0, 1. / n_bins)
+        z = x + noise
+        logdet_factor = x.shape[1] * ops.count_pixels(x)
+        objective = torch.full((x.shape[0],), float(-np.log(n_bins)) * logdet_factor, device=x.device,
+                               dtype=torch.float32)
+        z, objective = self.flow(z, logdet=objective, reverse=False)
+        if self._plain_top_prior and not (torch.is_grad_enabled() and z.requires_grad):
+            objective = K.gaussian_logp(None, z.contiguous(), 0, z.shape[1], objective)   # N(0,1) top prior
+        else:
+            mean, logs = self.prior(y_onehot)
+            objective = objective + module.GaussianDiag.logp(mean, logs, z)
+        if self.hps.ablation.y_condition and self.hps.model.weight_y > 0:
+            y_logits = self.classifier(ops.reduce_mean(z, dim=[2, 3]))
+        else:
+            y_logits = None
+        nll = (-objective) / float(np.log(2.) * logdet_factor)
+        return z, nll, y_logits
+
+    def reverse_flow(self, z, y_onehot, eps_std=None):
+        with torch.no_grad():
+            mean, logs = self.prior(y_onehot)
+            if z is None:
+                z = module.GaussianDiag.sample(mean, logs, eps_std)
+            return self.flow(z, eps_std=eps_std, reverse=True)
+
+    def forward(self, x=None, y_onehot=None, z=None, eps_std=None, reverse=False):
+        if not reverse:
+            return self.normal_flow(x, y_onehot)
+        return self.reverse_flow(z, y_onehot, eps_std)
+
+    @staticmethod
+    def generative_loss(nll):
+        return torch.mean(nll)
+
+    @staticmethod
+    def single_class_loss(y_logits, y):
+        if y_logits is None:
+            return 0
+        return Glow.ce_criterion(y_logits, y.long())
+
+    @staticmethod
+    def multi_class_loss(y_logits, y_onehot):
+        if y_logits is None:
+            return 0
+        return Glow.bce_criterion(y_logits, y_onehot.float())
+
+    def set_actnorm_inited(self, inited=True):
+        for name, m in self.named_modules():
+            if m.__class__.__name__.find("ActNorm") >= 0:
+                m.bias_inited = inited
+                m.logs_inited = inited
+
+
+def _graph_devices(hps):
+    """Number of model replicas the profile asks for (reference: misc/util.py:34-75 get_devices).
+    One process per GPU here, so a multi-device list still means "global batch / len(list)" per rank."""
+    devs = list(getattr(getattr(hps, 'device', None), 'graph', None) or ['cuda:0'])
+    if any('cpu' in str(d) for d in devs):
+        return ['cpu']
+    return devs

@@ -1,0 +1,90 @@
+"""Shared helpers for the GPU parity tests and __graft_entry__.smoke()."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import glow_oracle as O  # noqa: E402  (checker only)
+import pytorch_glow_b200 as G  # noqa: E402
+from pytorch_glow_b200.hps import make_hps  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def sd_from(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(np.array(z[k])) for k in z.files if k.startswith(prefix)}
+
+
+def perms_from(z, prefix):
+    out = {}
+    for k in z.files:
+        if k.startswith(prefix) and k.endswith("/indices"):
+            i = int(k[len(prefix):].split("/")[0])
+            out[i] = (np.array(z[k]), np.array(z[k[:-len("indices")] + "indices_inverse"]))
+    return out
+
+
+def adopt(model, sd, perms=None, strict=True):
+    """Load a reference state_dict (+ the unsaved permutation indices) into a pytorch_glow_b200 module."""
+    model.load_state_dict(sd, strict=strict)
+    for m in model.modules():
+        if isinstance(m, G.ActNorm):
+            m.bias_inited = m.logs_inited = True
+    if perms:
+        flow = model.flow if hasattr(model, "flow") else model
+        for i, (idx, _) in perms.items():
+            flow.layers[i].perm_module.set_indices(idx)
+    return model
+
+
+def randomize_(sd, seed, coupling_std=0.05):
+    """Same idea as tests/golden/make_golden.py: make zero-initialised tensors non-trivial."""
+    g = torch.Generator().manual_seed(seed)
+    for k, v in sd.items():
+        if k == "h_top":
+            continue
+        if ".f.4." in k or "conv2d_zeros" in k:
+            std = 0.1 if k.endswith("logs") else coupling_std
+            v.copy_(torch.randn(v.shape, generator=g) * std)
+        elif "actnorm" in k:
+            std = 0.1 if k.endswith("logs") else 0.2
+            v.copy_(torch.randn(v.shape, generator=g) * std)
+        elif k.endswith("invconv.weight"):
+            v.add_(0.05 * torch.randn(v.shape, generator=g))
+    return sd
+
+
+def tiny_glow_parity(device="cuda:0", conv_dtype="fp32"):
+    """Glow (16x16x3, K=2, L=2, hidden 16) bits/dim + sampling vs the golden fixture. Returns rel errs."""
+    z = load_golden("glow.npz")
+    tag = "invconv_affine/"
+    hps = make_hps((16, 16, 3), K=2, L=2, hidden_channels=16, coupling="affine", permutation="invconv", batch=4)
+    np.random.seed(0)
+    glow = G.Glow(hps)
+    adopt(glow, sd_from(z, tag + "sd/"))
+    glow = glow.to(device).eval()
+    glow.flow.set_conv_dtype(conv_dtype)
+    x = torch.from_numpy(z[tag + "x"]).to(device)
+    noise = torch.from_numpy(z[tag + "noise"]).to(device)
+    with torch.no_grad():
+        zz, nll, _ = glow.normal_flow(x, None, noise=noise)
+        top = torch.from_numpy(z[tag + "sample/eps/0"]).to(device)
+        eps = [torch.from_numpy(z[tag + "sample/eps/1"]).to(device)]
+        xs = glow.flow.decode(top, eps_list=eps)
+    torch.cuda.synchronize()
+    return (rel(zz, z[tag + "z"]), rel(nll, z[tag + "nll"]), rel(xs, z[tag + "sample/x"]))

@@ -1,0 +1,276 @@
+"""GPU parity, model level: FlowStep / FlowModel / Glow of pytorch_glow_b200 (CUDA, through the C ABI)
+against the committed golden fixtures of the reference and against the CPU oracle on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, rel_err
+from oracle import glow_oracle as O
+import pytorch_glow_b200 as G
+from pytorch_glow_b200 import _C
+from pytorch_glow_b200.hps import make_hps
+from parity_util import adopt, randomize_, tiny_glow_parity, rel
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+PERMS = ("invconv", "reverse", "shuffle")
+COUPS = ("additive", "affine")
+FP32_TOL = 1e-4          # north_star: z, logdet, bits/dim within 1e-4 relative in fp32
+BF16_TOL = 3e-2          # stated looser bound for bf16 coupling convs
+
+
+def cu(t):
+    return t.to(DEV)
+
+
+def build_step(G_, tag, perm, coup, c=8, hidden=16):
+    np.random.seed(0)
+    fs = G.FlowStep(c, hidden, permutation=perm, coupling=coup)
+    adopt(fs, G_.sd(tag + "sd/"))
+    if perm != "invconv":
+        fs.perm_module.set_indices(G_.np(tag + "indices"))
+    fs.conv_dtype = "fp32"
+    return fs.to(DEV).eval()
+
+
+# ---------------------------------------------------------------- FlowStep vs reference fixtures
+@pytest.mark.parametrize("perm", PERMS)
+@pytest.mark.parametrize("coup", COUPS)
+def test_flowstep_golden(golden_flowstep, perm, coup):
+    G_ = golden_flowstep
+    tag = "%s_%s/" % (perm, coup)
+    fs = build_step(G_, tag, perm, coup)
+    with torch.no_grad():
+        z, ld = fs(cu(G_.t(tag + "x")), cu(G_.t(tag + "logdet_in")), reverse=False)
+        assert rel_err(z, G_.t(tag + "z")) < FP32_TOL
+        assert rel_err(ld, G_.t(tag + "logdet")) < FP32_TOL
+        xr, ldr = fs(cu(G_.t(tag + "z")), cu(G_.t(tag + "logdet")), reverse=True)
+        assert rel_err(xr, G_.t(tag + "x_rev")) < FP32_TOL
+        assert rel_err(ldr, G_.t(tag + "logdet_rev")) < FP32_TOL
+        # reference test/test_model.py:12-32: rev(fwd(x)) == x, logdet passed as python 0
+        y, det = fs(cu(G_.t(tag + "x")), 0, reverse=False)
+        x2, _ = fs(y, det, reverse=True)
+        assert float((x2.cpu() - G_.t(tag + "x")).abs().max()) < 1e-5
+        # logdet=None propagates as None (module.py:77,361)
+        _, none = fs(cu(G_.t(tag + "x")), None)
+        assert none is None
+
+
+def test_flowstep_scalar_logdet_semantics(golden_flowstep):
+    G_ = golden_flowstep
+    fs = build_step(G_, "reverse_additive/", "reverse", "additive")
+    with torch.no_grad():
+        _, ld = fs(cu(G_.t("reverse_additive/x")), 0.)
+    assert ld.dim() == 0          # additive coupling keeps a sample-independent (0-dim) logdet
+    fs = build_step(G_, "invconv_affine/", "invconv", "affine")
+    with torch.no_grad():
+        _, ld = fs(cu(G_.t("invconv_affine/x")), 0.)
+    assert tuple(ld.shape) == (2,)
+
+
+# ---------------------------------------------------------------- FlowModel vs reference fixtures
+@pytest.mark.parametrize("perm,coup", [("invconv", "affine"), ("shuffle", "additive"), ("reverse", "affine")])
+def test_flowmodel_golden(golden_flowmodel, perm, coup):
+    G_ = golden_flowmodel
+    tag = "%s_%s/" % (perm, coup)
+    np.random.seed(0)
+    fm = G.FlowModel((16, 16, 3), 16, K=2, L=3, permutation=perm, coupling=coup)
+    sd = {k[len("flow."):]: v for k, v in G_.sd(tag + "sd/").items()}
+    adopt(fm, sd, G_.perms(tag + "perm/"))
+    fm.set_conv_dtype("fp32")
+    fm = fm.to(DEV).eval()
+    assert np.array_equal(np.asarray(fm.output_shapes), G_.np(tag + "output_shapes"))
+    with torch.no_grad():
+        z, ld = fm(cu(G_.t(tag + "x")), cu(G_.t(tag + "logdet_in")), reverse=False)
+        assert tuple(z.shape) == (2, 48, 2, 2)           # test/test_model.py:56
+        assert rel_err(z, G_.t(tag + "z")) < FP32_TOL
+        assert rel_err(ld, G_.t(tag + "logdet")) < FP32_TOL
+        eps = [cu(G_.t(tag + "eps/%d" % k)) for k in range(2)]
+        xr = fm.decode(cu(G_.t(tag + "z")), eps_list=eps)
+        assert rel_err(xr, G_.t(tag + "x_rev")) < FP32_TOL
+        # API shape check of the reference's own test: reverse(z, det) returns a tensor of x's shape
+        y, det = fm(cu(G_.t(tag + "x")), 0, reverse=False)
+        x_ = fm(y, det, reverse=True)
+        assert tuple(x_.shape) == (2, 3, 16, 16)
+
+
+# ---------------------------------------------------------------- Glow: bits/dim, sampling, init pass
+def test_glow_bits_per_dim_and_sampling_golden():
+    ez, enll, exs = tiny_glow_parity(DEV, "fp32")
+    assert ez < FP32_TOL and enll < FP32_TOL and exs < FP32_TOL
+
+
+@pytest.mark.parametrize("perm,coup", [("invconv", "affine"), ("reverse", "additive")])
+def test_glow_actnorm_init_pass(golden_glow, perm, coup):
+    """First training-mode call performs the layer-by-layer data-dependent init (trainer.py:112-115)."""
+    G_ = golden_glow
+    tag = "%s_%s/" % (perm, coup)
+    hps = make_hps((16, 16, 3), K=2, L=2, hidden_channels=16, coupling=coup, permutation=perm, batch=4)
+    np.random.seed(0)
+    glow = G.Glow(hps)
+    sd = G_.sd(tag + "init/sd/")
+    # start from the reference's *un-initialised* weights: same conv / invconv weights, zero actnorms
+    for k in sd:
+        if "actnorm" in k:
+            sd[k] = torch.zeros_like(sd[k])
+    glow.load_state_dict(sd)
+    for i, (idx, _) in G_.perms(tag + "perm/").items():
+        glow.flow.layers[i].perm_module.set_indices(idx)
+    glow.flow.set_conv_dtype("fp32")
+    glow = glow.to(DEV).train()
+    with torch.no_grad():
+        _, nll, _ = glow.normal_flow(cu(G_.t(tag + "x")), None, noise=cu(G_.t(tag + "init/noise")))
+    ref_sd = G_.sd(tag + "init/sd/")
+    got = glow.state_dict()
+    for k, v in ref_sd.items():
+        if "actnorm" in k:
+            assert_close(got[k], v, 2e-4, 2e-4, k)
+    assert rel_err(nll, G_.t(tag + "init/nll")) < 2e-4
+    assert all(m.bias_inited and m.logs_inited for m in glow.modules() if isinstance(m, G.ActNorm))
+
+
+# ---------------------------------------------------------------- oracle comparisons at BASELINE channel widths
+def _random_step(c, hidden, perm, coup, seed):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    fs = G.FlowStep(c, hidden, permutation=perm, coupling=coup)
+    sd = randomize_({k: v.clone() for k, v in fs.state_dict().items()}, seed + 1)
+    adopt(fs, sd)
+    return fs, sd
+
+
+@pytest.mark.parametrize("c,h,w", [(12, 32, 32), (24, 16, 16), (48, 8, 8), (48, 4, 4)])
+@pytest.mark.parametrize("coup", COUPS)
+def test_flowstep_vs_oracle_fp32(c, h, w, coup):
+    fs, sd = _random_step(c, 32, "invconv", coup, 3)
+    fs.conv_dtype = "fp32"
+    fs = fs.to(DEV).eval()
+    x = torch.randn(3, c, h, w, generator=torch.Generator().manual_seed(9))
+    ld0 = torch.randn(3, generator=torch.Generator().manual_seed(10))
+    z_ref, ld_ref = O.flowstep(x, ld0, sd, "", "invconv", coup)
+    with torch.no_grad():
+        z, ld = fs(cu(x), cu(ld0))
+        assert rel_err(z, z_ref) < FP32_TOL and rel_err(ld, ld_ref) < FP32_TOL
+        xr, ldr = fs(z.clone(), ld, reverse=True)
+        assert rel_err(xr, x) < FP32_TOL and rel_err(ldr, ld0) < 1e-3
+
+
+@pytest.mark.parametrize("c,h,w,hidden", [(12, 32, 32, 512), (24, 16, 16, 512), (48, 8, 8, 512), (12, 16, 16, 64), (48, 4, 4, 128)])
+@pytest.mark.parametrize("coup", COUPS)
+def test_flowstep_vs_oracle_bf16(c, h, w, hidden, coup):
+    """tcgen05 path (bf16 operands, fp32 accumulate) against the fp32 oracle: looser, stated bound."""
+    fs, sd = _random_step(c, hidden, "invconv", coup, 4)
+    fs.conv_dtype = "bf16"
+    fs = fs.to(DEV).eval()
+    x = torch.randn(4, c, h, w, generator=torch.Generator().manual_seed(11))
+    ld0 = torch.zeros(4)
+    z_ref, ld_ref = O.flowstep(x, ld0, sd, "", "invconv", coup)
+    with torch.no_grad():
+        z, ld = fs(cu(x), cu(ld0))
+        ez, el = rel_err(z, z_ref), rel_err(ld, ld_ref)
+        print("bf16 step c=%d hid=%d %s: rel err z %.2e logdet %.2e" % (c, hidden, coup, ez, el))
+        assert ez < BF16_TOL and el < BF16_TOL
+        # invertibility does not depend on the conv precision: both directions compute the same h
+        xr, _ = fs(z.clone(), ld, reverse=True)
+        assert rel_err(xr, x) < FP32_TOL
+
+
+def test_flowmodel_full_size_properties():
+    """CelebA-64 shape (K reduced to 4 for test time), bf16 path: shapes, finite outputs, L=1 round trip,
+    and per-layer invertibility on the full-width hidden layer."""
+    np.random.seed(1)
+    torch.manual_seed(1)
+    fm = G.FlowModel((64, 64, 3), 512, K=4, L=3, permutation="invconv", coupling="affine")
+    sd = randomize_({k: v.clone() for k, v in fm.state_dict().items()}, 5, coupling_std=0.01)
+    adopt(fm, sd)
+    fm = fm.to(DEV).eval()
+    x = torch.rand(8, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        z, ld = fm(cu(x), torch.zeros(8, device=DEV))
+        assert tuple(z.shape) == (8, 48, 8, 8) and bool(torch.isfinite(z).all()) and bool(torch.isfinite(ld).all())
+        # fp32 oracle on 2 samples (CPU, seconds)
+        z_ref, ld_ref = O.flow_encode(x[:2], torch.zeros(2), sd, (64, 64, 3), 4, 3, "invconv", "affine", prefix="")
+        ez, el = rel_err(z[:2], z_ref), rel_err(ld[:2], ld_ref)
+        print("full-size bf16 encode: rel err z %.2e logdet %.2e" % (ez, el))
+        assert ez < 5e-2 and el < BF16_TOL
+        h = fm.layers[0](cu(x))[0]
+        for layer in list(fm.layers)[1:5]:
+            y, _ = layer(h, None)
+            back, _ = layer(y.clone(), None, reverse=True)
+            assert rel_err(back, h) < FP32_TOL
+            h = y
+    np.random.seed(1)
+    fm1 = G.FlowModel((32, 32, 3), 64, K=4, L=1, permutation="invconv", coupling="affine")
+    adopt(fm1, randomize_({k: v.clone() for k, v in fm1.state_dict().items()}, 6))
+    fm1 = fm1.to(DEV).eval()
+    xs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        z, ld = fm1(cu(xs), 0.)
+        xr = fm1(z, reverse=True)
+    assert float((xr.cpu() - xs).abs().max()) < 1e-4        # 6.6e-7 for L=1 in the reference
+
+
+def test_standalone_modules_match_oracle(golden_layers):
+    G_ = golden_layers
+    # CouplingNet == f() (module.py:300-319)
+    net = G.f(4, 16, 8)
+    adopt(net, G_.sd("f/sd/"))
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        y = net(cu(G_.t("f/x")), conv_dtype="fp32")
+        assert rel_err(y, G_.t("f/y")) < FP32_TOL
+        c1 = net[0](cu(G_.t("f/x")), conv_dtype="fp32")
+        assert rel_err(c1, G_.t("f/conv1")) < FP32_TOL
+    # Split2d (module.py:486-536)
+    sp = G.Split2d(8)
+    adopt(sp, G_.sd("split/sd/"))
+    sp = sp.to(DEV).eval()
+    with torch.no_grad():
+        z1, ld = sp(cu(G_.t("split/x")), cu(G_.t("split/logdet_in")))
+        assert torch.equal(z1.cpu(), G_.t("split/z1"))
+        assert rel_err(ld, G_.t("split/logdet")) < FP32_TOL
+        xr, _ = sp(cu(G_.t("split/z1")), 0., reverse=True, eps=cu(G_.t("split/eps")))
+        assert rel_err(xr, G_.t("split/x_rev")) < FP32_TOL
+    # ActNorm incl. data-dependent init (module.py:86-149) and the known-answer vector of SURVEY 8(c)
+    an = G.ActNorm(4, scale=1.3).to(DEV).train()
+    with torch.no_grad():
+        y, ld = an(cu(G_.t("actnorm/x")), logdet=torch.zeros(3, device=DEV))
+    assert_close(an.bias, G_.t("actnorm/bias"), 1e-5, 1e-6)
+    assert_close(an.logs, G_.t("actnorm/logs"), 1e-5, 1e-6)
+    assert rel_err(y, G_.t("actnorm/y")) < 1e-5 and rel_err(ld, G_.t("actnorm/logdet")) < 1e-5
+    an2 = G.ActNorm(2).to(DEV).eval()
+    with torch.no_grad():
+        y2, _ = an2(cu(torch.tensor([[[[1., 2.], [3., 4.]], [[0., 0.], [2., 2.]]]])))
+    assert not an2.bias_inited and torch.equal(y2.cpu().flatten(), torch.tensor([1., 2., 3., 4., 0., 0., 2., 2.]))
+    # Invertible1x1Conv + Permutation2d (module.py:322-397)
+    np.random.seed(0)
+    ic = G.Invertible1x1Conv(6)
+    ic.weight.data.copy_(G_.t("invconv/weight"))
+    ic = ic.to(DEV)
+    with torch.no_grad():
+        y, ld = ic(cu(G_.t("invconv/x")), cu(G_.t("invconv/logdet_in")))
+        assert rel_err(y, G_.t("invconv/y")) < FP32_TOL and rel_err(ld, G_.t("invconv/logdet")) < FP32_TOL
+        xr, ldr = ic(y, ld, reverse=True)
+        assert rel_err(xr, G_.t("invconv/x_rev")) < FP32_TOL and rel_err(ldr, G_.t("invconv/logdet_rev")) < 1e-3
+    np.random.seed(0)
+    pm = G.Permutation2d(6, shuffle=True)
+    assert pm.indices.tolist() == [0, 3, 4, 2, 5, 1] and pm.indices_inverse.tolist() == [0, 5, 3, 1, 2, 4]
+    with torch.no_grad():
+        assert torch.equal(pm(cu(G_.t("perm/c6_seed0/x"))).cpu(), G_.t("perm/c6_seed0/y"))
+
+
+def test_lu_invconv_matches_dense(golden_layers):
+    """LU parameterisation (unpinned by the reference, F2): same z / logdet as the dense layer it was built from."""
+    G_ = golden_layers
+    np.random.seed(0)
+    dense = G.Invertible1x1Conv(6)
+    dense.weight.data.copy_(G_.t("invconv/weight"))
+    lu = G.Invertible1x1Conv(6, lu_decomposition=True)
+    lu.load_state_dict({"weight": G_.t("invconv/weight")})      # import a dense reference snapshot
+    dense, lu = dense.to(DEV), lu.to(DEV)
+    with torch.no_grad():
+        x, ld0 = cu(G_.t("invconv/x")), cu(G_.t("invconv/logdet_in"))
+        y, ld = lu(x, ld0)
+        assert rel_err(y, G_.t("invconv/y")) < FP32_TOL and rel_err(ld, G_.t("invconv/logdet")) < FP32_TOL
+        xr, ldr = lu(y, ld, reverse=True)
+        assert rel_err(xr, G_.t("invconv/x_rev")) < FP32_TOL
