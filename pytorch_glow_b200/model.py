@@ -146,7 +146,7 @@ class FlowModel(nn.Module):
     def set_conv_dtype(self, mode):
         """'fp32' | 'bf16' | None for every FlowStep (see config.conv_dtype)."""
         for layer in self.layers:
-            if isinstance(layer, FlowStep):
+            if isinstance(layer, (FlowStep, module.Split2d)):
                 layer.conv_dtype = mode
 
     def adopt_permutations(self, other):

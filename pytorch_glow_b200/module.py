@@ -474,10 +474,11 @@ class Split2d(nn.Module):
         super().__init__()
         self.num_channels = num_channels
         self.conv2d_zeros = Conv2dZeros(num_channels // 2, num_channels)
+        self.conv_dtype = None      # override of config.conv_dtype ("fp32" | "bf16" | None)
 
     def prior_rows(self, x, conv_dtype=None):
         """h rows [P][C] fp32: Conv2dZeros(z1) with (mean, logs) interleaved ('cross' split)."""
-        return self.conv2d_zeros.forward_rows(x, 0, self.num_channels // 2, conv_dtype)
+        return self.conv2d_zeros.forward_rows(x, 0, self.num_channels // 2, conv_dtype or self.conv_dtype)
 
     def prior(self, z):
         h = self.conv2d_zeros(z)

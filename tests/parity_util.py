@@ -58,7 +58,7 @@ def randomize_(sd, seed, coupling_std=0.05):
     for k, v in sd.items():
         if k == "h_top":
             continue
-        if ".f.4." in k or "conv2d_zeros" in k:
+        if ".f.4." in k or k.startswith("f.4.") or "conv2d_zeros" in k:
             std = 0.1 if k.endswith("logs") else coupling_std
             v.copy_(torch.randn(v.shape, generator=g) * std)
         elif "actnorm" in k:

@@ -16,7 +16,7 @@ DEV = "cuda:0"
 PERMS = ("invconv", "reverse", "shuffle")
 COUPS = ("additive", "affine")
 FP32_TOL = 1e-4          # north_star: z, logdet, bits/dim within 1e-4 relative in fp32
-BF16_TOL = 3e-2          # stated looser bound for bf16 coupling convs
+BF16_TOL = 1e-2          # stated looser bound for bf16 coupling convs (measured 3-5e-3)
 
 
 def cu(t):
@@ -192,22 +192,29 @@ def test_flowmodel_full_size_properties():
         z_ref, ld_ref = O.flow_encode(x[:2], torch.zeros(2), sd, (64, 64, 3), 4, 3, "invconv", "affine", prefix="")
         ez, el = rel_err(z[:2], z_ref), rel_err(ld[:2], ld_ref)
         print("full-size bf16 encode: rel err z %.2e logdet %.2e" % (ez, el))
-        assert ez < 5e-2 and el < BF16_TOL
+        assert ez < BF16_TOL and el < BF16_TOL
         h = fm.layers[0](cu(x))[0]
         for layer in list(fm.layers)[1:5]:
             y, _ = layer(h, None)
             back, _ = layer(y.clone(), None, reverse=True)
             assert rel_err(back, h) < FP32_TOL
             h = y
-    np.random.seed(1)
-    fm1 = G.FlowModel((32, 32, 3), 64, K=4, L=1, permutation="invconv", coupling="affine")
-    adopt(fm1, randomize_({k: v.clone() for k, v in fm1.state_dict().items()}, 6))
-    fm1 = fm1.to(DEV).eval()
-    xs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(3))
-    with torch.no_grad():
-        z, ld = fm1(cu(xs), 0.)
-        xr = fm1(z, reverse=True)
-    assert float((xr.cpu() - xs).abs().max()) < 1e-4        # 6.6e-7 for L=1 in the reference
+    # L=1 round trip (6.6e-7 in the reference).  fp32 convs: 1e-4 bound.  bf16 convs: a 1-ulp
+    # difference in the reconstructed z1 can flip a bf16 rounding of the conv input, so h differs at the
+    # 2^-8 level between the two directions; stated bound 1e-2 on inputs in [0, 1).
+    for mode, bound in (("fp32", 1e-4), ("bf16", 1e-2)):
+        np.random.seed(1)
+        fm1 = G.FlowModel((32, 32, 3), 64, K=4, L=1, permutation="invconv", coupling="affine")
+        adopt(fm1, randomize_({k: v.clone() for k, v in fm1.state_dict().items()}, 6))
+        fm1.set_conv_dtype(mode)
+        fm1 = fm1.to(DEV).eval()
+        xs = torch.rand(4, 3, 32, 32, generator=torch.Generator().manual_seed(3))
+        with torch.no_grad():
+            z, ld = fm1(cu(xs), 0.)
+            xr = fm1(z, reverse=True)
+        err = float((xr.cpu() - xs).abs().max())
+        print("L=1 round trip (%s convs): max abs err %.2e" % (mode, err))
+        assert err < bound
 
 
 def test_standalone_modules_match_oracle(golden_layers):
@@ -225,6 +232,7 @@ def test_standalone_modules_match_oracle(golden_layers):
     sp = G.Split2d(8)
     adopt(sp, G_.sd("split/sd/"))
     sp = sp.to(DEV).eval()
+    sp.conv_dtype = "fp32"
     with torch.no_grad():
         z1, ld = sp(cu(G_.t("split/x")), cu(G_.t("split/logdet_in")))
         assert torch.equal(z1.cpu(), G_.t("split/z1"))
