@@ -163,6 +163,51 @@ int glowk_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t N, 
 int glowk_split2d_sample(const float* h, int64_t ldh, const float* z1, const float* eps, float* out,
                          int64_t N, int64_t Chalf, int64_t HW, void* stream);
 
+/* ================================ backward (training) =====================================
+ * The reference trains through torch autograd over the ATen ops of the lines cited above
+ * (network/trainer.py:138-140 loss.backward()).  These are the analytic adjoints of the forward
+ * kernels; parameter gradients are ACCUMULATED (atomically) into the given fp32 buffers. */
+
+/* Adjoint of glowk_coupling (+ the Conv2dZeros scale): y = step output, hrows = h saved by the forward
+ * ([P][Cout]), dy = grad wrt y, dld = grad wrt this step's per-sample logdet ([N], nullable).
+ * Writes dz [N,C,H,W] (dz1 = dy1; the conv dgrad is added by glowk_tapsum_to_nchw) and du rows
+ * [P][Cout] = grad wrt the tap-summed conv output; accumulates dlogs3/dbias3 [Cout]. */
+int glowk_coupling_bwd(const float* y, const float* hrows, const float* dy, const float* dld,
+                       const float* logs3, float logscale_factor, float* dz, float* du, float* dlogs3,
+                       float* dbias3, int64_t N, int64_t C, int64_t H, int64_t W, int affine, void* stream);
+
+/* Adjoint of Split2d forward (module.py:526-530): dz1 = grad wrt the returned z1 ([N,C/2,H,W], batch
+ * stride dz1_sN; nullable), dld = grad wrt logdet [N].  Writes dx [N,C,H,W] and du rows [P][ldu]. */
+int glowk_split2d_bwd(const float* x, const float* hrows, int64_t ldh, const float* dz1, int64_t dz1_sN,
+                      const float* dld, const float* logs_p, float logscale_factor, float* dx, float* du,
+                      int64_t ldu, float* dlogs_p, float* dbias_p, int64_t N, int64_t C, int64_t HW, void* stream);
+
+/* Adjoint of glowk_actnorm_mix (forward direction): dx = s*(W^T dz); dw += sum_p dz a^T;
+ * dlogs += f*sum da*a; dbias += sum da*s, with a = (x+bias)*s recomputed from the step input x. */
+int glowk_actnorm_mix_bwd(const float* x, const float* dz, const float* w, const int64_t* idx,
+                          const float* bias, const float* logs, float logscale_factor, float* dx, float* dw,
+                          float* dlogs, float* dbias, int64_t N, int64_t C, int64_t HW, void* stream);
+
+/* Gradient of the sample-independent logdet terms: dlogs[c] += f*HW*G, dw += HW*G*W^-T, G = sum_n dld[n]. */
+int glowk_logdet_param_grad(const float* dld, int64_t N, int64_t HW, float logscale_factor, float* dlogs,
+                            int64_t C, const float* winv, float* dw, void* stream);
+
+/* Inverse of glowk_pack_conv_weight for gradients: grad[O][I][k][k] (+)= src (packed layout, fp32). */
+int glowk_unpack_weight_grad(const float* src, int64_t ld, int64_t O, int64_t I, int ksize, int layout,
+                             float* grad, int accumulate, void* stream);
+
+/* ---- Fused optimizer step over a flat fp32 arena: trainer.py:142-150 + torch.optim.Adam (builder.py:10-13)
+ * clip_norm: grads = clamp(grads, +-clip_value) in place (clip_grad_value_), then workspace[0] = global
+ * L2 norm, workspace[1] = min(1, max_norm/(norm+1e-6)) (clip_grad_norm_).  workspace: device floats,
+ * glowk_optim_workspace_floats() long.
+ * adam: grads *= norm_coef[1]; m,v,params updated (no weight decay, no amsgrad).  sched_dev (nullable):
+ * device [lr, 1-beta1^step, sqrt(1-beta2^step)] overriding lr/step so a CUDA graph can be replayed. */
+int64_t glowk_optim_workspace_floats(void);
+int glowk_optim_clip_norm(float* grads, int64_t n, float clip_value, float max_norm, float* workspace, void* stream);
+int glowk_optim_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     const float* norm_coef, const float* sched_dev, float lr, float beta1, float beta2,
+                     float eps, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -243,3 +243,73 @@ def split2d_sample(h_rows, z1, eps):
     out = torch.empty(n, 2 * ch, h, w, device=z1.device, dtype=torch.float32)
     call("glowk_split2d_sample", ptr(h_rows), h_rows.shape[1], ptr(z1), ptr(eps), ptr(out), n, ch, h * w)
     return out
+
+
+# ------------------------------------------------------------------ backward (training) wrappers
+def coupling_bwd(y, hrows, dy, dld, logs3, affine, dlogs3, dbias3, logscale_factor=3.0):
+    """Adjoint of `coupling` (+ Conv2dZeros scale).  Returns (dz [N,C,H,W], du rows [P][Cout])."""
+    check_cuda(y, hrows, dy, dld, logs3, dlogs3, dbias3)
+    n, c, h, w = y.shape
+    cout = c if affine else c // 2
+    dy = _f32c(dy)
+    dz = torch.empty_like(y)
+    du = torch.empty(n * h * w, cout, device=y.device, dtype=torch.float32)
+    call("glowk_coupling_bwd", ptr(y), ptr(hrows), ptr(dy), ptr(dld), ptr(logs3), float(logscale_factor), ptr(dz),
+         ptr(du), ptr(dlogs3), ptr(dbias3), n, c, h, w, int(bool(affine)))
+    return dz, du
+
+
+def split2d_bwd(x, hrows, dz1, dld, logs_p, dlogs_p, dbias_p, logscale_factor=3.0):
+    """Adjoint of Split2d forward.  Returns (dx [N,C,H,W], du rows [P][C])."""
+    check_cuda(x, hrows, dz1, dld, logs_p)
+    n, c, h, w = x.shape
+    dx = torch.empty_like(x)
+    du = torch.empty(n * h * w, c, device=x.device, dtype=torch.float32)
+    sn = 0
+    if dz1 is not None:
+        if not (dz1.stride(3) == 1 and dz1.stride(2) == w and dz1.stride(1) == h * w):
+            dz1 = dz1.contiguous()
+        sn = dz1.stride(0) if n > 1 else (c // 2) * h * w
+    call("glowk_split2d_bwd", ptr(x), ptr(hrows), hrows.shape[1], None if dz1 is None else dz1.data_ptr(), sn,
+         ptr(dld), ptr(logs_p), float(logscale_factor), ptr(dx), ptr(du), c, ptr(dlogs_p), ptr(dbias_p), n, c, h * w)
+    return dx, du
+
+
+def actnorm_mix_bwd(x, dz, weight=None, indices=None, bias=None, logs=None, dw=None, dlogs=None, dbias=None,
+                    logscale_factor=3.0):
+    """Adjoint of the forward `actnorm_mix`; accumulates dw / dlogs / dbias, returns dx."""
+    check_cuda(x, dz, weight, indices, bias, logs, dw, dlogs, dbias)
+    n, c, h, w = x.shape
+    dz = _f32c(dz)
+    dx = torch.empty_like(x)
+    call("glowk_actnorm_mix_bwd", ptr(x), ptr(dz), ptr(weight), ptr(indices), ptr(bias), ptr(logs),
+         float(logscale_factor), ptr(dx), ptr(dw), ptr(dlogs), ptr(dbias), n, c, h * w)
+    return dx
+
+
+def logdet_param_grad(dld, hw, dlogs=None, winv=None, dw=None, logscale_factor=3.0):
+    check_cuda(dld, dlogs, winv, dw)
+    c = dlogs.numel() if dlogs is not None else winv.shape[0]
+    call("glowk_logdet_param_grad", ptr(dld), dld.numel(), hw, float(logscale_factor), ptr(dlogs), c, ptr(winv), ptr(dw))
+
+
+def unpack_weight_grad(src, o, i, ksize, layout, grad, accumulate=True):
+    check_cuda(src, grad)
+    assert src.dtype == torch.float32 and grad.is_contiguous()
+    call("glowk_unpack_weight_grad", ptr(src), src.shape[1], o, i, int(ksize), int(layout), ptr(grad),
+         int(bool(accumulate)))
+
+
+def optim_workspace(device):
+    return torch.zeros(int(_C.lib().glowk_optim_workspace_floats()), device=device, dtype=torch.float32)
+
+
+def optim_clip_norm(grads, clip_value, max_norm, workspace):
+    """In-place clip_grad_value_ then norm/coef into workspace[0:2] (trainer.py:142-147)."""
+    call("glowk_optim_clip_norm", ptr(grads), grads.numel(), float(clip_value or 0.0), float(max_norm or 0.0),
+         ptr(workspace))
+
+
+def optim_adam(params, grads, exp_avg, exp_avg_sq, workspace, step, lr, beta1, beta2, eps, sched=None):
+    call("glowk_optim_adam", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(workspace),
+         ptr(sched), float(lr), float(beta1), float(beta2), float(eps), int(step))

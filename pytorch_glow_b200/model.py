@@ -156,6 +156,10 @@ class FlowModel(nn.Module):
                 mine.perm_module.set_indices(getattr(theirs, mine.permutation).indices)
 
     def encode(self, z, logdet=0.):
+        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters())):
+            from .autograd import flow_encode_autograd
+            _C.check_cuda(z)
+            return flow_encode_autograd(self, z, logdet)      # the whole encode is one autograd node
         for layer in self.layers:
             z, logdet = layer(z, logdet, reverse=False)
         return z, logdet
@@ -235,7 +239,10 @@ class Glow(nn.Module):
         objective = torch.full((x.shape[0],), float(-np.log(n_bins)) * logdet_factor, device=x.device,
                                dtype=torch.float32)
         z, objective = self.flow(z, logdet=objective, reverse=False)
-        if self._plain_top_prior and not (torch.is_grad_enabled() and z.requires_grad):
+        if self._plain_top_prior and torch.is_grad_enabled() and z.requires_grad:
+            from .autograd import TopPriorFunction
+            objective = TopPriorFunction.apply(z, objective)
+        elif self._plain_top_prior:
             objective = K.gaussian_logp(None, z.contiguous(), 0, z.shape[1], objective)   # N(0,1) top prior
         else:
             mean, logs = self.prior(y_onehot)

@@ -36,6 +36,15 @@ def _logdet_out(vec, scalar_like):
     return vec.reshape(()) if scalar_like else vec
 
 
+_WEIGHT_GENERATION = [0]
+
+
+def bump_weight_generation():
+    """Invalidate every packed-weight / LU cache.  Called by optimizers that update parameters through
+    raw pointers (train.FusedTrainStep), which torch's per-tensor version counter cannot see."""
+    _WEIGHT_GENERATION[0] += 1
+
+
 class _PackCache:
     """Packed (GEMM-layout) copies of a parameter, rebuilt when the parameter changes."""
 
@@ -43,7 +52,7 @@ class _PackCache:
         self._d = {}
 
     def get(self, key, param, build):
-        tag = (param.data_ptr(), param._version, param.device)
+        tag = (param.data_ptr(), param._version, param.device, _WEIGHT_GENERATION[0])
         hit = self._d.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -301,10 +310,11 @@ class CouplingNet(nn.Sequential):
                     an1.logs.detach().reshape(-1), an1.logscale_factor, out_dtype=dt, ldo=kh)
         w2 = self.packed("w2", dt)
         if an2.needs_init:
-            an2.initialize_from_rows(K.gemm(h1, w2, hid, kh, _C.EPI_STORE, out_dtype=_C.F32))
-        h2 = K.gemm(h1, w2, hid, kh, _C.EPI_ACTNORM_RELU, an2.bias.detach().reshape(-1),
+            an2.initialize_from_rows(K.gemm(h1, w2, hid, hid, _C.EPI_STORE, out_dtype=_C.F32))
+        h2 = K.gemm(h1, w2, hid, hid, _C.EPI_ACTNORM_RELU, an2.bias.detach().reshape(-1),
                     an2.logs.detach().reshape(-1), an2.logscale_factor, out_dtype=dt, ldo=kh)
-        p3 = K.gemm(h2, self.packed("w3", dt), self.n3, kh, _C.EPI_STORE, out_dtype=_C.F32, ldo=self.n3p)
+        # K = hid (not the padded pitch): pad columns of h1/h2 are never read (TMA clips at K)
+        p3 = K.gemm(h2, self.packed("w3", dt), self.n3, hid, _C.EPI_STORE, out_dtype=_C.F32, ldo=self.n3p)
         if save is not None:
             save.update(a1=a1, h1=h1, h2=h2)
         return p3
@@ -380,6 +390,23 @@ class Invertible1x1Conv(nn.Module):
 
     def dense_weight(self):
         return self.prepared(False)[0]
+
+    def accumulate_lu_grads(self, dw):
+        """Chain dL/dW (CxC, includes the logdet term) into the LU parameters: W = P Lf Uf."""
+        with torch.no_grad():
+            c = self.num_channels
+            eye = torch.eye(c, device=dw.device)
+            lf = torch.tril(self.l, -1) + eye
+            s = self.sign_s * torch.exp(self.log_s)
+            uf = torch.triu(self.u, 1) + torch.diag(s)
+            ptdw = self.p.t() @ dw
+            dlf = ptdw @ uf.t()
+            duf = lf.t() @ ptdw
+            for prm, g in ((self.l, torch.tril(dlf, -1)), (self.u, torch.triu(duf, 1)),
+                           (self.log_s, torch.diagonal(duf) * s)):
+                if prm.grad is None:
+                    prm.grad = torch.zeros_like(prm)
+                prm.grad.add_(g)
 
     def forward(self, x, logdet=None, reverse=False):
         _C.check_cuda(x)

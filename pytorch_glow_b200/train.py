@@ -1,0 +1,175 @@
+"""Data-parallel training step (the caller side of the hot path, network/trainer.py:84-150).
+
+One process per GPU.  All trainable parameters live in ONE flat fp32 arena with a matching flat
+gradient arena, so that
+  * the backward kernels accumulate straight into the arena (no per-tensor autograd adds),
+  * gradient averaging across ranks is a single NCCL all-reduce over NVLink (the reference's
+    DataParallel re-broadcasts 176 MB of parameters and reduces 176 MB of gradients to device 0
+    every step, trainer.py:117-120),
+  * clip_grad_value_(5) -> clip_grad_norm_(100) -> Adam (trainer.py:142-150) is three kernels over
+    the arena (glowk_optim_*), and
+  * the whole step can be captured in CUDA graphs (launch-bound otherwise: ~2000 kernels/step).
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import functional as K
+from . import module as _module
+
+
+def noam_lr(base_lr, global_step, warmup_steps=4000, min_lr=None):
+    """misc/lr_scheduler.py:18-37 (the schedule profile/celeba.json selects)."""
+    step_num = global_step + 1.0
+    lr = base_lr * warmup_steps ** 0.5 * min(step_num * warmup_steps ** -1.5, step_num ** -0.5)
+    if global_step >= warmup_steps and min_lr is not None:
+        lr = max(lr, min_lr)
+    return lr
+
+
+class FlatArena:
+    """Re-homes a module's trainable parameters (and their .grad) into flat fp32 buffers."""
+
+    def __init__(self, model, skip=("h_top",)):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad and n.split(".")[-1] not in skip]
+        self.names = [n for n, _ in named]
+        self.params = [p for _, p in named]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # 16-byte aligned slots
+        self.offsets, self.numel = offs, total
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        for p, o in zip(self.params, offs):
+            n = p.numel()
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+        _module.bump_weight_generation()
+
+    def rebind_grads(self):
+        """(Re)attach .grad views -- e.g. after someone called zero_grad(set_to_none=True)."""
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+
+class FusedTrainStep:
+    """forward + backward + (all-reduce) + clip + Adam for a pytorch_glow_b200.Glow.
+
+    Mirrors one iteration of Trainer.train (network/trainer.py:84-150) for the generative loss.
+    `use_graphs=True` captures the iteration in two CUDA graphs around the (eager) NCCL all-reduce.
+    """
+
+    def __init__(self, glow, lr=1e-3, betas=(0.9, 0.9999), eps=1e-8, max_grad_clip=5.0, max_grad_norm=100.0,
+                 warmup_steps=4000, min_lr=1e-4, use_graphs=False, process_group=None, world_size=1):
+        self.glow = glow
+        self.base_lr, self.betas, self.eps = lr, betas, eps
+        self.max_grad_clip, self.max_grad_norm = max_grad_clip, max_grad_norm
+        self.warmup_steps, self.min_lr = warmup_steps, min_lr
+        self.world_size, self.pg = world_size, process_group
+        for p in glow.parameters():
+            if p is glow.h_top:
+                p.requires_grad_(False)           # never receives a gradient
+        self.arena = FlatArena(glow)
+        dev = self.arena.flat.device
+        self.exp_avg = torch.zeros_like(self.arena.flat)
+        self.exp_avg_sq = torch.zeros_like(self.arena.flat)
+        self.ws = K.optim_workspace(dev)
+        self.sched_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(4)
+        self.sched_dev = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.global_step = 0
+        self.use_graphs = use_graphs
+        self._g_fb = self._g_opt = None
+        self._static_x = None
+        self._static_loss = None
+
+    # -- step 0 of the reference trainer: data-dependent ActNorm init on the first shard (trainer.py:112-115)
+    def init_actnorm(self, x):
+        self.glow.train()
+        with torch.no_grad():
+            self.glow(x=x)
+        _module.bump_weight_generation()
+        if self.world_size > 1:
+            dist.broadcast(self.arena.flat, src=0, group=self.pg)    # rank 0's initialisation wins
+
+    def _set_schedule(self):
+        lr = noam_lr(self.base_lr, self.global_step, self.warmup_steps, self.min_lr)
+        t = self.global_step + 1
+        self.sched_host[0] = lr
+        self.sched_host[1] = 1.0 - self.betas[0] ** t
+        self.sched_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
+        return lr
+
+    def _forward_backward(self, x):
+        self.arena.grad.zero_()
+        self.arena.rebind_grads()
+        z, nll, _ = self.glow(x=x)
+        loss = self.glow.generative_loss(nll)
+        loss.backward()
+        return loss.detach()
+
+    def _optimizer(self):
+        self.sched_dev.copy_(self.sched_host, non_blocking=True)
+        K.optim_clip_norm(self.arena.grad, self.max_grad_clip, self.max_grad_norm, self.ws)
+        K.optim_adam(self.arena.flat, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.ws, self.global_step + 1,
+                     0.0, self.betas[0], self.betas[1], self.eps, sched=self.sched_dev)
+
+    def _allreduce(self):
+        if self.world_size > 1:
+            # average BEFORE clipping so every rank clips identical tensors
+            dist.all_reduce(self.arena.grad, op=dist.ReduceOp.AVG, group=self.pg)
+
+    def step(self, x):
+        """One training iteration on the device batch x [B,3,H,W] in [0,1).  Returns the loss (bits/dim)
+        as a 0-dim device tensor."""
+        self.glow.train()
+        self._set_schedule()
+        if not self.use_graphs:
+            loss = self._forward_backward(x)
+            self._allreduce()
+            self._optimizer()
+            _module.bump_weight_generation()
+        else:
+            if self._g_fb is None:
+                self._capture(x)
+            self._static_x.copy_(x, non_blocking=True)
+            self._g_fb.replay()
+            self._allreduce()
+            self._g_opt.replay()
+            _module.bump_weight_generation()      # eager callers (sampling, eval) must re-pack the new weights
+            loss = self._static_loss
+        self.global_step += 1
+        return loss
+
+    @property
+    def grad_norm(self):
+        return self.ws[0]
+
+    def _capture(self, x):
+        self._static_x = torch.empty_like(x)
+        self._static_x.copy_(x)
+        # warm-up on a side stream (allocator + lazy init), then capture; weights caches are invalidated so
+        # that every pack / LU kernel is part of the graph and re-runs on each replay
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        saved = (self.arena.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                _module.bump_weight_generation()
+                self._forward_backward(self._static_x)
+                self._optimizer()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.arena.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+        _module.bump_weight_generation()
+        self._g_fb = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_fb):
+            self._static_loss = self._forward_backward(self._static_x)
+        self._g_opt = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g_opt):
+            self._optimizer()
+        # the captures above only recorded; nothing has executed yet
