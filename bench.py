@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: training (and sampling) images/s of the 64x64 CelebA-shaped Glow
+(K=32, L=3, hidden 512, affine coupling, invertible 1x1 conv -- profile/celeba.json:47-70 of the
+reference) on N B200s of one node, synthetic images, one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference's CPU arithmetic (oracle port) on the host cores
+
+Prints ONE JSON line (rank 0).  A "step" is one full training iteration of network/trainer.py:84-150:
+dequantise -> encode -> bits/dim -> backward -> gradient all-reduce -> clip(5)/clip-norm(100) -> Adam.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (image_shape HWC, K, L, hidden, coupling, default per-GPU batch, fwd GFLOP/img)
+    "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 64, 32.06),
+    "cifar32": ((32, 32, 3), 32, 3, 512, "affine", 256, 8.02),
+    "tiny": ((32, 32, 3), 4, 3, 64, "affine", 16, None),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="celeba64", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
+    ap.add_argument("--sample-batch", type=int, default=256, help="per-GPU sampling batch (BASELINE config 4)")
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sample", action="store_true")
+    ap.add_argument("--conv-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--profile-step", action="store_true",
+                    help="for ncu --profile-from-start off: run ONE eager train step (and one sampling pass) "
+                         "between cudaProfilerStart/Stop after warm-up, print nothing, exit")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if not (t0 - 0.1 <= t <= t1 + 0.3):
+                continue
+            f = [c.strip() for c in line.split(",")]
+            try:
+                sm.append(float(f[1])); smax = float(f[2]); power.append(float(f[3]))
+            except (ValueError, IndexError):
+                continue
+            for nme, val in zip(names, f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_train_baseline(workload, batch, steps, warmup, state_dict=None):
+    """The reference's arithmetic (CPU oracle port, torch fp32 on the host cores): full train iterations
+    on a bounded batch.  Returns (img/s, cores, seconds per step)."""
+    from oracle import glow_oracle as O
+    shape, K, L, hidden, coupling, _, _ = WORKLOADS[workload]
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    if state_dict is None:
+        import pytorch_glow_b200 as G
+        from pytorch_glow_b200.hps import make_hps
+        np.random.seed(2384); torch.manual_seed(2384)
+        state_dict = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=batch)).state_dict()
+    p = {k: v.detach().float().cpu().clone().requires_grad_(k != "h_top") for k, v in state_dict.items()}
+    names = [k for k in p if k != "h_top"]
+    ms = {k: torch.zeros_like(p[k]) for k in names}
+    vs = {k: torch.zeros_like(p[k]) for k in names}
+    g = torch.Generator().manual_seed(1234)
+    x = torch.rand(batch, shape[2], shape[0], shape[1], generator=g)
+    times = []
+    for t in range(warmup + steps):
+        t0 = time.perf_counter()
+        noise = torch.rand(x.shape, generator=g) / 256
+        for k in names:
+            p[k].grad = None
+        _, nll = O.glow_nll(x, noise, p, shape, K, L, "invconv", coupling)
+        loss = O.generative_loss(nll)
+        loss.backward()
+        O.clip_grads_([p[k].grad for k in names], 5.0, 100.0)
+        with torch.no_grad():
+            for k in names:
+                O.adam_step_(p[k], p[k].grad, ms[k], vs[k], t + 1, O.noam_lr(1e-3, t, 4000, 1e-4))
+        if t >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return batch / sec, cores, sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))   # bounded: ~4 s per CPU step
+    ips, cores, sec = cpu_train_baseline(args.workload, args.cpu_batch, steps, warmup)
+    sample = "%d train iterations (+%d warm-up) of the oracle port on a batch of %d" % (steps, warmup, args.cpu_batch)
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "img/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "per_gpu_batch": args.cpu_batch, "device": "host CPU"},
+        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w):
+    shape, K, L, hidden, coupling, _, _ = WORKLOADS[w]
+    return "%s: Glow %dx%dx%d K=%d L=%d hidden=%d %s coupling, invconv, train iteration" % (
+        w, shape[2], shape[0], shape[1], K, L, hidden, coupling)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def timed(fn, steps, dist_on, device):
+    """K calls of fn bracketed by barrier + synchronize on both sides; device time by CUDA events; max over ranks."""
+    import torch.distributed as dist
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist_on:
+        dist.barrier()
+    w1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if dist_on:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / 1e3, w0, w1
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    import pytorch_glow_b200 as G
+    from pytorch_glow_b200 import _C, config
+    from pytorch_glow_b200 import functional as KF
+    from pytorch_glow_b200.hps import make_hps
+    from pytorch_glow_b200.train import FusedTrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", device_id=device)
+    _C.lib()                                            # fail loudly if the extension is missing
+    config.conv_dtype = args.conv_dtype
+
+    shape, K, L, hidden, coupling, default_b, gflop = WORKLOADS[args.workload]
+    B = args.batch or default_b
+    seed = 2384                                         # profile/celeba.json:66
+    np.random.seed(seed); torch.manual_seed(seed)       # identical initial replicas on every rank
+    glow = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=B)).to(device)
+    n_params = sum(p.numel() for n, p in glow.named_parameters() if n != "h_top")
+    ts = FusedTrainStep(glow, use_graphs=not args.no_graphs, world_size=world)
+
+    # synthetic images in [0,1) like ToTensor() output (train.py:41-45); distinct per rank and per step
+    gen = torch.Generator().manual_seed(1234 + rank)
+    nb = 4
+    x_host = [torch.rand(B, shape[2], shape[0], shape[1], generator=gen).pin_memory() for _ in range(nb)]
+    x_dev = [x.to(device) for x in x_host]
+    x_stage = torch.empty_like(x_dev[0])
+
+    ts.init_actnorm(x_dev[0])                           # trainer.py:112-115
+    launches0 = _C.launch_count
+    for i in range(max(args.warmup, 3)):
+        ts.step(x_dev[i % nb])
+    torch.cuda.synchronize()
+    calls_per_step = None
+    if not args.no_graphs:
+        calls_per_step = getattr(ts, "captured_calls", None)
+
+    if args.profile_step:
+        rt = torch.cuda.cudart()
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+        ts.step(x_dev[0])
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        return
+
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    losses = []
+
+    def resident(i):
+        losses.append(ts.step(x_dev[i % nb]))
+
+    def end_to_end(i):
+        x_stage.copy_(x_host[i % nb], non_blocking=True)        # H2D of this step's inputs (pinned)
+        losses.append(float(ts.step(x_stage)))                   # D2H read of the step's loss
+
+    for attempt in range(2):
+        sampler.start()
+        c0 = _C.launch_count
+        sec, w0, w1 = timed(resident, args.steps, dist_on, device)
+        c1 = _C.launch_count
+        clocks = sampler.stop(w0, w1)
+        if not (set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}):
+            break
+        sampler = ClockSampler(sampler.idx)
+    sec_e2e, _, _ = timed(end_to_end, args.steps, dist_on, device)
+    last_loss = float(losses[-1])
+
+    imgs = B * world * args.steps
+    value, e2e = imgs / sec, imgs / sec_e2e
+    if args.no_graphs:
+        gpu_launches = c1 - c0
+    else:
+        gpu_launches = (ts.captured_calls if hasattr(ts, "captured_calls") else 0) * args.steps
+
+    # ---- sampling (BASELINE config 4): reverse pass, eps_std 0.7, no collective
+    sample = None
+    if not args.no_sample:
+        SB = args.sample_batch
+        glow_s = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=SB))
+        sd = {k: v for k, v in glow.state_dict().items() if k != "h_top"}
+        glow_s.load_state_dict(sd, strict=False)
+        glow_s.set_actnorm_inited()
+        glow_s = glow_s.to(device).eval()
+
+        def sample_fn(i):
+            with torch.no_grad():
+                return glow_s(z=None, eps_std=0.7, reverse=True)
+        for _ in range(2):
+            sample_fn(0)
+        ssec, _, _ = timed(sample_fn, max(2, args.steps // 2), dist_on, device)
+        sample = {"value": SB * world * max(2, args.steps // 2) / ssec, "unit": "img/s", "per_gpu_batch": SB,
+                  "eps_std": 0.7, "collective": "none"}
+        del glow_s
+
+    # ---- roofline of the dominant kernel: the 512x512 1x1 conv as a tcgen05 GEMM (76% of the step's FLOPs)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    roof = None
+    if rank == 0 and args.conv_dtype == "bf16":
+        M = B * (shape[0] // 2) * (shape[1] // 2)
+        a = [torch.randn(M, hidden, device=device).bfloat16() for _ in range(3)]     # 3 x 64 MB: larger than L2
+        wgt = (torch.randn(hidden, hidden, device=device) * 0.05).bfloat16()
+        bias = torch.zeros(hidden, device=device); logs = torch.zeros(hidden, device=device)
+        outs = [torch.empty(M, hidden, device=device, dtype=torch.bfloat16) for _ in range(3)]
+        for i in range(3):
+            KF.gemm(a[i], wgt, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i])
+        torch.cuda.synchronize()
+        reps = 12
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            KF.gemm(a[i % 3], wgt, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i % 3])
+        e1.record()
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps / 1e3
+        flops = 2.0 * M * hidden * hidden
+        peak = peaks.get("bf16_tflops", 1590.0)
+        roof = {"kernel": "gemm_tc_kernel<ACTNORM_RELU,bf16> (coupling conv2, M=%d N=K=%d)" % (M, hidden),
+                "bound": "tensor", "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "frac": flops / t / 1e12 / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
+                "us_per_launch": t * 1e6}
+        del a, outs
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload through the oracle port
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sd_cpu = {k: v.detach().cpu() for k, v in glow.state_dict().items()}
+        ips, cores, sec_cpu = cpu_train_baseline(args.workload, args.cpu_batch, 2, 1, sd_cpu)
+        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
+               "sample": "2 train iterations (+1 warm-up) of oracle/glow_oracle.py on a batch of %d (%.1f s/iteration)" % (args.cpu_batch, sec_cpu)}
+
+    if rank == 0:
+        act_gb = None
+        line = {
+            "metric": "train_images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.conv_dtype, "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "global_batch": B * world, "per_gpu_batch": B,
+                       "parallelism": "dp%d" % world, "cuda_graphs": not args.no_graphs,
+                       "l2": "per-step working set (saved activations ~%.1f GB/GPU) >> 126 MB L2; 4 rotating input batches" % (B * 0.1),
+                       "grad_allreduce_mb": n_params * 4 / 1e6 if world > 1 else 0,
+                       "flow_state_dtype": "fp32", "conv_operands": args.conv_dtype},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": x_host[0].numel() * 4 * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": sec_e2e / args.steps * 1e3},
+            "gpu_launches": gpu_launches, "clocks": clocks, "loss_bits_per_dim": last_loss,
+            "roofline": roof, "cpu_baseline": cpu, "sample": sample,
+        }
+        if gflop:
+            tf = value * gflop * 3 / 1e3          # fwd + dgrad + wgrad
+            line["tensor_tflops_train"] = tf
+            line["tensor_frac_of_sustained"] = tf / world / peaks.get("bf16_tflops_sustained", 1400.0)
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

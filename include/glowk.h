@@ -65,6 +65,11 @@ int glowk_actnorm_init(const void* x, int act_dtype, int64_t N, int64_t C, int64
  * LU with partial pivoting of the CxC matrix W (one CTA, fp64 internally):
  * logabsdet_out[0] = log|det W|; winv_out (nullable) = W^-1. */
 int glowk_invconv_prepare(const float* w, int64_t C, float* logabsdet_out, float* winv_out, void* stream);
+/* Same for `batch` matrices stored back to back (w: [batch][C][C]; logabsdet_out: [batch];
+ * winv_out: [batch][C][C] or null): one launch, one CTA per matrix.  A FlowModel factorises all the
+ * invconv weights of one channel count at once (FlowModel.encode's loop calls module.py:357 K*L times). */
+int glowk_invconv_prepare_batched(const float* w, int64_t batch, int64_t C, float* logabsdet_out,
+                                  float* winv_out, void* stream);
 
 /* LU parameterisation (north_star; the reference raises NotImplementedError, module.py:336-337):
  * W = P . L . (U + diag(sign_s*exp(log_s))), L unit-lower (strict lower part of l), U strictly
@@ -126,6 +131,12 @@ int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int act_d
                int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
                float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
                void* out, int out_dtype, int64_t ldo, void* stream);
+/* Same with an explicit thread-block-cluster shape for the tcgen05 path: cluster_m m-tiles share (TMA-multicast)
+ * the B tile and cluster_n n-tiles share the A tile; powers of two, cluster_m*cluster_n <= 8; 0 = library default. */
+int glowk_gemm_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype,
+                  int64_t M, int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
+                  float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
+                  void* out, int out_dtype, int64_t ldo, int cluster_m, int cluster_n, void* stream);
 
 /* Weight-gradient GEMM: dW[Mo][No] (+)= A[P][Mo]^T . B[P][No]  (reduction over pixels, fp32 out,
  * split over CTAs with atomic accumulation).  A: [P][lda], B: [P][ldb] of act_dtype. */

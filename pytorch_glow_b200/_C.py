@@ -27,6 +27,7 @@ SIGNATURES = {
     "glowk_actnorm": [_p, _p, _p, _p, _f32, _i64, _i64, _i64, _i32, _p],
     "glowk_actnorm_init": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _p, _p, _p],
     "glowk_invconv_prepare": [_p, _i64, _p, _p, _p],
+    "glowk_invconv_prepare_batched": [_p, _i64, _i64, _p, _p, _p],
     "glowk_invconv_lu_assemble": [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     "glowk_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i64, _i32, _p],
     "glowk_squeeze2d": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
@@ -37,6 +38,8 @@ SIGNATURES = {
     "glowk_pack_conv_weight": [_p, _i64, _i64, _i32, _i32, _p, _i32, _i64, _i64, _p],
     "glowk_gemm": [_p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p, _p,
                    _p, _i32, _i64, _p],
+    "glowk_gemm_ex": [_p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p, _p,
+                      _p, _i32, _i64, _i32, _i32, _p],
     "glowk_gemm_wgrad": [_p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p],
     "glowk_coupling_nblk": [_i64],
     "glowk_coupling": [_p, _i64, _p, _p, _f32, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p],

@@ -42,6 +42,14 @@ extern "C" int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb
                           int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
                           float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
                           void* out, int out_dtype, int64_t ldo, void* stream) {
+  return glowk_gemm_ex(A, lda, B, ldb, act_dtype, M, N, K, epilogue, bias, logs, logscale_factor, y, ldy, dlogs,
+                       dbias, out, out_dtype, ldo, 0, 0, stream);
+}
+
+extern "C" int glowk_gemm_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype, int64_t M,
+                             int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,
+                             float logscale_factor, const void* y, int64_t ldy, float* dlogs, float* dbias,
+                             void* out, int out_dtype, int64_t ldo, int cluster_m, int cluster_n, void* stream) {
   if (M == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(A && B && out, "glowk_gemm: null pointer");
   GLOWK_CHECK_ARG(M >= 0 && N > 0 && K > 0, "glowk_gemm: bad shape M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
@@ -59,7 +67,7 @@ extern "C" int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb
   if (act_dtype == GLOWK_F32)
     return gemm_f32((const float*)A, lda, (const float*)B, ldb, M, N, K, epilogue, ep, out, out_dtype, ldo, st);
   if (act_dtype == GLOWK_BF16)
-    return gemm_bf16_tc(A, lda, B, ldb, M, N, K, epilogue, ep, out, out_dtype, ldo, st);
+    return gemm_bf16_tc(A, lda, B, ldb, M, N, K, epilogue, ep, out, out_dtype, ldo, cluster_m, cluster_n, st);
   return fail(GLOWK_EINVAL, "glowk_gemm: bad act_dtype %d", act_dtype);
 }
 

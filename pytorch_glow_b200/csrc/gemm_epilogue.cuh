@@ -52,7 +52,8 @@ int wgrad_simt(const void* A, int64_t lda, const void* B, int64_t ldb, int act_d
                int64_t No, float* dW, int64_t lddw, cudaStream_t st);
 // implemented in gemm_sm100.cu
 int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                 int epilogue, const EpiParams& ep, void* out, int out_dtype, int64_t ldo, cudaStream_t st);
+                 int epilogue, const EpiParams& ep, void* out, int out_dtype, int64_t ldo, int cluster_m, int cluster_n,
+                 cudaStream_t st);
 int wgrad_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t P, int64_t Mo, int64_t No,
                   float* dW, int64_t lddw, cudaStream_t st);
 bool tc_available();

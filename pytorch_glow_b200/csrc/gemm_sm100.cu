@@ -13,6 +13,7 @@
 //                                swizzled smem staging -> TMA store (or red.global for wgrad)
 // The two accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -23,16 +24,18 @@ namespace tc {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;          // one 128-byte swizzle span of bf16
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;         // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
+constexpr int EPI_WARPS = 8;
 constexpr int ACC_STAGE_COLS = 256;  // TMEM columns per accumulator stage (2 stages = 512 columns)
 constexpr int MAX_STAGES = 8;
-constexpr int STAGING_BYTES = 4 * 2 * 4096;  // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+constexpr int STAGING_BYTES = 8 * 4096;      // one (32 rows x 128 B) TMA-store box per epilogue warp
 
 struct Shared {
   uint64_t full_bar[MAX_STAGES];
   uint64_t empty_bar[MAX_STAGES];
   uint64_t tmem_full_bar[2];
   uint64_t tmem_empty_bar[2];
+  uint64_t y_bar[8];
   uint32_t tmem_base;
 };
 
@@ -84,6 +87,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -121,6 +128,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// Same without the wait: issue several, then tmem_ld_wait() once (the loads overlap).
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor, SWIZZLE_128B (layout_type 2), descriptor version 1 (sm_100).
 //   K-major  operand: rows of 128 B (64 bf16 along K); SBO = 1024 B between 8-row groups; LBO unused (1).
@@ -161,38 +181,88 @@ struct OutBox {  // one TMA-store box = 32 rows x 128 bytes
   static constexpr int COLS = 128 / (int)sizeof(OutT);
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+constexpr int EPI_NMAX = 1024;   // column sums of RELU_BWD are kept in shared memory up to this N
+
+// ---------------------------------------------------------------------------------------------
+// out[M][N] = epilogue(A[M][K] . B[N][K]^T).  Optional thread-block cluster of CM x CN CTAs working on
+// CM m-tiles x CN n-tiles of one "super tile": the A tile of an m-tile is needed by the CN CTAs of that
+// row and the B tile of an n-tile by the CM CTAs of that column, so every CTA loads 1/CN of its A tile
+// and 1/CM of its B tile and TMA-multicasts the slice to its row / column mates (L2 -> SM traffic per CTA
+// drops from A+B to A/CN + B/CM).
 // ---------------------------------------------------------------------------------------------
 template <int EPI, typename OutT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               const __grid_constant__ CUtensorMap tm_o, int M, int N, int K, int block_n, int num_stages,
-               EpiParams ep) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+               const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_y, int M, int N,
+               int K, int block_n, int num_stages, int CM, int CN, EpiParams ep) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
   const uint32_t b_bytes = (uint32_t)block_n * BLOCK_K * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* staging = smem + (size_t)num_stages * stage_bytes;
-  Shared* sh = reinterpret_cast<Shared*>(staging + STAGING_BYTES);
+  uint8_t* ybuf = staging + STAGING_BYTES;                                        // RELU_BWD: one 4 KB y box per epilogue warp
+  float* s_scale = reinterpret_cast<float*>(ybuf + (EPI == GLOWK_EPI_RELU_BWD ? STAGING_BYTES : 0));
+  float* s_shift = s_scale + 256;
+  float* s_gy = s_shift + 256;                                                    // RELU_BWD: [EPI_NMAX] x 2
+  float* s_g = s_gy + EPI_NMAX;
+  Shared* sh = reinterpret_cast<Shared*>(s_gy + (EPI == GLOWK_EPI_RELU_BWD ? 2 * EPI_NMAX : 0));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int csize = CM * CN;
+  const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
+  const int cm = (int)crank % CM, cn = (int)crank / CM;
+  const int cluster_id = blockIdx.x / csize, num_clusters = gridDim.x / csize;
   const int m_blocks = (M + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (N + block_n - 1) / block_n;
-  const int num_tiles = m_blocks * n_blocks;
+  const int sup_n = (n_blocks + CN - 1) / CN;
+  const int num_super = ((m_blocks + CM - 1) / CM) * sup_n;
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  // multicast masks: row mates (same cm) receive my A slice, column mates (same cn) my B slice
+  uint16_t mask_a = 0, mask_b = 0;
+  for (int j = 0; j < CN; ++j) mask_a |= (uint16_t)(1u << (cm + CM * j));
+  for (int i = 0; i < CM; ++i) mask_b |= (uint16_t)(1u << (i + CM * cn));
+  const uint16_t mask_all = mask_a | mask_b;
+  const bool small_n = N <= EPI_NMAX;
 
+  if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_o);
-    for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], 4); }
+    if (EPI == GLOWK_EPI_RELU_BWD) prefetch_tensormap(&tm_y);
+    for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], (uint32_t)(CM + CN - 1)); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], EPI_WARPS); }
+    for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: 512 columns (two accumulator stages), allocated and freed by this warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (EPI == GLOWK_EPI_RELU_BWD)
+    for (int i = threadIdx.x; i < 2 * EPI_NMAX; i += GEMM_THREADS) s_gy[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();        // peers' barriers must be initialised before any remote arrive / multicast
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
 
@@ -200,14 +270,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
+      const int a_rows = BLOCK_M / CN, b_rows = block_n / CM;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
+        const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&sh->empty_bar[stage], phase ^ 1);
+          mbar_wait(&sh->empty_bar[stage], phase ^ 1);     // every CTA I write into has drained this slot
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           mbar_arrive_expect_tx(&sh->full_bar[stage], stage_bytes);
-          tma_load_2d(&tm_a, &sh->full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
-          tma_load_2d(&tm_b, &sh->full_bar[stage], sa + a_bytes, kb * BLOCK_K, n_blk * block_n);
+          if (csize == 1) {
+            tma_load_2d(&tm_a, &sh->full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d(&tm_b, &sh->full_bar[stage], sa + a_bytes, kb * BLOCK_K, n_blk * block_n);
+          } else {
+            tma_load_2d_mc(&tm_a, &sh->full_bar[stage], sa + (size_t)cn * a_rows * 128, kb * BLOCK_K,
+                           m_blk * BLOCK_M + cn * a_rows, mask_a);
+            tma_load_2d_mc(&tm_b, &sh->full_bar[stage], sa + a_bytes + (size_t)cm * b_rows * 128, kb * BLOCK_K,
+                           n_blk * block_n + cm * b_rows, mask_b);
+          }
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -218,7 +296,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t idesc = make_idesc(block_n, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
         mbar_wait(&sh->tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STAGE_COLS;
@@ -233,7 +311,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span (>>4 => +2)
             tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          tcgen05_commit(&sh->empty_bar[stage]);        // smem slot reusable once these MMAs retire
+          // smem slot reusable once these MMAs retire: tell every CTA that writes into it
+          if (csize == 1) tcgen05_commit(&sh->empty_bar[stage]);
+          else tcgen05_commit_mc(&sh->empty_bar[stage], mask_all);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit(&sh->tmem_full_bar[acc]);        // accumulator complete
@@ -241,42 +321,107 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    // ===================== epilogue warps =====================
+    // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter take alternate column chunks.
     const int quarter = warp & 3;
+    const int ew = warp - 2, half = ew >> 2;
+    const int et = (int)threadIdx.x - 64;
     constexpr int BOX = OutBox<OutT>::COLS;
-    uint8_t* my_stage = staging + (size_t)quarter * 2 * 4096;
-    int buf = 0;
+    constexpr int NSUB = BOX / 32;
+    uint8_t* sbuf = staging + (size_t)ew * 4096;
+    uint8_t* my_y = ybuf + (size_t)ew * 4096;
+    const uint8_t* yrow = my_y + lane * 128;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
+    int cached_nblk = -1;
+    uint32_t yit = 0;                       // RELU_BWD: y boxes consumed so far by this warp (mbarrier parity)
+    auto issue_y = [&](int st, int c0) {
+      if (lane == 0) {
+        const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
+        mbar_arrive_expect_tx(&sh->y_bar[ew], 4096);
+        tma_load_2d(&tm_y, &sh->y_bar[ew], my_y, n_blk * block_n + c0, m_blk * BLOCK_M + quarter * 32);
+      }
+    };
+    // first super tile at or after `st` in which this warp has a column chunk (ragged clusters / narrow N)
+    auto next_valid = [&](int st) {
+      while (st < num_super && ((st % sup_n) * CN + cn) * block_n + half * BOX >= N) st += num_clusters;
+      return st;
+    };
+    if (EPI == GLOWK_EPI_RELU_BWD) {
+      const int st0 = next_valid(cluster_id);
+      if (st0 < num_super) issue_y(st0, half * BOX);
+    }
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
       const int row0 = m_blk * BLOCK_M + quarter * 32;
       const int64_t m = row0 + lane;
+      if (EPI != GLOWK_EPI_STORE && n_blk != cached_nblk) {
+        // per-column scale = exp(f*logs), shift = bias*scale for this n-tile (ActNorm / Conv2dZeros epilogue)
+        epi_bar_sync();
+        if (et < block_n) {
+          const int n = n_blk * block_n + et;
+          float sc = 1.f, sf = 0.f;
+          if (n < N) { sc = expf(ep.logs[n] * ep.f); sf = ep.bias ? ep.bias[n] * sc : 0.f; }
+          s_scale[et] = sc; s_shift[et] = sf;
+        }
+        epi_bar_sync();
+        cached_nblk = n_blk;
+      }
       mbar_wait(&sh->tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_STAGE_COLS;
-      for (int c0 = 0; c0 < block_n; c0 += BOX) {
+      for (int c0 = half * BOX; c0 < block_n; c0 += 2 * BOX) {
         const int ncol0 = n_blk * block_n + c0;
         if (ncol0 >= N) break;
-        uint8_t* sbuf = my_stage + buf * 4096;
-        // the TMA store that last read this staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
+        uint32_t raw[NSUB][32];
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) tmem_ld32_async(t_row + (uint32_t)(c0 + sub * 32), raw[sub]);
+        if (EPI == GLOWK_EPI_RELU_BWD) mbar_wait(&sh->y_bar[ew], yit & 1);
+        // the TMA store that last read the staging box must have finished reading it
+        if (lane == 0) tma_store_wait_read<0>();
+        tmem_ld_wait();
         __syncwarp();
 #pragma unroll
-        for (int sub = 0; sub < BOX / 32; ++sub) {
+        for (int sub = 0; sub < NSUB; ++sub) {
           float v[32];
-          tmem_ld32(t_row + (uint32_t)(c0 + sub * 32), v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[sub][j]);
           const int nc = ncol0 + sub * 32;
+          const float* scl = s_scale + c0 + sub * 32;
+          const float* sft = s_shift + c0 + sub * 32;
           if (EPI == GLOWK_EPI_RELU_BWD) {
             float ga[32], gb[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { ga[j] = 0.f; gb[j] = 0.f; }
-            if (m < M) epilogue_apply<EPI, 32>(ep, m, nc, N, v, ga, gb);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              // this lane's row of y: 16-byte chunk (sub*4 + j4) of the 128B-swizzled box
+              const uint4 yraw = *reinterpret_cast<const uint4*>(yrow + (((sub * 4 + j4) ^ (lane & 7)) * 16));
+              const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&yraw);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 yv = __bfloat1622float2(yp[u]);
+                const int j = j4 * 8 + u * 2;
+                const float g0 = yv.x > 0.f ? v[j] : 0.f, g1 = yv.y > 0.f ? v[j + 1] : 0.f;
+                ga[j] = g0 * yv.x; ga[j + 1] = g1 * yv.y;
+                gb[j] = g0; gb[j + 1] = g1;
+                v[j] = g0 * scl[j]; v[j + 1] = g1 * scl[j + 1];
+              }
+            }
+            if (m >= M) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { ga[j] = 0.f; gb[j] = 0.f; }
+            }
             const float sa = warp_colsum32(ga, lane);
             const float sb = warp_colsum32(gb, lane);
-            if (nc + lane < N) epilogue_commit_colsums(ep, nc + lane, sa, sb);
-          } else {
-            float d0[32], d1[32];
-            if (m < M) epilogue_apply<EPI, 32>(ep, m, nc, N, v, d0, d1);
+            if (nc + lane < N) {
+              if (small_n) { atomicAdd(&s_gy[nc + lane], sa); atomicAdd(&s_g[nc + lane], sb); }
+              else epilogue_commit_colsums(ep, nc + lane, sa, sb);
+            }
+          } else if (EPI != GLOWK_EPI_STORE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float r = fmaf(v[j], scl[j], sft[j]);
+              if (EPI == GLOWK_EPI_ACTNORM_RELU) r = fmaxf(r, 0.f);
+              v[j] = r;
+            }
           }
           // write this lane's row segment into the 128B-swizzled staging box
           uint8_t* srow = sbuf + lane * 128;
@@ -297,24 +442,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             }
           }
         }
+        if (EPI == GLOWK_EPI_RELU_BWD) {
+          // y box consumed: fetch this warp's next one (same tile or the next) behind the store below
+          ++yit;
+          __syncwarp();
+          int nst = st, nc0 = c0 + 2 * BOX;
+          if (nc0 >= block_n || n_blk * block_n + nc0 >= N) { nst = next_valid(st + num_clusters); nc0 = half * BOX; }
+          if (nst < num_super) issue_y(nst, nc0);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
           tma_store_2d(&tm_o, sbuf, ncol0, row0);   // rows >= M and columns >= N are clipped by TMA
           tma_store_commit();
         }
-        buf ^= 1;
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI == GLOWK_EPI_RELU_BWD && small_n) {
+      // one global atomic per column per CTA: dlogs += f * sum g*y ; dbias += exp(f*logs) * sum g
+      epi_bar_sync();
+      for (int n = et; n < N; n += 32 * EPI_WARPS) {
+        const float a = s_gy[n], b = s_g[n];
+        if (a != 0.f || b != 0.f) epilogue_commit_colsums(ep, n, a, b);
+      }
+    }
     if (lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();        // no CTA may exit while peers still multicast into it
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -326,15 +487,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // forward pass stored them ([pixels][channels]) => MN-major UMMA operands.  Work item = (output tile,
 // pixel chunk); partial tiles are accumulated with red.global.add.f32.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int P,
-                int Mo, int No, int block_n, int num_stages, int kb_per_item, float* __restrict__ dW, int64_t lddw) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                const __grid_constant__ CUtensorMap tm_d, int P, int Mo, int No, int block_n, int num_stages,
+                int kb_per_item) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;                 // two [64 k][64 m] boxes
   const uint32_t b_bytes = (uint32_t)block_n * BLOCK_K * 2;       // block_n/64 boxes
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  Shared* sh = reinterpret_cast<Shared*>(smem + (size_t)num_stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)num_stages * stage_bytes;     // one [32][32] fp32 box per epilogue warp
+  Shared* sh = reinterpret_cast<Shared*>(staging + STAGING_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (Mo + BLOCK_M - 1) / BLOCK_M;
@@ -343,10 +505,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int k_items = (total_kb + kb_per_item - 1) / kb_per_item;
   const int num_items = m_blocks * n_blocks * k_items;
 
+  if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b);
+    prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_d);
     for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -412,25 +575,38 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
     }
   } else {
+    // epilogue: TMEM -> registers -> 128B-swizzled staging box -> TMA reduce-add (fp32) into dW.  The
+    // reduction runs in L2 on whole 32x32 boxes instead of one scattered atomic per element.
     const int quarter = warp & 3;
+    const int ew = warp - 2, half = ew >> 2;
+    uint8_t* sbuf = staging + (size_t)ew * 4096;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int tile = item / k_items;
       const int m_blk = tile / n_blocks, n_blk = tile - m_blk * n_blocks;
-      const int mrow = m_blk * BLOCK_M + quarter * 32 + lane;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
       mbar_wait(&sh->tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_STAGE_COLS;
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
+      for (int c0 = half * 32; c0 < block_n; c0 += 64) {
         const int nc = n_blk * block_n + c0;
         if (nc >= No) break;
-        float v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
-        if (mrow < Mo) {
-          float* d = dW + (int64_t)mrow * lddw + nc;
+        uint32_t raw[32];
+        tmem_ld32_async(t_row + (uint32_t)c0, raw);
+        if (lane == 0) tma_store_wait_read<0>();
+        tmem_ld_wait();
+        __syncwarp();
+        uint8_t* srow = sbuf + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (nc + j < No) atomicAdd(d + j, v[j]);
+        for (int j = 0; j < 8; ++j) {
+          const int chunk = j ^ (lane & 7);
+          *reinterpret_cast<uint4*>(srow + chunk * 16) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tm_d, sbuf, nc, row0);     // rows >= Mo / columns >= No are clipped
+          tma_store_commit();
         }
       }
       tcgen05_fence_before();
@@ -438,6 +614,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       if (lane == 0) mbar_arrive(&sh->tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait_all();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -483,21 +660,40 @@ static int make_map_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt
 }
 
 static int pick_stages(size_t stage_bytes, size_t extra) {
-  const size_t budget = 227 * 1024 - 1024 /*align slack*/ - sizeof(Shared) - 64 - extra;
+  const size_t budget = 227 * 1024 - extra;
   int s = (int)(budget / stage_bytes);
   if (s > MAX_STAGES) s = MAX_STAGES;
   return s;
 }
 
+static size_t gemm_fixed_smem(int epilogue) {
+  return STAGING_BYTES + 2 * 256 * sizeof(float) + sizeof(Shared) +
+         (epilogue == GLOWK_EPI_RELU_BWD ? STAGING_BYTES + 2 * EPI_NMAX * sizeof(float) : 0);
+}
+
 template <int EPI, typename OutT>
-static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, int M, int N, int K,
-                          int block_n, int stages, const EpiParams& ep, cudaStream_t st) {
-  const size_t smem = 1024 + (size_t)stages * (BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2) + STAGING_BYTES + sizeof(Shared) + 64;
+static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& ty,
+                          int M, int N, int K, int block_n, int stages, int cm, int cn, const EpiParams& ep,
+                          cudaStream_t st) {
+  const size_t smem = (size_t)stages * (BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2) + gemm_fixed_smem(EPI);
   auto kern = gemm_tc_kernel<EPI, OutT>;
   GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int tiles = (int)(ceil_div(M, BLOCK_M) * ceil_div(N, block_n));
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, NUM_THREADS, smem, st>>>(ta, tb, to, M, N, K, block_n, stages, ep);
+  const int csize = cm * cn;
+  const int64_t supers = ceil_div(ceil_div(M, BLOCK_M), cm) * ceil_div(ceil_div(N, block_n), cn);
+  int clusters = sm_count() / csize;
+  if (supers < clusters) clusters = (int)supers;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)(clusters * csize), 1, 1);
+  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = csize > 1 ? 1 : 0;
+  GLOWK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ty, M, N, K, block_n, stages, cm, cn, ep));
   GLOWK_CHECK_LAUNCH("glowk_gemm(tcgen05)");
   return GLOWK_OK;
 }
@@ -511,41 +707,64 @@ bool tc_available() {
   return major == 10 && tc::encode_fn() != nullptr;
 }
 
+// Cluster shape heuristic: share the B (weight) tile among `cm` m-tiles and the A tile among `cn` n-tiles
+// whenever the problem has enough tiles; measured on B200 the 128x256 tiles are L2->SM bandwidth bound
+// without it.
+static void default_cluster(int64_t m_blocks, int64_t n_blocks, int block_n, int* cm, int* cn) {
+  *cm = 1; *cn = 1;
+  const char* e = getenv("GLOWK_GEMM_CLUSTER");      // "CMxCN" override for experiments (read per call, no state)
+  if (e && e[0] >= '1' && e[0] <= '8' && e[1] == 'x' && e[2] >= '1' && e[2] <= '8') { *cm = e[0] - '0'; *cn = e[2] - '0'; }
+  if (*cn > n_blocks) *cn = 1;
+  while (*cm > 1 && (m_blocks < 2 * *cm * 16 || block_n % (8 * *cm) != 0)) *cm /= 2;
+}
+
 int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t M, int64_t N, int64_t K,
-                 int epilogue, const EpiParams& ep, void* out, int out_dtype, int64_t ldo, cudaStream_t st) {
+                 int epilogue, const EpiParams& ep, void* out, int out_dtype, int64_t ldo, int cm, int cn,
+                 cudaStream_t st) {
   using namespace tc;
   GLOWK_CHECK_ARG(lda % 8 == 0 && ldb % 8 == 0, "glowk_gemm(bf16): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
   GLOWK_CHECK_ARG(((uintptr_t)A | (uintptr_t)B | (uintptr_t)out) % 16 == 0, "glowk_gemm(bf16): operands must be 16-byte aligned");
   GLOWK_CHECK_ARG(M < (1ll << 31) && N < (1 << 20) && K < (1 << 24), "glowk_gemm(bf16): shape out of range");
   const int elo = out_dtype == GLOWK_BF16 ? 2 : 4;
   GLOWK_CHECK_ARG((ldo * elo) % 16 == 0, "glowk_gemm(bf16): output row pitch must be a multiple of 16 bytes");
+  if (epilogue == GLOWK_EPI_RELU_BWD) {
+    if (out_dtype != GLOWK_BF16) return fail(GLOWK_EUNSUP, "glowk_gemm(bf16): RELU_BWD writes bf16 on the tensor-core path");
+    GLOWK_CHECK_ARG(ep.ldy % 8 == 0 && ((uintptr_t)ep.y) % 16 == 0, "glowk_gemm(bf16): y must be 16-byte aligned with ldy %% 8 == 0");
+  }
   const int box_cols = 128 / elo;
   const int npad = (int)ceil_div(N, 16) * 16;
   const int n_blocks = (int)ceil_div(npad, 256);
   int block_n = n_blocks == 1 ? npad : (int)ceil_div(ceil_div(npad, n_blocks), box_cols) * box_cols;
   GLOWK_CHECK_ARG(block_n <= 256 && block_n % 16 == 0, "glowk_gemm(bf16): cannot tile N=%lld", (long long)N);
+  if (cm <= 0 || cn <= 0) default_cluster(ceil_div(M, BLOCK_M), n_blocks, block_n, &cm, &cn);
+  GLOWK_CHECK_ARG(cm * cn <= 8 && (cm & (cm - 1)) == 0 && (cn & (cn - 1)) == 0 && block_n % (8 * cm) == 0 && cn <= 16,
+                  "glowk_gemm(bf16): bad cluster shape %dx%d for block_n=%d", cm, cn, block_n);
   const size_t stage_bytes = BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2;
-  const int stages = pick_stages(stage_bytes, STAGING_BYTES);
+  const int stages = pick_stages(stage_bytes, gemm_fixed_smem(epilogue));
   GLOWK_CHECK_ARG(stages >= 2, "glowk_gemm(bf16): not enough shared memory for a 2-stage pipeline");
 
-  CUtensorMap ta, tb, to;
+  CUtensorMap ta, tb, to, ty;
   int rc;
-  if ((rc = make_map_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M))) return rc;
-  if ((rc = make_map_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, (uint32_t)block_n))) return rc;
+  if ((rc = make_map_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, (uint32_t)(BLOCK_M / cn)))) return rc;
+  if ((rc = make_map_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, (uint32_t)(block_n / cm)))) return rc;
   if ((rc = make_map_2d(&to, out, out_dtype == GLOWK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         elo, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, (uint32_t)box_cols, 32))) return rc;
+  ty = to;
+  if (epilogue == GLOWK_EPI_RELU_BWD &&
+      (rc = make_map_2d(&ty, ep.y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldy, 64, 32))) return rc;
 
-#define GLOWK_TC_CASE(E)                                                                                         \
-  case E:                                                                                                        \
-    return out_dtype == GLOWK_BF16                                                                               \
-               ? launch_gemm_tc<E, __nv_bfloat16>(ta, tb, to, (int)M, (int)N, (int)K, block_n, stages, ep, st)   \
-               : launch_gemm_tc<E, float>(ta, tb, to, (int)M, (int)N, (int)K, block_n, stages, ep, st);
+#define GLOWK_TC_CASE(E)                                                                                                  \
+  case E:                                                                                                                 \
+    return out_dtype == GLOWK_BF16                                                                                        \
+               ? launch_gemm_tc<E, __nv_bfloat16>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st) \
+               : launch_gemm_tc<E, float>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
   switch (epilogue) {
     GLOWK_TC_CASE(GLOWK_EPI_STORE)
     GLOWK_TC_CASE(GLOWK_EPI_ACTNORM_RELU)
     GLOWK_TC_CASE(GLOWK_EPI_ACTNORM)
     GLOWK_TC_CASE(GLOWK_EPI_ZEROS)
-    GLOWK_TC_CASE(GLOWK_EPI_RELU_BWD)
+    case GLOWK_EPI_RELU_BWD:
+      return launch_gemm_tc<GLOWK_EPI_RELU_BWD, __nv_bfloat16>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
   }
 #undef GLOWK_TC_CASE
   return fail(GLOWK_EINVAL, "glowk_gemm: unknown epilogue %d", epilogue);
@@ -560,7 +779,7 @@ int wgrad_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_
   const int n_blocks = (int)ceil_div(No, 256);
   const int block_n = (int)ceil_div(ceil_div(No, n_blocks), 64) * 64;
   const size_t stage_bytes = BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2;
-  const int stages = pick_stages(stage_bytes, 0);
+  const int stages = pick_stages(stage_bytes, STAGING_BYTES + sizeof(Shared));
   const int tiles = (int)(ceil_div(Mo, BLOCK_M) * n_blocks);
   const int total_kb = (int)ceil_div(P, BLOCK_K);
   int k_items = (int)ceil_div(2 * sm_count(), tiles);
@@ -568,16 +787,18 @@ int wgrad_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_
   int kb_per_item = (int)ceil_div(total_kb, k_items);
   if (kb_per_item < 4) kb_per_item = total_kb < 4 ? total_kb : 4;
   k_items = (int)ceil_div(total_kb, kb_per_item);
-  CUtensorMap ta, tb;
+  GLOWK_CHECK_ARG(((uintptr_t)dW) % 16 == 0 && lddw % 4 == 0, "glowk_gemm_wgrad(bf16): dW must be 16-byte aligned with lddw %% 4 == 0");
+  CUtensorMap ta, tb, td;
   int rc;
   // [P][Mo] row-major: inner dimension = channels (64-wide boxes), outer = pixels (64 per stage)
   if ((rc = make_map_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)Mo, (uint64_t)P, (uint64_t)lda, 64, BLOCK_K))) return rc;
   if ((rc = make_map_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)No, (uint64_t)P, (uint64_t)ldb, 64, BLOCK_K))) return rc;
-  const size_t smem = 1024 + (size_t)stages * stage_bytes + sizeof(Shared) + 64;
+  if ((rc = make_map_2d(&td, dW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)No, (uint64_t)Mo, (uint64_t)lddw, 32, 32))) return rc;
+  const size_t smem = (size_t)stages * stage_bytes + STAGING_BYTES + sizeof(Shared);
   GLOWK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = tiles * k_items;
   const int grid = items < sm_count() ? items : sm_count();
-  wgrad_tc_kernel<<<grid, NUM_THREADS, smem, st>>>(ta, tb, (int)P, (int)Mo, (int)No, block_n, stages, kb_per_item, dW, lddw);
+  wgrad_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, td, (int)P, (int)Mo, (int)No, block_n, stages, kb_per_item);
   GLOWK_CHECK_LAUNCH("glowk_gemm_wgrad(tcgen05)");
   return GLOWK_OK;
 }

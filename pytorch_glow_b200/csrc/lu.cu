@@ -50,13 +50,20 @@ __device__ void lu_factor_inplace(double* A, int* perm, int C, double* logabs_ou
   *logabs_out = logabs;
 }
 
+// grid.x = number of matrices (one CTA each): the 96 invconv weights of a K=32, L=3 model are factorised
+// by three launches (one per channel count) instead of 96 host-synchronising cuSOLVER calls.
 __global__ void invconv_prepare_kernel(const float* __restrict__ w, int C, float* __restrict__ logabsdet_out,
                                        float* __restrict__ winv_out, double* gwork) {
   extern __shared__ __align__(16) unsigned char lu_smem[];
   double* A;
   double* X;
   int* perm;
+  const size_t mat = blockIdx.x;
+  w += mat * C * C;
+  logabsdet_out += mat;
+  if (winv_out) winv_out += mat * C * C;
   if (gwork) {
+    gwork += mat * 2 * (size_t)C * C;
     A = gwork; X = gwork + (size_t)C * C; perm = reinterpret_cast<int*>(lu_smem);
   } else {
     A = reinterpret_cast<double*>(lu_smem);
@@ -138,20 +145,27 @@ using namespace glowk;
 // inverse, C <= 160 without); otherwise in a per-call device allocation from the stream-ordered
 // pool (cudaMallocAsync), which neither synchronises nor keeps global state.
 extern "C" int glowk_invconv_prepare(const float* w, int64_t C, float* logabsdet_out, float* winv_out, void* stream) {
+  return glowk_invconv_prepare_batched(w, 1, C, logabsdet_out, winv_out, stream);
+}
+
+extern "C" int glowk_invconv_prepare_batched(const float* w, int64_t batch, int64_t C, float* logabsdet_out,
+                                             float* winv_out, void* stream) {
+  if (batch == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(w && logabsdet_out, "glowk_invconv_prepare: null pointer");
   GLOWK_CHECK_ARG(C > 0 && C <= 1024, "glowk_invconv_prepare: C=%lld out of range", (long long)C);
+  GLOWK_CHECK_ARG(batch > 0 && batch <= 65535, "glowk_invconv_prepare: batch=%lld out of range", (long long)batch);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t mats = winv_out ? 2 : 1;
   size_t smem = mats * (size_t)C * C * sizeof(double) + (size_t)C * sizeof(int);
   double* gwork = nullptr;
   if (smem > 200 * 1024) {
-    GLOWK_CUDA(cudaMallocAsync((void**)&gwork, 2 * (size_t)C * C * sizeof(double), st));
+    GLOWK_CUDA(cudaMallocAsync((void**)&gwork, (size_t)batch * 2 * (size_t)C * C * sizeof(double), st));
     smem = (size_t)C * sizeof(int);
   }
   if (smem > 48 * 1024)
     GLOWK_CUDA(cudaFuncSetAttribute(invconv_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = C <= 16 ? 64 : (C <= 48 ? 128 : 256);
-  invconv_prepare_kernel<<<1, threads, smem, st>>>(w, (int)C, logabsdet_out, winv_out, gwork);
+  invconv_prepare_kernel<<<(unsigned)batch, threads, smem, st>>>(w, (int)C, logabsdet_out, winv_out, gwork);
   cudaError_t e = cudaGetLastError();
   if (gwork) cudaFreeAsync(gwork, st);
   if (e != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_invconv_prepare: %s", cudaGetErrorString(e));

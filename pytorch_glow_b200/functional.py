@@ -69,6 +69,17 @@ def invconv_prepare(weight, need_inverse):
     return logabsdet, winv
 
 
+def invconv_prepare_batched(weights, need_inverse):
+    """weights: [B][C][C] -> (log|det| [B], inverses [B][C][C] or None) in one launch."""
+    check_cuda(weights)
+    w = _f32c(weights)
+    b, c, _ = w.shape
+    logabsdet = torch.empty(b, device=w.device, dtype=torch.float32)
+    winv = torch.empty_like(w) if need_inverse else None
+    call("glowk_invconv_prepare_batched", ptr(w), b, c, ptr(logabsdet), ptr(winv))
+    return logabsdet, winv
+
+
 def invconv_lu_assemble(p, l, u, sign_s, log_s, need_inverse):
     """W = P L (U + diag(sign_s exp(log_s))), optional W^-1, sum(log_s)."""
     check_cuda(p, l, u, sign_s, log_s)
@@ -168,7 +179,7 @@ def pack_conv_weight(weight, layout, dtype, rows, ld):
 
 # ------------------------------------------------------------------ GEMMs
 def gemm(a, b, n, k, epilogue=_C.EPI_STORE, bias=None, logs=None, logscale_factor=3.0, y=None,
-         dlogs=None, dbias=None, out_dtype=F32, ldo=None, out=None):
+         dlogs=None, dbias=None, out_dtype=F32, ldo=None, out=None, cluster=None):
     """out[M][n] = epilogue(a[M][:k] . b[:n][:k]^T).  a, b: 2-D row-major, same dtype."""
     check_cuda(a, b)
     assert a.dim() == 2 and b.dim() == 2 and a.dtype == b.dtype
@@ -177,9 +188,10 @@ def gemm(a, b, n, k, epilogue=_C.EPI_STORE, bias=None, logs=None, logscale_facto
     ldo = n if ldo is None else ldo
     if out is None:
         out = torch.empty(m, ldo, device=a.device, dtype=TORCH_DTYPE[out_dtype])
-    call("glowk_gemm", ptr(a), a.shape[1], ptr(b), b.shape[1], dt, m, n, k, int(epilogue), ptr(bias), ptr(logs),
+    cm, cn = cluster or (0, 0)
+    call("glowk_gemm_ex", ptr(a), a.shape[1], ptr(b), b.shape[1], dt, m, n, k, int(epilogue), ptr(bias), ptr(logs),
          float(logscale_factor), ptr(y), 0 if y is None else y.shape[1], ptr(dlogs), ptr(dbias), ptr(out),
-         out_dtype, ldo)
+         out_dtype, ldo, int(cm), int(cn))
     return out
 
 

@@ -155,8 +155,28 @@ class FlowModel(nn.Module):
             if isinstance(mine, FlowStep) and mine.permutation != 'invconv':
                 mine.perm_module.set_indices(getattr(theirs, mine.permutation).indices)
 
+    def prepare_invconvs(self, need_inverse):
+        """Factorise every stale dense invconv weight now, one launch per channel count
+        (glowk_invconv_prepare_batched), instead of one LU per FlowStep call (module.py:357,365)."""
+        groups = {}
+        for layer in self.layers:
+            if isinstance(layer, FlowStep) and layer.permutation == 'invconv' and not layer.invconv.lu_decomposition:
+                ic = layer.invconv
+                if ic.weight.is_cuda and not ic._cache.fresh(("dense", need_inverse), ic.weight):
+                    groups.setdefault((ic.num_channels, ic.weight.device), []).append(ic)
+        for (c, _), mods in groups.items():
+            if len(mods) == 1:
+                continue                      # the per-module path handles it
+            w = torch.stack([m.weight.detach() for m in mods])
+            ld, winv = K.invconv_prepare_batched(w, need_inverse)
+            for i, m in enumerate(mods):
+                m._cache.put(("dense", need_inverse), m.weight, (ld[i:i + 1], None if winv is None else winv[i]))
+
     def encode(self, z, logdet=0.):
-        if torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters())):
+        use_autograd = torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if z.is_cuda:
+            self.prepare_invconvs(need_inverse=use_autograd)      # the adjoint needs W^-T (logdet term)
+        if use_autograd:
             from .autograd import flow_encode_autograd
             _C.check_cuda(z)
             return flow_encode_autograd(self, z, logdet)      # the whole encode is one autograd node
@@ -167,6 +187,8 @@ class FlowModel(nn.Module):
     def decode(self, z, eps_std=None, eps_list=None):
         """model.py:278-294.  `eps_list` optionally supplies the Split2d noise (deepest split first)."""
         k = 0
+        if z.is_cuda:
+            self.prepare_invconvs(need_inverse=True)
         for layer in reversed(self.layers):
             if isinstance(layer, module.Split2d):
                 e = None if eps_list is None else eps_list[k]

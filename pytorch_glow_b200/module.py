@@ -60,6 +60,13 @@ class _PackCache:
         self._d[key] = (tag, val)
         return val
 
+    def fresh(self, key, param):
+        hit = self._d.get(key)
+        return hit is not None and hit[0] == (param.data_ptr(), param._version, param.device, _WEIGHT_GENERATION[0])
+
+    def put(self, key, param, val):
+        self._d[key] = ((param.data_ptr(), param._version, param.device, _WEIGHT_GENERATION[0]), val)
+
     def clear(self):
         self._d.clear()
 

@@ -166,10 +166,13 @@ class FusedTrainStep:
         torch.cuda.synchronize()
         self.arena.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
         _module.bump_weight_generation()
+        from . import _C
+        c0 = _C.launch_count
         self._g_fb = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_fb):
             self._static_loss = self._forward_backward(self._static_x)
         self._g_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._g_opt):
             self._optimizer()
+        self.captured_calls = _C.launch_count - c0     # glowk C-ABI launches replayed per step
         # the captures above only recorded; nothing has executed yet
