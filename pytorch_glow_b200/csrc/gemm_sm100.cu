@@ -64,15 +64,20 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug must surface as a launch error (trap), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a launch error (trap), never as a hung GPU.  The clock is
+// only consulted every 64K failed polls: reading %globaltimer on every contended wait put several hundred
+// cycles on the critical path of each pipeline hand-off (measured: 490 cycles per k-block in an empty pipeline).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
   uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (((++spins) & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      printf("glowk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-      __trap();
+    if (((++spins) & 0xffff) == 0) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {
+        printf("glowk: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+        __trap();
+      }
     }
   }
 }
@@ -215,7 +220,7 @@ template <int EPI, typename OutT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_y, int M, int N,
-               int K, int block_n, int num_stages, int CM, int CN, EpiParams ep) {
+               int K, int block_n, int num_stages, int CM, int CN, int dbg, EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
   const uint32_t b_bytes = (uint32_t)block_n * BLOCK_K * 2;
@@ -271,11 +276,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const int a_rows = BLOCK_M / CN, b_rows = block_n / CM;
-      for (int st = cluster_id; st < num_super; st += num_clusters) {
+      for (int st = cluster_id; st < num_super && !(dbg & 8); st += num_clusters) {
         const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&sh->empty_bar[stage], phase ^ 1);     // every CTA I write into has drained this slot
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          if ((dbg & 1) && (st != cluster_id || kb >= num_stages)) {     // profiling aid: no operand traffic
+            mbar_arrive(&sh->full_bar[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&sh->full_bar[stage], stage_bytes);
           if (csize == 1) {
             tma_load_2d(&tm_a, &sh->full_bar[stage], sa, kb * BLOCK_K, m_blk * BLOCK_M);
@@ -301,18 +311,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STAGE_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&sh->full_bar[stage], phase);
+          if (!(dbg & 8)) mbar_wait(&sh->full_bar[stage], phase);   // dbg 8: free-running MMA issue (raw tensor rate)
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + a_bytes, 16, 1024);
+          if (!(dbg & 2)) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span (>>4 => +2)
-            tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span (>>4 => +2)
+              tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
           }
           // smem slot reusable once these MMAs retire: tell every CTA that writes into it
-          if (csize == 1) tcgen05_commit(&sh->empty_bar[stage]);
+          if (dbg & 8) {}
+          else if (csize == 1) tcgen05_commit(&sh->empty_bar[stage]);
           else tcgen05_commit_mc(&sh->empty_bar[stage], mask_all);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
@@ -371,7 +384,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_STAGE_COLS;
       for (int c0 = half * BOX; c0 < block_n; c0 += 2 * BOX) {
         const int ncol0 = n_blk * block_n + c0;
-        if (ncol0 >= N) break;
+        if (ncol0 >= N || (dbg & 4)) break;
         uint32_t raw[NSUB][32];
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub) tmem_ld32_async(t_row + (uint32_t)(c0 + sub * 32), raw[sub]);
@@ -693,7 +706,9 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = csize > 1 ? 1 : 0;
-  GLOWK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ty, M, N, K, block_n, stages, cm, cn, ep));
+  const char* dbg_env = getenv("GLOWK_GEMM_DEBUG");      // profiling aid (1: no loads, 2: no MMA, 4: no epilogue)
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
+  GLOWK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ty, M, N, K, block_n, stages, cm, cn, dbg, ep));
   GLOWK_CHECK_LAUNCH("glowk_gemm(tcgen05)");
   return GLOWK_OK;
 }
