@@ -219,6 +219,75 @@ int glowk_optim_adam(float* params, float* grads, float* exp_avg, float* exp_avg
                      const float* norm_coef, const float* sched_dev, float lr, float beta1, float beta2,
                      float eps, int64_t step, void* stream);
 
+/* =========================== pixel-major ("rows") flow state ================================
+ * FlowModel.encode / decode (network/model.py:263-294) keep the flow state between the NCHW tensors of
+ * the reference API as rows x[p][c] (p = (n*H + y)*W + x, c contiguous, fp32) -- the layout of every
+ * coupling-network GEMM operand -- so each kernel below reads and writes whole contiguous pixels.
+ * Element arithmetic is identical to the NCHW entry points above; only reduction orders differ.
+ * All of them need C %% 4 == 0 and C <= glowk_rows_max_channels(). */
+int glowk_rows_max_channels(void);
+
+/* glowk_actnorm_mix on rows: x, z: [P][C] (model.py:94-103 fwd / 142-152 rev). */
+int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, const int64_t* idx, const float* bias,
+                           const float* logs, float logscale_factor, int64_t P, int64_t C, int reverse, void* stream);
+
+/* glowk_coupling + glowk_logdet_finish on rows (model.py:105-115 / 131-140; module.py:77-82,357-367):
+ * z: [P][C], channels C/2.. updated in place; h_save (nullable): [P][Cout].  If ld_out is non-null:
+ * ld_out[n] = ld_in[n] + sign*HW*(sum_c an_logscale_factor*an_logs[c] + logabsdet[0]) + sum log(scale)
+ * (an_logs / logabsdet / ld_in nullable), reduced deterministically through `partials`
+ * ([N][glowk_rows_coupling_nblk(HW, C)] floats) by the last CTA of each sample; `tickets` is N uint32
+ * that must be zero on entry and are left zero. */
+int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C);
+int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bias3, const float* logs3, float logscale_factor,
+                        float* z, float* h_save, int64_t N, int64_t C, int64_t H, int64_t W, int affine, int reverse,
+                        const float* ld_in, float* ld_out, const float* an_logs, float an_logscale_factor,
+                        const float* logabsdet, float sign, float* partials, void* tickets, void* stream);
+
+/* glowk_coupling_bwd on rows: y, dy, dz: [P][C]; hrows, du: [P][Cout]. */
+int glowk_rows_coupling_bwd(const float* y, const float* hrows, const float* dy, const float* dld, const float* logs3,
+                            float logscale_factor, float* dz, float* du, float* dlogs3, float* dbias3, int64_t N,
+                            int64_t C, int64_t HW, int affine, void* stream);
+
+/* glowk_actnorm_mix_bwd on rows, with the conv1 dgrad folded into the load of dz:
+ * dz[p][c] += sum_tap dA1[nbr(p, 8-tap)][tap*Cin + c] for c < Cin (dA1: [P][ld_a1] fp32, the dgrad GEMM of the
+ * coupling net's first conv in im2col form; nullable) -- i.e. glowk_tapsum_to_nchw(flip=1, accumulate=1). */
+int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const float* dA1, int64_t ld_a1, int64_t Cin,
+                               const float* w, const int64_t* idx, const float* bias, const float* logs,
+                               float logscale_factor, float* dx, float* dw, float* dlogs, float* dbias, int64_t N,
+                               int64_t C, int64_t H, int64_t W, void* stream);
+
+/* glowk_gaussian_logp on rows: x: [P][ldx], channels c0..c0+Cz; h: [P][ldh] or null (N(0,I)). */
+int glowk_rows_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t ldx, int64_t N, int64_t HW,
+                             int64_t c0, int64_t Cz, const float* logdet_in, float* logdet_out, void* stream);
+/* glowk_split2d_sample on rows: z1: [P][ldz1] (first Chalf channels), out: [P][2*Chalf]; eps stays NCHW
+ * [N,Chalf,H,W] (drawn by torch's generator in the reference's element order, module.py:419-421). */
+int glowk_rows_split2d_sample(const float* h, int64_t ldh, const float* z1, int64_t ldz1, const float* eps, float* out,
+                              int64_t N, int64_t Chalf, int64_t HW, void* stream);
+/* glowk_split2d_bwd on rows: writes channels C/2.. of dx ([P][C]) and du ([P][ldu]); channels 0..C/2-1 of dx
+ * (the gradient of the returned z1) are written by glowk_rows_squeeze beforehand. */
+int glowk_rows_split2d_bwd(const float* x, const float* hrows, int64_t ldh, const float* dld, const float* logs_p,
+                           float logscale_factor, float* dx, float* du, int64_t ldu, float* dlogs_p, float* dbias_p,
+                           int64_t N, int64_t C, int64_t HW, void* stream);
+
+/* glowk_tapsum_to_nchw on rows: dst[p][c0 + c] (+)= sum_tap P[nbr(p, tap)][tap*C + c]; dst: [P][ld_dst]. */
+int glowk_rows_tapsum(const float* P, int64_t ldp, float* dst, int64_t ld_dst, int64_t c0, int64_t C, int64_t N,
+                      int64_t H, int64_t W, int flip, int accumulate, void* stream);
+
+/* Squeeze2d / unsqueeze (module.py:551-591, bit-exact) between layouts.  `full` = [N,C,H,W],
+ * `squeezed` = [N,C*f*f,H/f,W/f]; reverse=0 reads full (src) and writes squeezed (dst), reverse=1 the
+ * other way.  Each side is NCHW (layout 0; ld = batch stride in elements) or rows (layout 1; ld = row
+ * pitch in floats, >= that side's channel count: only its first channels are touched).  factor=1 is a
+ * pure layout change. */
+int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* dst, int dst_layout, int64_t dst_ld,
+                       int64_t N, int64_t C, int64_t H, int64_t W, int factor, int reverse, void* stream);
+
+/* One launch for many glowk_pack_conv_weight / glowk_unpack_weight_grad calls.  jobs: device array of
+ *   struct { const float* w; void* packed; int32 O, I, ks, layout, rows, ld; int64 block0; }   (48 bytes)
+ * sorted by block0 = index of the job's first CTA (256 elements per CTA: rows*ld elements when packing,
+ * O*I*ks*ks when unpacking); total_blocks = sum over jobs.  Unpack ACCUMULATES into w (a gradient). */
+int glowk_pack_conv_weights_batched(const void* jobs, int64_t njobs, int64_t total_blocks, int act_dtype, void* stream);
+int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs, int64_t total_blocks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

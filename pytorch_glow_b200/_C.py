@@ -54,8 +54,24 @@ SIGNATURES = {
     "glowk_optim_workspace_floats": [],
     "glowk_optim_clip_norm": [_p, _i64, _f32, _f32, _p, _p],
     "glowk_optim_adam": [_p, _p, _p, _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _i64, _p],
+    "glowk_rows_max_channels": [],
+    "glowk_rows_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p],
+    "glowk_rows_coupling_nblk": [_i64, _i64],
+    "glowk_rows_coupling": [_p, _i64, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _f32,
+                            _p, _f32, _p, _p, _p],
+    "glowk_rows_coupling_bwd": [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p],
+    "glowk_rows_actnorm_mix_bwd": [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _i64, _i64, _i64,
+                                   _i64, _p],
+    "glowk_rows_gaussian_logp": [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p],
+    "glowk_rows_split2d_sample": [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _p],
+    "glowk_rows_split2d_bwd": [_p, _p, _i64, _p, _p, _f32, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _p],
+    "glowk_rows_tapsum": [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
+    "glowk_rows_squeeze": [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
+    "glowk_pack_conv_weights_batched": [_p, _i64, _i64, _i32, _p],
+    "glowk_unpack_weight_grads_batched": [_p, _i64, _i64, _p],
 }
-_RESTYPES = {"glowk_last_error": _c.c_char_p, "glowk_coupling_nblk": _i64, "glowk_optim_workspace_floats": _i64}
+_RESTYPES = {"glowk_last_error": _c.c_char_p, "glowk_coupling_nblk": _i64, "glowk_optim_workspace_floats": _i64,
+             "glowk_rows_coupling_nblk": _i64}
 
 _lib = None
 launch_count = 0  # kernels-launching C-ABI calls made by this process (bench.py's gpu_launches claim)

@@ -8,7 +8,7 @@ relies on torch autograd over ~170 ATen ops per step (network/trainer.py:138-140
 """
 import torch
 
-from . import _C
+from . import _C, config
 from . import functional as K
 from .functional import round_up
 
@@ -149,9 +149,17 @@ class FlowEncodeFunction(torch.autograd.Function):
     def forward(ctx, flow, z, logdet, *params):
         from .model import FlowStep
         from .module import Split2d, Squeeze2d
+        from . import rows_path
         z = z.detach().contiguous()
         ld = None if logdet is None else logdet.detach().contiguous()
+        ctx.flow = flow
+        ctx.rows = config.use_rows_path and rows_path.supported(flow, z)
         tape = []
+        if ctx.rows:
+            z, ld = rows_path.encode(flow, z, ld, tape)
+            ctx.tape = tape
+            ctx.has_ld = ld is not None
+            return z if ld is None else (z, ld)
         for layer in flow.layers:
             if isinstance(layer, Squeeze2d):
                 z = K.squeeze2d(z, layer.factor, reverse=False)
@@ -174,11 +182,16 @@ class FlowEncodeFunction(torch.autograd.Function):
     def backward(ctx, dz, dld=None):
         from .model import FlowStep
         from .module import Split2d
+        from . import rows_path
         if dz is None:
             raise RuntimeError("FlowModel.encode: the latent z must take part in the loss")
         dz = dz.contiguous()
         if dld is not None:
             dld = dld.contiguous()
+        if ctx.rows:
+            dx = rows_path.backward(ctx.flow, ctx.tape, dz, dld)
+            ctx.tape = None
+            return (None, dx, dld) + (None,) * (len(ctx.needs_input_grad) - 3)
         for layer, c in reversed(ctx.tape):
             if c is None:
                 dz = K.squeeze2d(dz, layer.factor, reverse=True)

@@ -7,6 +7,10 @@ from . import _C
 #   "auto": bf16 whenever the layer shape fits the tensor-core tiling, else fp32.
 conv_dtype = "auto"
 
+# FlowModel.encode / decode keep the flow state pixel-major between the NCHW tensors of the API
+# (rows_path.py) whenever the model fits those kernels; False forces the per-layer NCHW kernels.
+use_rows_path = True
+
 
 def resolve_conv_dtype(hidden_channels, override=None):
     mode = override or conv_dtype

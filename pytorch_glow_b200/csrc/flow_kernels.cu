@@ -272,24 +272,31 @@ __global__ void im2col_kernel(const float* __restrict__ src, int64_t ld_src, int
   const int64_t n = pix / HW;
   const int p = (int)(pix - n * HW);
   const int yy = p / W, xx = p - yy * W;
-  const int pad = (ks - 1) / 2, K = ks * ks * Cin;
+  const int pad = (ks - 1) / 2, T2 = ks * ks, K = T2 * Cin;
+  // walk (tap, ci) incrementally: one division per thread instead of two per element
+  int tap = k0 / Cin, ci = k0 - tap * Cin;
+  int cur_tap = -1;
+  bool inb = false;
+  const float* base = src;
   float v[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int k = k0 + u;
     float r = 0.f;
-    if (k < K) {
-      int tap = k / Cin;
-      const int ci = k - tap * Cin;
-      if (flip) tap = ks * ks - 1 - tap;
-      const int ky = tap / ks, kx = tap - ky * ks;
-      const int sy = yy + ky - pad, sx = xx + kx - pad;
-      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-        if (ROWS_SRC) r = src[(n * HW + (int64_t)sy * W + sx) * ld_src + c0 + ci];
-        else r = src[n * Ctot + ((c0 + ci) * (int64_t)H + sy) * W + sx];  // Ctot carries the batch stride
+    if (k0 + u < K) {
+      if (tap != cur_tap) {
+        const int tt = flip ? T2 - 1 - tap : tap;
+        const int ky = ks == 3 ? tt / 3 : 0, kx = tt - ky * ks;
+        const int sy = yy + ky - pad, sx = xx + kx - pad;
+        inb = sy >= 0 && sy < H && sx >= 0 && sx < W;
+        // Ctot carries the batch stride of an NCHW source
+        base = ROWS_SRC ? src + (n * HW + (int64_t)sy * W + sx) * ld_src + c0
+                        : src + n * Ctot + (c0 * (int64_t)H + sy) * W + sx;
+        cur_tap = tap;
       }
+      if (inb) r = ROWS_SRC ? base[ci] : base[(int64_t)ci * HW];
     }
     v[u] = r;
+    if (++ci == Cin) { ci = 0; ++tap; }
   }
   T* d = dst + pix * ld + k0;
   if (sizeof(T) == 2) {

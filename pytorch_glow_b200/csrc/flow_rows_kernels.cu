@@ -1,0 +1,799 @@
+// Glow flow kernels on a PIXEL-MAJOR flow state ("rows": x[p][c], p = (n*H + y)*W + x, c contiguous), sm_100a.
+//
+// FlowModel.encode / decode keep the flow state in this layout between the NCHW tensors of the
+// reference API (network/model.py:263-294): it is the layout of every coupling-network GEMM operand,
+// so ActNorm + 1x1 mix, the im2col of z1, the tap gather-sum + coupling and all their adjoints read
+// and write whole contiguous pixels (48..384 bytes) instead of C strided planes.  The arithmetic of
+// each element (operation order included) is that of the NCHW kernels in flow_kernels.cu /
+// flow_bwd_kernels.cu, so the two layouts agree bit for bit except for the order of the per-sample
+// and per-channel reductions.
+#include "common.cuh"
+
+namespace glowk {
+
+constexpr int ROWS_MAX_C = 96;   // shared-memory tiles below are sized for C <= 96 (levels 1..4 of every config)
+
+// ------------------------------------------------------------------------------------------
+// ActNorm + channel mix / permutation (model.py:94-103 fwd, 142-152 rev).
+// thread = (pixel, group of 4 output channels); the G = C/4 lanes of a pixel read the same
+// 16-byte chunks of x (one transaction) and W^T from shared memory.
+// ------------------------------------------------------------------------------------------
+template <bool PERM>
+__global__ void __launch_bounds__(256)
+rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
+                const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
+                float f, int64_t P, int C, int reverse) {
+  extern __shared__ __align__(16) float smem[];
+  float* wt = smem;                               // [C][C]: wt[i*C + o] = W[o][i]   (mix only)
+  float* sc = wt + (PERM ? 0 : C * C);            // [C] exp(+-f*logs)
+  float* bs = sc + C;                             // [C] bias
+  int* sidx = reinterpret_cast<int*>(bs + C);     // [C] (perm only)
+  const int tid = threadIdx.x;
+  const bool has_an = bias != nullptr;
+  for (int c = tid; c < C; c += 256) {
+    const float l = has_an ? logs[c] * f : 0.f;
+    sc[c] = has_an ? expf(reverse ? -l : l) : 1.f;
+    bs[c] = has_an ? bias[c] : 0.f;
+    if (PERM) sidx[c] = (int)idx[c];
+  }
+  if (!PERM)
+    for (int e = tid; e < C * C; e += 256) {
+      const int o = e / C, i = e - o * C;
+      wt[i * C + o] = w[e];
+    }
+  __syncthreads();
+  const int G = C >> 2;
+  const int64_t gid = (int64_t)blockIdx.x * 256 + tid;
+  if (gid >= P * G) return;
+  const int64_t pix = gid / G;
+  const int og = (int)(gid - pix * G);
+  const float* xr = x + pix * C;
+  float acc[4];
+  if (PERM) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int o = og * 4 + a, s = sidx[o];
+      float t = xr[s];
+      if (has_an) t = reverse ? (t * sc[o] - bs[o]) : ((t + bs[s]) * sc[s]);
+      acc[a] = t;
+    }
+  } else {
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    for (int i = 0; i < C; i += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + i);
+      float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+      if (!reverse && has_an) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xa[u] = (xa[u] + bs[i + u]) * sc[i + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
+        acc[0] = fmaf(wv.x, xa[u], acc[0]);
+        acc[1] = fmaf(wv.y, xa[u], acc[1]);
+        acc[2] = fmaf(wv.z, xa[u], acc[2]);
+        acc[3] = fmaf(wv.w, xa[u], acc[3]);
+      }
+    }
+    if (reverse && has_an) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) acc[a] = acc[a] * sc[og * 4 + a] - bs[og * 4 + a];
+    }
+  }
+  *reinterpret_cast<float4*>(z + pix * C + og * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tap gather-sum (second half of Conv2dZeros as nine pointwise GEMMs, module.py:295-296) + coupling
+// (model.py:105-115 fwd, 131-140 rev) + this step's logdet (module.py:77-82, 357-367; model.py:114,140).
+// grid = (nblk, N), thread = (pixel, j): lanes of a pixel read 8*Ch (affine) contiguous bytes per tap.
+// The last CTA of a sample (atomic ticket, self-resetting) sums the per-CTA partials in a fixed order:
+//   ld_out[n] = ld_in[n] + sign*HW*(sum_c f*an_logs[c] + logabsdet[0]) + sum_b partial[n][b]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __restrict__ bias3,
+                     const float* __restrict__ logs3, float f, float* __restrict__ z,
+                     float* __restrict__ h_save, int C, int H, int W, int affine, int reverse,
+                     const float* __restrict__ ld_in, float* __restrict__ ld_out,
+                     const float* __restrict__ an_logs, float an_f, const float* __restrict__ logabsdet,
+                     float sign, float* __restrict__ partials, unsigned int* __restrict__ tickets) {
+  __shared__ float red[32];
+  __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
+  __shared__ int s_last;
+  const int HW = H * W, Ch = C >> 1, Cout = affine ? C : Ch;
+  const int64_t n = blockIdx.y;
+  const int tid = threadIdx.x;
+  for (int c = tid; c < Cout; c += 256) { s_b[c] = bias3[c]; s_e[c] = expf(logs3[c] * f); }
+  __syncthreads();
+  float lsum = 0.f;
+  const int e = blockIdx.x * 256 + tid;
+  if (e < HW * Ch) {
+    const int pix = e / Ch, j = e - pix * Ch;
+    const int yy = pix / W, xx = pix - yy * W;
+    const float* Pn = P3 + n * HW * ldp;
+    float* zp = z + (n * HW + pix) * C + Ch + j;
+    if (affine) {
+      float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+          const float2 v = *reinterpret_cast<const float2*>(Pn + (int64_t)(sy * W + sx) * ldp + t * Cout + 2 * j);
+          u0 += v.x; u1 += v.y;
+        }
+      }
+      const float shift = (u0 + s_b[2 * j]) * s_e[2 * j];
+      const float hsc = (u1 + s_b[2 * j + 1]) * s_e[2 * j + 1];
+      const float scale = 1.f / (1.f + expf(-(hsc + 2.f)));   // F.sigmoid(scale + 2.)
+      float v = *zp;
+      if (!reverse) { v = (v + shift) * scale; lsum += logf(scale); }
+      else { v = v / scale - shift; lsum -= logf(scale); }
+      *zp = v;
+      if (h_save) *reinterpret_cast<float2*>(h_save + (n * HW + pix) * (int64_t)Cout + 2 * j) = make_float2(shift, hsc);
+    } else {
+      float u = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) u += Pn[(int64_t)(sy * W + sx) * ldp + t * Cout + j];
+      }
+      const float h = (u + s_b[j]) * s_e[j];
+      float v = *zp;
+      v = reverse ? v - h : v + h;
+      *zp = v;
+      if (h_save) h_save[(n * HW + pix) * (int64_t)Cout + j] = h;
+    }
+  }
+  if (!ld_out) return;
+  const float tot = block_sum(lsum, red);
+  const int nblk = gridDim.x;
+  if (tid == 0) {
+    partials[n * nblk + blockIdx.x] = tot;
+    __threadfence();
+    const unsigned int t = atomicAdd(tickets + n, 1u);
+    s_last = (t == (unsigned int)(nblk - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f;
+  if (an_logs)
+    for (int c = tid; c < C; c += 256) a += an_logs[c] * an_f;
+  const float term = block_sum(a, red);
+  if (tid == 0) {
+    float v = ld_in ? ld_in[n] : 0.f;
+    v += sign * (term * (float)HW);                              // torch.sum(logs)*HW   (module.py:78-80)
+    if (logabsdet) v += sign * (logabsdet[0] * (float)HW);       // log|det W| * HW      (module.py:357)
+    if (affine) {
+      float s = 0.f;
+      for (int b = 0; b < nblk; ++b) s += __ldcg(partials + n * nblk + b);
+      v += s;
+    }
+    ld_out[n] = v;
+    tickets[n] = 0u;                                             // ready for the next launch on this stream
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Coupling backward (see coupling_bwd_kernel in flow_bwd_kernels.cu for the formulas).
+// thread = (pixel slot, j) with j fixed over `iters` pixel groups, so the per-channel sums for
+// dlogs3 / dbias3 are accumulated in registers and reduced once per CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ hrows,
+                         const float* __restrict__ dy, const float* __restrict__ dld,
+                         const float* __restrict__ logs3, float f, float* __restrict__ dz,
+                         float* __restrict__ du, float* __restrict__ dlogs3, float* __restrict__ dbias3,
+                         int64_t NP, int C, int HW, int affine, int iters) {
+  __shared__ float s_part[4][256];
+  __shared__ float s_e[2 * ROWS_MAX_C];
+  const int Ch = C >> 1, Cout = affine ? C : Ch;
+  const int tid = threadIdx.x;
+  const int ppb = 256 / Ch;
+  for (int c = tid; c < Cout; c += 256) s_e[c] = expf(logs3[c] * f);
+  __syncthreads();
+  const int j = tid % Ch, slot = tid / Ch;
+  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+  if (slot < ppb) {
+    for (int it = 0; it < iters; ++it) {
+      const int64_t pix = ((int64_t)blockIdx.x * iters + it) * ppb + slot;
+      if (pix >= NP) break;
+      const int64_t n = pix / HW;
+      const float g = dld ? dld[n] : 0.f;
+      const int64_t o1 = pix * C + j, o2 = o1 + Ch;
+      dz[o1] = dy[o1];
+      const float dy2 = dy[o2];
+      if (affine) {
+        const float2 hv = *reinterpret_cast<const float2*>(hrows + pix * Cout + 2 * j);
+        const float h0 = hv.x, h1 = hv.y;
+        const float scale = 1.f / (1.f + expf(-(h1 + 2.f)));
+        const float zs = y[o2] / scale;            // z2 + shift
+        dz[o2] = dy2 * scale;
+        const float dh0 = dy2 * scale;
+        const float dh1 = (dy2 * zs + g / scale) * scale * (1.f - scale);
+        *reinterpret_cast<float2*>(du + pix * Cout + 2 * j) = make_float2(dh0 * s_e[2 * j], dh1 * s_e[2 * j + 1]);
+        a0 += dh0 * h0; b0 += dh0; a1 += dh1 * h1; b1 += dh1;
+      } else {
+        const float h0 = hrows[pix * Cout + j];
+        dz[o2] = dy2;
+        du[pix * Cout + j] = dy2 * s_e[j];
+        a0 += dy2 * h0; b0 += dy2;
+      }
+    }
+  }
+  s_part[0][tid] = a0; s_part[1][tid] = b0; s_part[2][tid] = a1; s_part[3][tid] = b1;
+  __syncthreads();
+  // thread (q, j): sum of quantity q over the pixel slots, then one global atomic per channel and CTA
+  const int nq = affine ? 4 : 2;
+  if (tid < nq * Ch) {
+    const int q = tid / Ch, jj = tid - q * Ch;
+    float s = 0.f;
+    for (int k = 0; k < ppb; ++k) s += s_part[q][k * Ch + jj];
+    const int c = affine ? (2 * jj + (q >> 1)) : jj;
+    if ((q & 1) == 0) atomicAdd(dlogs3 + c, f * s);
+    else atomicAdd(dbias3 + c, s_e[c] * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ActNorm + mix backward (model.py:94-103) with the conv1 dgrad tap gather-sum fused into the load:
+//   dz[p][c] += sum_tap dA1[nbr(p,tap)][tap*Cin + c]   (c < Cin; transposed conv => mirrored taps)
+//   a = (x+b)*s ; da = W^T dz ; dx = da*s ; db += sum da*s ; dlogs += f*sum da*a ; dW += sum_p dz a^T
+// Tile of 128 pixels in shared memory, rows padded to C+1 floats (conflict-free column walks).
+// ------------------------------------------------------------------------------------------
+constexpr int RMB_TP = 128;
+
+template <bool PERM>
+__global__ void __launch_bounds__(256)
+rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
+                    int64_t ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
+                    const float* __restrict__ bias, const float* __restrict__ logs, float f,
+                    float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
+                    float* __restrict__ dbias, int64_t NP, int C, int H, int W) {
+  extern __shared__ __align__(16) float smem[];
+  const int LD = C + 1;
+  float* a_s = smem;                          // [TP][LD]  a = actnorm(x)
+  float* d_s = a_s + RMB_TP * LD;             // [TP][LD]  dz, later da
+  float* ws = d_s + RMB_TP * LD;              // [C][C]    W (mix only)
+  float* sc = ws + (PERM ? 0 : C * C);        // [C]
+  float* bs = sc + C;                         // [C]
+  float* s_red = bs + C;                      // [2][C]
+  int* sinv = reinterpret_cast<int*>(s_red + 2 * C);   // [C] inverse permutation (perm only)
+  const int tid = threadIdx.x;
+  const int64_t g0 = (int64_t)blockIdx.x * RMB_TP;
+  const bool has_an = bias != nullptr;
+  const int HW = H * W;
+  for (int c = tid; c < C; c += 256) {
+    sc[c] = has_an ? expf(logs[c] * f) : 1.f;
+    bs[c] = has_an ? bias[c] : 0.f;
+    s_red[c] = 0.f; s_red[C + c] = 0.f;
+    if (PERM) sinv[(int)idx[c]] = c;          // z[o] = a[idx[o]]  =>  da[i] = dz[o] with idx[o] == i
+  }
+  if (!PERM)
+    for (int e = tid; e < C * C; e += 256) ws[e] = w[e];
+  __syncthreads();
+  // ---- stage a and dz (+ conv1 dgrad) : consecutive threads = consecutive channels of a pixel
+  for (int e = tid; e < RMB_TP * C; e += 256) {
+    const int p = e / C, c = e - p * C;
+    const int64_t pix = g0 + p;
+    float av = 0.f, dv = 0.f;
+    if (pix < NP) {
+      av = (x[pix * C + c] + bs[c]) * sc[c];
+      dv = dz[pix * C + c];
+      if (dA1 && c < Cin) {
+        const int64_t n = pix / HW;
+        const int q = (int)(pix - n * HW);
+        const int yy = q / W, xx = q - yy * W;
+        float r = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int tap = 8 - t;
+          const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+          if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+            r += dA1[(n * HW + (int64_t)sy * W + sx) * ld_a1 + t * Cin + c];
+        }
+        dv = dv + r;
+      }
+    }
+    a_s[p * LD + c] = av;
+    d_s[p * LD + c] = dv;
+  }
+  __syncthreads();
+  // ---- dW[o][i] += sum_p dz[p][o] a[p][i]
+  if (!PERM) {
+    for (int e = tid; e < C * C; e += 256) {
+      const int o = e / C, i = e - o * C;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int p = 0; p < RMB_TP; ++p) acc = fmaf(d_s[p * LD + o], a_s[p * LD + i], acc);
+      atomicAdd(dw + e, acc);
+    }
+  }
+  __syncthreads();                             // dW has read every dz element: da may now overwrite dz in place
+  // ---- da[p][i] = sum_o W[o][i] dz[p][o].  The G = C/4 threads of a pixel sit in ONE warp (32/G pixels per
+  // warp pass), so a pixel's dz row is replaced by its da row between two __syncwarp()s.
+  {
+    const int G = C >> 2;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int ppw = 32 / G;
+    const int pl = lane / G, ig = lane - pl * G;
+    for (int p0 = warp * ppw; p0 < RMB_TP; p0 += 8 * ppw) {
+      const int p = p0 + pl;
+      const bool act = pl < ppw && p < RMB_TP;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (act) {
+        if (PERM) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] = d_s[p * LD + sinv[ig * 4 + u]];
+        } else {
+          for (int o = 0; o < C; ++o) {
+            const float d = d_s[p * LD + o];
+            const float4 wv = *reinterpret_cast<const float4*>(ws + o * C + ig * 4);
+            acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]);
+            acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
+          }
+        }
+      }
+      __syncwarp();
+      if (act) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) d_s[p * LD + ig * 4 + u] = acc[u];
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- per-channel reductions over the tile's pixels
+  if (has_an) {
+    const int chunks = 256 / C;
+    if (tid < chunks * C) {
+      const int i = tid % C, ch = tid / C;
+      float sg = 0.f, sga = 0.f;
+      for (int p = ch; p < RMB_TP; p += chunks) {
+        const float d = d_s[p * LD + i];
+        sg += d; sga = fmaf(d, a_s[p * LD + i], sga);
+      }
+      atomicAdd(&s_red[i], sg);
+      atomicAdd(&s_red[C + i], sga);
+    }
+  }
+  // ---- dx = da * s, written back as whole pixels
+  for (int e = tid; e < RMB_TP * C; e += 256) {
+    const int p = e / C, c = e - p * C;
+    const int64_t pix = g0 + p;
+    if (pix < NP) dx[pix * C + c] = d_s[p * LD + c] * sc[c];
+  }
+  if (has_an) {
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+      atomicAdd(dbias + c, s_red[c] * sc[c]);
+      atomicAdd(dlogs + c, f * s_red[C + c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// GaussianDiag.logp on rows (module.py:437-467): one CTA per sample.  h == null => N(0, I).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_gaussian_logp_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ x, int64_t ldx,
+                          int HW, int c0, int Cz, const float* __restrict__ logdet_in,
+                          float* __restrict__ logdet_out) {
+  __shared__ float red[32];
+  const int64_t n = blockIdx.x;
+  const float log2pi = 1.8378770664093453f;
+  float acc = 0.f;
+  const int cnt = Cz * HW;
+  for (int e = threadIdx.x; e < cnt; e += 256) {
+    const int p = e / Cz, j = e - p * Cz;
+    const float v = x[(n * HW + p) * ldx + c0 + j];
+    float mean = 0.f, lg = 0.f;
+    if (h) {
+      const float2 ml = *reinterpret_cast<const float2*>(h + (n * HW + p) * ldh + 2 * j);
+      mean = ml.x; lg = ml.y;
+    }
+    const float d = v - mean;
+    acc += -0.5f * (log2pi + 2.f * lg + (d * d) / expf(2.f * lg));
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) logdet_out[n] = tot + (logdet_in ? logdet_in[n] : 0.f);
+}
+
+// Split2d reverse (module.py:482-483, 532-536): out[p] = cat(z1[p], mean + exp(logs) * eps); eps is NCHW
+// (torch's generator fills it in the reference's tensor order).
+__global__ void rows_split2d_sample_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ z1,
+                                           int64_t ldz1, const float* __restrict__ eps, float* __restrict__ out,
+                                           int64_t total, int Ch, int HW) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int C = 2 * Ch;
+  const int64_t pix = e / C;
+  const int c = (int)(e - pix * C);
+  float v;
+  if (c < Ch) {
+    v = z1[pix * ldz1 + c];
+  } else {
+    const int j = c - Ch;
+    const int64_t n = pix / HW, p = pix - n * HW;
+    const float2 ml = *reinterpret_cast<const float2*>(h + pix * ldh + 2 * j);
+    v = ml.x + expf(ml.y) * eps[(n * Ch + j) * HW + p];
+  }
+  out[e] = v;
+}
+
+// Split2d backward (module.py:526-530), channels C/2.. of dx and du rows; channels 0..C/2-1 of dx are
+// written by the un-squeeze of the next level's gradient (glowk_rows_squeeze) before this kernel.
+__global__ void __launch_bounds__(256)
+rows_split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ hrows, int64_t ldh,
+                        const float* __restrict__ dld, const float* __restrict__ logs_p, float f,
+                        float* __restrict__ dx, float* __restrict__ du, int64_t ldu,
+                        float* __restrict__ dlogs_p, float* __restrict__ dbias_p, int64_t NP, int C, int HW,
+                        int iters) {
+  __shared__ float s_part[4][256];
+  __shared__ float s_e[2 * ROWS_MAX_C];
+  const int Ch = C >> 1;
+  const int tid = threadIdx.x;
+  const int ppb = 256 / Ch;
+  for (int c = tid; c < C; c += 256) s_e[c] = expf(logs_p[c] * f);
+  __syncthreads();
+  const int j = tid % Ch, slot = tid / Ch;
+  float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
+  if (slot < ppb) {
+    for (int it = 0; it < iters; ++it) {
+      const int64_t pix = ((int64_t)blockIdx.x * iters + it) * ppb + slot;
+      if (pix >= NP) break;
+      const float g = dld[pix / HW];
+      const float2 hv = *reinterpret_cast<const float2*>(hrows + pix * ldh + 2 * j);
+      const float mean = hv.x, lg = hv.y;
+      const float d = x[pix * C + Ch + j] - mean;
+      const float iv = 1.f / expf(2.f * lg);
+      dx[pix * C + Ch + j] = -g * d * iv;
+      const float dm = g * d * iv;
+      const float dl = g * (d * d * iv - 1.f);
+      *reinterpret_cast<float2*>(du + pix * ldu + 2 * j) = make_float2(dm * s_e[2 * j], dl * s_e[2 * j + 1]);
+      a0 += dm * mean; b0 += dm; a1 += dl * lg; b1 += dl;
+    }
+  }
+  s_part[0][tid] = a0; s_part[1][tid] = b0; s_part[2][tid] = a1; s_part[3][tid] = b1;
+  __syncthreads();
+  if (tid < 4 * Ch) {
+    const int q = tid / Ch, jj = tid - q * Ch;
+    float s = 0.f;
+    for (int k = 0; k < ppb; ++k) s += s_part[q][k * Ch + jj];
+    const int c = 2 * jj + (q >> 1);
+    if ((q & 1) == 0) atomicAdd(dlogs_p + c, f * s);
+    else atomicAdd(dbias_p + c, s_e[c] * s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Squeeze2d / unsqueeze (module.py:551-591, bit-exact) between any two layouts.  Logical map (factor f):
+//   squeezed[n, c*f*f + fh*f + fw, i, j] = full[n, c, i*f+fh, j*f+fw]
+// `full` is [N,C,H,W], `squeezed` is [N,C*f*f,H/f,W/f]; each side is NCHW (layout 0, batch stride
+// `ld` elements) or rows (layout 1, row pitch `ld` floats: only the first channels of wider rows are
+// touched, which is how Split2d's z1 / dz1 halves are read and written in place).  reverse = 0 reads
+// `full` and writes `squeezed`; reverse = 1 the other way.  One thread per element of the destination.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t layout_off(int layout, int64_t ld, int64_t n, int c, int y, int x, int Cc, int Hh, int Ww) {
+  return layout == 0 ? n * ld + ((int64_t)c * Hh + y) * Ww + x
+                     : ((n * Hh + y) * (int64_t)Ww + x) * ld + c;
+}
+
+__global__ void rows_squeeze_kernel(const float* __restrict__ src, int src_layout, int64_t src_ld,
+                                    float* __restrict__ dst, int dst_layout, int64_t dst_ld, int64_t total,
+                                    int C, int H, int W, int f, int reverse) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int Cs = C * f * f, Hs = H / f, Ws = W / f;
+  // decode e in the DESTINATION's own element order so that writes are coalesced
+  int64_t n; int c, y, x;     // logical coordinates in the destination tensor
+  const int Cd = reverse ? C : Cs, Hd = reverse ? H : Hs, Wd = reverse ? W : Ws;
+  if (dst_layout == 0) {
+    x = (int)(e % Wd); y = (int)((e / Wd) % Hd); c = (int)((e / ((int64_t)Wd * Hd)) % Cd); n = e / ((int64_t)Wd * Hd * Cd);
+  } else {
+    c = (int)(e % Cd); x = (int)((e / Cd) % Wd); y = (int)((e / ((int64_t)Cd * Wd)) % Hd); n = e / ((int64_t)Cd * Wd * Hd);
+  }
+  int64_t so, dofs;
+  if (!reverse) {   // destination = squeezed (c = cf*f*f + fh*f + fw), source = full
+    const int cf = c / (f * f), r = c - cf * f * f, fh = r / f, fw = r - fh * f;
+    so = layout_off(src_layout, src_ld, n, cf, y * f + fh, x * f + fw, C, H, W);
+    dofs = layout_off(dst_layout, dst_ld, n, c, y, x, Cs, Hs, Ws);
+  } else {          // destination = full, source = squeezed
+    const int i = y / f, fh = y - i * f, jx = x / f, fw = x - jx * f;
+    so = layout_off(src_layout, src_ld, n, c * f * f + fh * f + fw, i, jx, Cs, Hs, Ws);
+    dofs = layout_off(dst_layout, dst_ld, n, c, y, x, C, H, W);
+  }
+  dst[dofs] = src[so];
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched conv-weight packing / gradient unpacking: one launch for every coupling network of a
+// FlowModel (a train step otherwise launches ~6 pack and ~2 unpack kernels per FlowStep).
+// ------------------------------------------------------------------------------------------
+struct PackJob {           // 48 bytes, mirrored by pytorch_glow_b200/rows_path.py
+  const float* w;          // fp32 [O][I][k][k]  (unpack: the gradient, accumulated into)
+  void* packed;            // GEMM-layout copy   (unpack: fp32 source)
+  int32_t O, I, ks, layout;
+  int32_t rows, ld;
+  int64_t block0;          // first CTA of this job (256 elements per CTA)
+};
+
+__device__ __forceinline__ int find_job(const PackJob* jobs, int njobs, int64_t blk) {
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].block0 <= blk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ bool packed_coords(int layout, int O, int I, int T2, int64_t r, int64_t col, int* o, int* i, int* tap) {
+  if (layout == 0) {            // packed[o][tap*I + i]
+    if (r < O && col < (int64_t)T2 * I) { *o = (int)r; *tap = (int)(col / I); *i = (int)(col - (int64_t)*tap * I); return true; }
+  } else if (layout == 1) {     // packed[tap*O + o][i]
+    if (r < (int64_t)T2 * O && col < I) { *tap = (int)(r / O); *o = (int)(r - (int64_t)*tap * O); *i = (int)col; return true; }
+  } else if (layout == 2) {     // packed[tap*I + i][o]
+    if (r < (int64_t)T2 * I && col < O) { *tap = (int)(r / I); *i = (int)(r - (int64_t)*tap * I); *o = (int)col; return true; }
+  } else {                      // packed[i][tap*O + o]
+    if (r < I && col < (int64_t)T2 * O) { *i = (int)r; *tap = (int)(col / O); *o = (int)(col - (int64_t)*tap * O); return true; }
+  }
+  return false;
+}
+
+template <typename T>
+__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) s_job = find_job(jobs, njobs, blockIdx.x);
+  __syncthreads();
+  const PackJob jb = jobs[s_job];
+  const int64_t e = ((int64_t)blockIdx.x - jb.block0) * 256 + threadIdx.x;
+  if (e >= (int64_t)jb.rows * jb.ld) return;
+  const int64_t r = e / jb.ld, col = e - r * jb.ld;
+  const int T2 = jb.ks * jb.ks;
+  int o, i, tap;
+  float v = 0.f;
+  if (packed_coords(jb.layout, jb.O, jb.I, T2, r, col, &o, &i, &tap)) v = jb.w[((int64_t)o * jb.I + i) * T2 + tap];
+  reinterpret_cast<T*>(jb.packed)[e] = from_f32<T>(v);
+}
+
+__global__ void unpack_grads_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ int s_job;
+  if (threadIdx.x == 0) s_job = find_job(jobs, njobs, blockIdx.x);
+  __syncthreads();
+  const PackJob jb = jobs[s_job];
+  const int64_t e = ((int64_t)blockIdx.x - jb.block0) * 256 + threadIdx.x;
+  const int T2 = jb.ks * jb.ks;
+  if (e >= (int64_t)jb.O * jb.I * T2) return;
+  const int tap = (int)(e % T2);
+  const int i = (int)((e / T2) % jb.I);
+  const int o = (int)(e / ((int64_t)T2 * jb.I));
+  int64_t s;
+  if (jb.layout == 0) s = (int64_t)o * jb.ld + (int64_t)tap * jb.I + i;
+  else if (jb.layout == 1) s = ((int64_t)tap * jb.O + o) * jb.ld + i;
+  else if (jb.layout == 2) s = ((int64_t)tap * jb.I + i) * jb.ld + o;
+  else s = (int64_t)i * jb.ld + (int64_t)tap * jb.O + o;
+  float* g = const_cast<float*>(jb.w);
+  g[e] += reinterpret_cast<const float*>(jb.packed)[s];
+}
+
+}  // namespace glowk
+
+using namespace glowk;
+
+// ============================================================================================
+// C ABI
+// ============================================================================================
+static inline int bwd_iters(int64_t NP, int ppb) {
+  int64_t it = NP / ((int64_t)ppb * 2 * sm_count());
+  if (it < 1) it = 1;
+  if (it > 8) it = 8;
+  return (int)it;
+}
+
+extern "C" int glowk_rows_max_channels(void) { return ROWS_MAX_C; }
+
+extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, const int64_t* idx,
+                                      const float* bias, const float* logs, float logscale_factor, int64_t P,
+                                      int64_t C, int reverse, void* stream) {
+  if (P == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(x && z && x != z, "glowk_rows_actnorm_mix: bad pointers");
+  GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_rows_actnorm_mix: exactly one of w / idx");
+  GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr), "glowk_rows_actnorm_mix: bias and logs go together");
+  GLOWK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= ROWS_MAX_C, "glowk_rows_actnorm_mix: C=%lld must be a multiple of 4, <= %d", (long long)C, ROWS_MAX_C);
+  GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)z) & 15) == 0, "glowk_rows_actnorm_mix: rows must be 16-byte aligned");
+  const int64_t threads = P * (C / 4);
+  const unsigned grid = (unsigned)ceil_div(threads, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w) {
+    const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
+    rows_mix_kernel<false><<<grid, 256, smem, st>>>(x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse);
+  } else {
+    const size_t smem = sizeof(float) * (3 * (size_t)C);
+    rows_mix_kernel<true><<<grid, 256, smem, st>>>(x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse);
+  }
+  GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
+  return GLOWK_OK;
+}
+
+extern "C" int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C) { return ceil_div(HW * (C / 2), 256); }
+
+extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bias3, const float* logs3,
+                                   float logscale_factor, float* z, float* h_save, int64_t N, int64_t C, int64_t H,
+                                   int64_t W, int affine, int reverse, const float* ld_in, float* ld_out,
+                                   const float* an_logs, float an_logscale_factor, const float* logabsdet,
+                                   float sign, float* partials, void* tickets, void* stream) {
+  if (N == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(P3 && bias3 && logs3 && z, "glowk_rows_coupling: null pointer");
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling: bad channel count %lld", (long long)C);
+  const int64_t Cout = affine ? C : C / 2;
+  GLOWK_CHECK_ARG(ldp >= 9 * Cout && ldp % 2 == 0, "glowk_rows_coupling: ldp=%lld too small for 9*Cout=%lld", (long long)ldp, (long long)(9 * Cout));
+  GLOWK_CHECK_ARG(!ld_out || (partials && tickets), "glowk_rows_coupling: logdet output needs partials and tickets");
+  GLOWK_CHECK_ARG(N <= 65535 && H * W * C < (1ll << 30), "glowk_rows_coupling: shape out of range");
+  dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
+  rows_coupling_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P3, ldp, bias3, logs3, logscale_factor, z, h_save,
+                                                                (int)C, (int)H, (int)W, affine, reverse, ld_in, ld_out,
+                                                                an_logs, an_logscale_factor, logabsdet, sign, partials,
+                                                                (unsigned int*)tickets);
+  GLOWK_CHECK_LAUNCH("glowk_rows_coupling");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_coupling_bwd(const float* y, const float* hrows, const float* dy, const float* dld,
+                                       const float* logs3, float logscale_factor, float* dz, float* du,
+                                       float* dlogs3, float* dbias3, int64_t N, int64_t C, int64_t HW, int affine,
+                                       void* stream) {
+  if (N == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(y && hrows && dy && logs3 && dz && du && dlogs3 && dbias3, "glowk_rows_coupling_bwd: null pointer");
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling_bwd: bad channel count");
+  const int64_t NP = N * HW;
+  const int ppb = 256 / (int)(C / 2);
+  const int iters = bwd_iters(NP, ppb);
+  const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
+  rows_coupling_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, hrows, dy, dld, logs3, logscale_factor, dz, du,
+                                                                    dlogs3, dbias3, NP, (int)C, (int)HW, affine, iters);
+  GLOWK_CHECK_LAUNCH("glowk_rows_coupling_bwd");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const float* dA1, int64_t ld_a1,
+                                          int64_t Cin, const float* w, const int64_t* idx, const float* bias,
+                                          const float* logs, float logscale_factor, float* dx, float* dw,
+                                          float* dlogs, float* dbias, int64_t N, int64_t C, int64_t H, int64_t W,
+                                          void* stream) {
+  if (N == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(x && dz && dx, "glowk_rows_actnorm_mix_bwd: null pointer");
+  GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_rows_actnorm_mix_bwd: exactly one of w / idx");
+  GLOWK_CHECK_ARG(!w || dw, "glowk_rows_actnorm_mix_bwd: dw required with w");
+  GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr) && (!bias || (dlogs && dbias)), "glowk_rows_actnorm_mix_bwd: actnorm args");
+  GLOWK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= ROWS_MAX_C, "glowk_rows_actnorm_mix_bwd: bad channel count");
+  GLOWK_CHECK_ARG(!dA1 || (Cin > 0 && Cin <= C && ld_a1 >= 9 * Cin), "glowk_rows_actnorm_mix_bwd: bad conv1 dgrad operand");
+  const int64_t NP = N * H * W;
+  const size_t smem = sizeof(float) * (2 * (size_t)RMB_TP * (C + 1) + (w ? (size_t)C * C : 0) + 5 * (size_t)C);
+  const unsigned grid = (unsigned)ceil_div(NP, RMB_TP);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (w) {
+    if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_mix_bwd_kernel<false><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                                                        dx, dw, dlogs, dbias, NP, (int)C, (int)H, (int)W);
+  } else {
+    if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rows_mix_bwd_kernel<true><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                                                       dx, dw, dlogs, dbias, NP, (int)C, (int)H, (int)W);
+  }
+  GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t ldx, int64_t N,
+                                        int64_t HW, int64_t c0, int64_t Cz, const float* logdet_in,
+                                        float* logdet_out, void* stream) {
+  GLOWK_CHECK_ARG(x && logdet_out, "glowk_rows_gaussian_logp: null pointer");
+  GLOWK_CHECK_ARG(c0 >= 0 && c0 + Cz <= ldx, "glowk_rows_gaussian_logp: channel window out of range");
+  GLOWK_CHECK_ARG(!h || (ldh >= 2 * Cz && ldh % 2 == 0), "glowk_rows_gaussian_logp: ldh too small");
+  GLOWK_CHECK_ARG(HW * Cz < (1ll << 31), "glowk_rows_gaussian_logp: sample too large");
+  if (N == 0) return GLOWK_OK;
+  rows_gaussian_logp_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(h, ldh, x, ldx, (int)HW, (int)c0, (int)Cz,
+                                                                            logdet_in, logdet_out);
+  GLOWK_CHECK_LAUNCH("glowk_rows_gaussian_logp");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_split2d_sample(const float* h, int64_t ldh, const float* z1, int64_t ldz1, const float* eps,
+                                         float* out, int64_t N, int64_t Chalf, int64_t HW, void* stream) {
+  GLOWK_CHECK_ARG(h && z1 && eps && out, "glowk_rows_split2d_sample: null pointer");
+  GLOWK_CHECK_ARG(ldh >= 2 * Chalf && ldh % 2 == 0 && ldz1 >= Chalf, "glowk_rows_split2d_sample: pitches too small");
+  const int64_t total = N * HW * 2 * Chalf;
+  if (total == 0) return GLOWK_OK;
+  rows_split2d_sample_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(h, ldh, z1, ldz1, eps, out, total, (int)Chalf, (int)HW);
+  GLOWK_CHECK_LAUNCH("glowk_rows_split2d_sample");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_split2d_bwd(const float* x, const float* hrows, int64_t ldh, const float* dld,
+                                      const float* logs_p, float logscale_factor, float* dx, float* du, int64_t ldu,
+                                      float* dlogs_p, float* dbias_p, int64_t N, int64_t C, int64_t HW, void* stream) {
+  if (N == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(x && hrows && dld && logs_p && dx && du && dlogs_p && dbias_p, "glowk_rows_split2d_bwd: null pointer");
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C && ldh >= C && ldu >= C && ldu % 2 == 0 && ldh % 2 == 0, "glowk_rows_split2d_bwd: bad shape");
+  const int64_t NP = N * HW;
+  const int ppb = 256 / (int)(C / 2);
+  const int iters = bwd_iters(NP, ppb);
+  const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
+  rows_split2d_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, hrows, ldh, dld, logs_p, logscale_factor, dx, du, ldu,
+                                                                   dlogs_p, dbias_p, NP, (int)C, (int)HW, iters);
+  GLOWK_CHECK_LAUNCH("glowk_rows_split2d_bwd");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* dst, int dst_layout,
+                                  int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W, int factor, int reverse,
+                                  void* stream) {
+  if (N == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(src && dst && src != dst, "glowk_rows_squeeze: bad pointers");
+  GLOWK_CHECK_ARG(factor >= 1 && H % factor == 0 && W % factor == 0, "glowk_rows_squeeze: H,W not divisible by factor");   // module.py:588
+  GLOWK_CHECK_ARG((src_layout | dst_layout) >= 0 && src_layout <= 1 && dst_layout <= 1, "glowk_rows_squeeze: layout must be 0 (NCHW) or 1 (rows)");
+  const int64_t Cs = C * factor * factor;
+  const int64_t c_src = reverse ? Cs : C, c_dst = reverse ? C : Cs;
+  GLOWK_CHECK_ARG(src_ld >= (src_layout ? c_src : C * H * W) && dst_ld >= (dst_layout ? c_dst : C * H * W), "glowk_rows_squeeze: pitch too small");
+  const int64_t total = N * C * H * W;
+  if (total == 0) return GLOWK_OK;
+  rows_squeeze_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      src, src_layout, src_ld, dst, dst_layout, dst_ld, total, (int)C, (int)H, (int)W, factor, reverse);
+  GLOWK_CHECK_LAUNCH("glowk_rows_squeeze");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_pack_conv_weights_batched(const void* jobs, int64_t njobs, int64_t total_blocks, int act_dtype,
+                                               void* stream) {
+  if (njobs == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(jobs && njobs > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "glowk_pack_conv_weights_batched: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (act_dtype == GLOWK_BF16) pack_weights_batched_kernel<__nv_bfloat16><<<(unsigned)total_blocks, 256, 0, st>>>((const PackJob*)jobs, (int)njobs);
+  else if (act_dtype == GLOWK_F32) pack_weights_batched_kernel<float><<<(unsigned)total_blocks, 256, 0, st>>>((const PackJob*)jobs, (int)njobs);
+  else return fail(GLOWK_EINVAL, "glowk_pack_conv_weights_batched: bad act_dtype %d", act_dtype);
+  GLOWK_CHECK_LAUNCH("glowk_pack_conv_weights_batched");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs, int64_t total_blocks, void* stream) {
+  if (njobs == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(jobs && njobs > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "glowk_unpack_weight_grads_batched: bad arguments");
+  unpack_grads_batched_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>((const PackJob*)jobs, (int)njobs);
+  GLOWK_CHECK_LAUNCH("glowk_unpack_weight_grads_batched");
+  return GLOWK_OK;
+}
+
+// 3x3 tap gather-sum on rows: dst[p][c0 + c] (+)= sum_tap P[nbr(p, tap)][tap*C + c]  (Split2d's conv dgrad).
+namespace glowk {
+__global__ void rows_tapsum_kernel(const float* __restrict__ P, int64_t ldp, float* __restrict__ dst, int64_t ld_dst,
+                                   int64_t total, int c0, int C, int H, int W, int flip, int accumulate) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t pix = e / C;
+  const int c = (int)(e - pix * C);
+  const int HW = H * W;
+  const int64_t n = pix / HW;
+  const int q = (int)(pix - n * HW);
+  const int yy = q / W, xx = q - yy * W;
+  float r = 0.f;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tap = flip ? 8 - t : t;
+    const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) r += P[(n * HW + (int64_t)sy * W + sx) * ldp + t * C + c];
+  }
+  float* d = dst + pix * ld_dst + c0 + c;
+  *d = accumulate ? (*d + r) : r;
+}
+}  // namespace glowk
+
+extern "C" int glowk_rows_tapsum(const float* P, int64_t ldp, float* dst, int64_t ld_dst, int64_t c0, int64_t C,
+                                 int64_t N, int64_t H, int64_t W, int flip, int accumulate, void* stream) {
+  GLOWK_CHECK_ARG(P && dst && ldp >= 9 * C && c0 >= 0 && c0 + C <= ld_dst, "glowk_rows_tapsum: bad arguments");
+  const int64_t total = N * H * W * C;
+  if (total == 0) return GLOWK_OK;
+  glowk::rows_tapsum_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      P, ldp, dst, ld_dst, total, (int)c0, (int)C, (int)H, (int)W, flip, accumulate);
+  GLOWK_CHECK_LAUNCH("glowk_rows_tapsum");
+  return GLOWK_OK;
+}

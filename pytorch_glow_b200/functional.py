@@ -325,3 +325,109 @@ def optim_clip_norm(grads, clip_value, max_norm, workspace):
 def optim_adam(params, grads, exp_avg, exp_avg_sq, workspace, step, lr, beta1, beta2, eps, sched=None):
     call("glowk_optim_adam", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(workspace),
          ptr(sched), float(lr), float(beta1), float(beta2), float(eps), int(step))
+
+
+# ------------------------------------------------------------------ pixel-major ("rows") flow state
+NCHW, ROWS = 0, 1
+
+
+def rows_max_channels():
+    return int(_C.lib().glowk_rows_max_channels())
+
+
+def rows_squeeze(src, src_layout, src_ld, dst, dst_layout, dst_ld, n, c, h, w, factor, reverse):
+    """Squeeze2d / unsqueeze between layouts (module.py:551-591); see glowk_rows_squeeze."""
+    check_cuda(src, dst)
+    call("glowk_rows_squeeze", src.data_ptr(), int(src_layout), int(src_ld), dst.data_ptr(), int(dst_layout),
+         int(dst_ld), n, c, h, w, int(factor), int(bool(reverse)))
+    return dst
+
+
+def rows_actnorm_mix(x, weight=None, indices=None, bias=None, logs=None, logscale_factor=3.0, reverse=False):
+    check_cuda(x, weight, indices, bias, logs)
+    p, c = x.shape
+    z = torch.empty_like(x)
+    call("glowk_rows_actnorm_mix", ptr(x), ptr(z), ptr(weight), ptr(indices), ptr(bias), ptr(logs),
+         float(logscale_factor), p, c, int(bool(reverse)))
+    return z
+
+
+def rows_coupling_nblk(hw, c):
+    return int(_C.lib().glowk_rows_coupling_nblk(hw, c))
+
+
+def rows_coupling(p_rows, bias3, logs3, z, n, h, w, affine, reverse, logscale_factor=3.0, save_h=False,
+                  ld_in=None, want_ld=False, an_logs=None, an_f=3.0, logabsdet=None, sign=1.0, partials=None,
+                  tickets=None):
+    """Tap gather-sum + coupling in place on z[:, C/2:] (+ this step's logdet).  Returns (ld_out, h rows)."""
+    check_cuda(p_rows, bias3, logs3, z)
+    c = z.shape[1]
+    cout = c if affine else c // 2
+    hs = torch.empty(n * h * w, cout, device=z.device, dtype=torch.float32) if save_h else None
+    ld_out = torch.empty(n, device=z.device, dtype=torch.float32) if want_ld else None
+    call("glowk_rows_coupling", ptr(p_rows), p_rows.shape[1], ptr(bias3), ptr(logs3), float(logscale_factor), ptr(z),
+         ptr(hs), n, c, h, w, int(bool(affine)), int(bool(reverse)), ptr(ld_in), ptr(ld_out), ptr(an_logs),
+         float(an_f), ptr(logabsdet), float(sign), ptr(partials), ptr(tickets))
+    return ld_out, hs
+
+
+def rows_coupling_bwd(y, hrows, dy, dld, logs3, n, hw, affine, dlogs3, dbias3, logscale_factor=3.0):
+    check_cuda(y, hrows, dy, dld, logs3, dlogs3, dbias3)
+    c = y.shape[1]
+    cout = c if affine else c // 2
+    dz = torch.empty_like(y)
+    du = torch.empty(y.shape[0], cout, device=y.device, dtype=torch.float32)
+    call("glowk_rows_coupling_bwd", ptr(y), ptr(hrows), ptr(dy), ptr(dld), ptr(logs3), float(logscale_factor),
+         ptr(dz), ptr(du), ptr(dlogs3), ptr(dbias3), n, c, hw, int(bool(affine)))
+    return dz, du
+
+
+def rows_actnorm_mix_bwd(x, dz, n, h, w, da1=None, cin=0, weight=None, indices=None, bias=None, logs=None, dw=None,
+                         dlogs=None, dbias=None, logscale_factor=3.0):
+    check_cuda(x, dz, da1, weight, indices, bias, logs, dw, dlogs, dbias)
+    c = x.shape[1]
+    dx = torch.empty_like(x)
+    call("glowk_rows_actnorm_mix_bwd", ptr(x), ptr(dz), ptr(da1), 0 if da1 is None else da1.shape[1], int(cin),
+         ptr(weight), ptr(indices), ptr(bias), ptr(logs), float(logscale_factor), ptr(dx), ptr(dw), ptr(dlogs),
+         ptr(dbias), n, c, h, w)
+    return dx
+
+
+def rows_gaussian_logp(h_rows, x, n, hw, c0, cz, logdet_in=None):
+    check_cuda(h_rows, x, logdet_in)
+    out = torch.empty(n, device=x.device, dtype=torch.float32)
+    call("glowk_rows_gaussian_logp", ptr(h_rows), 0 if h_rows is None else h_rows.shape[1], ptr(x), x.shape[1], n, hw,
+         c0, cz, ptr(logdet_in), ptr(out))
+    return out
+
+
+def rows_split2d_sample(h_rows, z1, ldz1, eps, n, ch, hw):
+    check_cuda(h_rows, z1, eps)
+    out = torch.empty(n * hw, 2 * ch, device=z1.device, dtype=torch.float32)
+    call("glowk_rows_split2d_sample", ptr(h_rows), h_rows.shape[1], z1.data_ptr(), int(ldz1), ptr(_f32c(eps)), ptr(out),
+         n, ch, hw)
+    return out
+
+
+def rows_split2d_bwd(x, hrows, dld, logs_p, dx, dlogs_p, dbias_p, n, hw, logscale_factor=3.0):
+    check_cuda(x, hrows, dld, logs_p, dx, dlogs_p, dbias_p)
+    c = x.shape[1]
+    du = torch.empty(x.shape[0], c, device=x.device, dtype=torch.float32)
+    call("glowk_rows_split2d_bwd", ptr(x), ptr(hrows), hrows.shape[1], ptr(dld), ptr(logs_p), float(logscale_factor),
+         ptr(dx), ptr(du), c, ptr(dlogs_p), ptr(dbias_p), n, c, hw)
+    return du
+
+
+def rows_tapsum(p_rows, dst, c0, c, n, h, w, flip=False, accumulate=False):
+    check_cuda(p_rows, dst)
+    call("glowk_rows_tapsum", ptr(p_rows), p_rows.shape[1], ptr(dst), dst.shape[1], c0, c, n, h, w, int(bool(flip)),
+         int(bool(accumulate)))
+    return dst
+
+
+def pack_conv_weights_batched(jobs_dev, njobs, total_blocks, dtype):
+    call("glowk_pack_conv_weights_batched", ptr(jobs_dev), njobs, total_blocks, int(dtype))
+
+
+def unpack_weight_grads_batched(jobs_dev, njobs, total_blocks):
+    call("glowk_unpack_weight_grads_batched", ptr(jobs_dev), njobs, total_blocks)

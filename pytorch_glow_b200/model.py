@@ -9,7 +9,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _C, module, ops
+from . import _C, config, module, ops, rows_path
 from . import functional as K
 from .module import _logdet_in, _logdet_out
 
@@ -180,6 +180,10 @@ class FlowModel(nn.Module):
             from .autograd import flow_encode_autograd
             _C.check_cuda(z)
             return flow_encode_autograd(self, z, logdet)      # the whole encode is one autograd node
+        vector_ld = logdet is None or (torch.is_tensor(logdet) and logdet.dim() == 1 and logdet.shape[0] == z.shape[0])
+        if config.use_rows_path and vector_ld and rows_path.supported(self, z):
+            ld = None if logdet is None else logdet.to(torch.float32).contiguous()
+            return rows_path.encode(self, z, ld)              # pixel-major flow state (rows_path.py)
         for layer in self.layers:
             z, logdet = layer(z, logdet, reverse=False)
         return z, logdet
@@ -189,6 +193,9 @@ class FlowModel(nn.Module):
         k = 0
         if z.is_cuda:
             self.prepare_invconvs(need_inverse=True)
+        if config.use_rows_path and rows_path.supported(self, z):
+            with torch.no_grad():
+                return rows_path.decode(self, z, eps_std, eps_list)
         for layer in reversed(self.layers):
             if isinstance(layer, module.Split2d):
                 e = None if eps_list is None else eps_list[k]

@@ -299,16 +299,30 @@ class CouplingNet(nn.Sequential):
             return self._packs.get(("w3t", dt), c3.weight, lambda: K.pack_conv_weight(c3.weight.detach(), 3, dt, hp, round_up(self.n3, 64)))
         raise KeyError(which)
 
+    def pack_specs(self, dt, backward):
+        """[(key, parameter, layout, rows, ld)] of the GEMM-layout weight copies this net uses (see `packed`)."""
+        c1, c2, c3 = self[0], self[2], self[4]
+        hid, hp, kh = self.hidden_channels, round_up(self.hidden_channels, 16), round_up(self.hidden_channels, 64)
+        specs = [("w1", c1.weight, 0, hp, self.k1p), ("w2", c2.weight, 0, hp, kh), ("w3", c3.weight, 1, self.n3p, kh)]
+        if backward:
+            specs += [("w1t", c1.weight, 2, self.k1p, kh), ("w2t", c2.weight, 2, hp, kh),
+                      ("w3t", c3.weight, 3, hp, round_up(self.n3, 64))]
+        return specs
+
     def tap_rows(self, z, conv_dtype=None, save=None):
-        """P3 rows [P][n3p] fp32 (conv3 before the tap gather-sum) from channels 0..Cin-1 of NCHW z.
+        """P3 rows [P][n3p] fp32 (conv3 before the tap gather-sum) from channels 0..Cin-1 of NCHW z."""
+        dt = self.dtype(conv_dtype)
+        a1 = K.im2col(z, 0, self.in_channels, 3, dt, self.k1p)
+        return self.tap_rows_from_a1(a1, dt, save)
+
+    def tap_rows_from_a1(self, a1, dt, save=None):
+        """The three GEMMs of the coupling net on a1 = im2col(z1) ([P][k1p]); returns P3 rows [P][n3p] fp32.
 
         Performs the data-dependent ActNorm init of the two hidden ActNorms on the first training
         call (module.py:86-120, 238-239).  `save`, if a dict, receives a1/h1/h2 for the backward pass."""
-        dt = self.dtype(conv_dtype)
         c1, c2, c3 = self[0], self[2], self[4]
         hid = self.hidden_channels
         kh = round_up(hid, 64)
-        a1 = K.im2col(z, 0, self.in_channels, 3, dt, self.k1p)
         w1 = self.packed("w1", dt)
         an1, an2 = c1.actnorm, c2.actnorm
         if an1.needs_init:
@@ -509,6 +523,14 @@ class Split2d(nn.Module):
         self.num_channels = num_channels
         self.conv2d_zeros = Conv2dZeros(num_channels // 2, num_channels)
         self.conv_dtype = None      # override of config.conv_dtype ("fp32" | "bf16" | None)
+
+    def pack_specs(self, dt, backward):
+        conv, c = self.conv2d_zeros, self.num_channels
+        kp = round_up(9 * (c // 2), 64)
+        specs = [(conv, "w0", conv.weight, 0, round_up(c, 16), kp)]
+        if backward:
+            specs.append((conv, "w0t", conv.weight, 2, kp, round_up(c, 64)))
+        return specs
 
     def prior_rows(self, x, conv_dtype=None):
         """h rows [P][C] fp32: Conv2dZeros(z1) with (mean, logs) interleaved ('cross' split)."""

@@ -1,0 +1,446 @@
+"""FlowModel.encode / decode / backward on a pixel-major ("rows") flow state.
+
+Between the NCHW tensors of the reference API (network/model.py:263-294) the flow state lives as
+x[p][c] (p = (n*H + y)*W + x, fp32) -- the layout of every coupling-network GEMM operand -- so each
+flow kernel (csrc/flow_rows_kernels.cu) reads and writes whole contiguous pixels.  Squeeze2d doubles
+as the layout change at the model's entry and exit, Split2d's halves are addressed in place through
+row pitches, and the conv weight packing / weight-gradient unpacking of ALL coupling networks is one
+launch each (`PackPlan`, `GradPlan`).
+
+The per-layer modules (module.py / model.py) keep the reference's NCHW call conventions and kernels;
+this file is what FlowModel uses when the whole model fits the rows kernels (`supported`).
+"""
+import numpy as np
+import torch
+
+from . import _C, config, module
+from . import functional as K
+from .functional import NCHW, ROWS, round_up
+
+_JOB = np.dtype([("w", "<u8"), ("packed", "<u8"), ("O", "<i4"), ("I", "<i4"), ("ks", "<i4"), ("layout", "<i4"),
+                 ("rows", "<i4"), ("ld", "<i4"), ("block0", "<i8")])
+assert _JOB.itemsize == 48
+
+
+def _gbuf(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad.view(-1)
+
+
+def _steps_and_splits(flow):
+    from .model import FlowStep
+    steps = [l for l in flow.layers if isinstance(l, FlowStep)]
+    splits = [l for l in flow.layers if isinstance(l, module.Split2d)]
+    return steps, splits
+
+
+def supported(flow, z):
+    """True iff FlowModel `flow` can run on the rows kernels for input z (else: per-layer NCHW path)."""
+    from .model import FlowStep
+    if not (torch.is_tensor(z) and z.is_cuda and z.dtype == torch.float32 and z.dim() == 4):
+        return False
+    if not (0 < z.shape[0] <= 65535) or len(flow.layers) == 0:
+        return False
+    cmax = K.rows_max_channels()
+    layers = list(flow.layers)
+    if not isinstance(layers[0], module.Squeeze2d) or isinstance(layers[-1], module.Split2d):
+        return False
+    for i, layer in enumerate(layers):
+        if isinstance(layer, FlowStep):
+            if layer.in_channels % 4 or layer.in_channels > cmax:
+                return False
+        elif isinstance(layer, module.Split2d):
+            if layer.num_channels % 4 or layer.num_channels > cmax or not isinstance(layers[i + 1], module.Squeeze2d):
+                return False
+        elif not isinstance(layer, module.Squeeze2d):
+            return False
+    return True
+
+
+# ------------------------------------------------------------------ per-model device workspaces
+class _Workspace:
+    """Deterministic-reduction scratch of glowk_rows_coupling (tickets stay zero between launches)."""
+
+    def __init__(self, device, n, nblk):
+        self.n, self.nblk = n, nblk
+        self.tickets = torch.zeros(n, dtype=torch.int32, device=device)
+        self.partials = torch.empty(n * nblk, dtype=torch.float32, device=device)
+
+
+def _workspace(flow, device, n, nblk):
+    cache = flow.__dict__.setdefault("_rows_ws", {})
+    key = (str(device), n)
+    ws = cache.get(key)
+    if ws is None or ws.nblk < nblk:
+        ws = _Workspace(device, n, max(nblk, 32))
+        cache[key] = ws
+    return ws
+
+
+class PackPlan:
+    """GEMM-layout copies of every conv weight of a FlowModel in one arena, refreshed by ONE kernel."""
+
+    def __init__(self, flow, backward, device):
+        steps, splits = _steps_and_splits(flow)
+        entries = []          # (cache, key, param, layout, rows, ld, dt)
+        for st in steps:
+            dt = st.f.dtype(st.conv_dtype)
+            for key, prm, layout, rows, ld in st.f.pack_specs(dt, backward):
+                entries.append((st.f._packs, key, prm, layout, rows, ld, dt))
+        for sp in splits:
+            dt = config.resolve_conv_dtype(64, sp.conv_dtype)
+            for conv, key, prm, layout, rows, ld in sp.pack_specs(dt, backward):
+                entries.append((conv._packs, key, prm, layout, rows, ld, dt))
+        self.entries = entries
+        self.sig = tuple(e[2].data_ptr() for e in entries)
+        self.groups = {}
+        for dt in sorted(set(e[6] for e in entries)):
+            mine = [e for e in entries if e[6] == dt]
+            numel = sum(e[4] * e[5] for e in mine)
+            arena = torch.empty(numel, device=device, dtype=K.TORCH_DTYPE[dt])
+            jobs = np.zeros(len(mine), dtype=_JOB)
+            views, off, blk = [], 0, 0
+            esz = arena.element_size()
+            for i, (cache, key, prm, layout, rows, ld, _) in enumerate(mine):
+                v = arena[off:off + rows * ld].view(rows, ld)
+                views.append(v)
+                jobs[i] = (prm.data_ptr(), arena.data_ptr() + off * esz, prm.shape[0], prm.shape[1], prm.shape[2],
+                           layout, rows, ld, blk)
+                off += rows * ld
+                blk += (rows * ld + 255) // 256
+            jobs_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(device)
+            self.groups[dt] = (mine, views, arena, jobs_dev, len(mine), blk)
+
+    def valid(self, flow):
+        return self.sig == tuple(e[2].data_ptr() for e in self.entries)
+
+    def fresh(self):
+        return all(cache.fresh((key, dt), prm) for cache, key, prm, _, _, _, dt in self.entries)
+
+    def run(self):
+        for dt, (mine, views, arena, jobs_dev, njobs, blocks) in self.groups.items():
+            K.pack_conv_weights_batched(jobs_dev, njobs, blocks, dt)
+            for (cache, key, prm, _, _, _, _), v in zip(mine, views):
+                cache.put((key, dt), prm, v)
+
+
+def prepare_packs(flow, backward, device):
+    plans = flow.__dict__.setdefault("_pack_plans", {})
+    key = (bool(backward), str(device))
+    plan = plans.get(key)
+    if plan is None or not plan.valid(flow):
+        plan = PackPlan(flow, backward, device)
+        plans[key] = plan
+    if not plan.fresh():
+        plan.run()
+
+
+class GradPlan:
+    """fp32 scratch for the packed-layout weight gradients of conv1 / conv3 / the Split2d prior conv of every
+    layer (zeroed once per backward) and ONE kernel scattering them into the [O][I][k][k] .grad tensors."""
+
+    def __init__(self, flow, device):
+        steps, splits = _steps_and_splits(flow)
+        items = []            # (owner, tag, param, layout, rows, ld)
+        for st in steps:
+            net = st.f
+            kh = round_up(net.hidden_channels, 64)
+            k3p = round_up(9 * net.out_channels, 64)
+            items.append((st, "w3", net[4].weight, 1, k3p, kh))
+            items.append((st, "w1", net[0].weight, 0, kh, net.k1p))
+        for sp in splits:
+            c = sp.num_channels
+            items.append((sp, "w0", sp.conv2d_zeros.weight, 0, round_up(c, 64), round_up(9 * (c // 2), 64)))
+        self.items = items
+        self.sig = tuple(_gbuf(it[2]).data_ptr() for it in items)
+        numel = sum(it[4] * it[5] for it in items)
+        self.arena = torch.zeros(numel, device=device, dtype=torch.float32)
+        jobs = np.zeros(len(items), dtype=_JOB)
+        self.views = {}
+        off = blk = 0
+        for i, (owner, tag, prm, layout, rows, ld) in enumerate(items):
+            self.views[(id(owner), tag)] = self.arena[off:off + rows * ld].view(rows, ld)
+            jobs[i] = (_gbuf(prm).data_ptr(), self.arena.data_ptr() + off * 4, prm.shape[0], prm.shape[1],
+                       prm.shape[2], layout, rows, ld, blk)
+            off += rows * ld
+            blk += (prm.numel() + 255) // 256
+        self.jobs_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(device)
+        self.njobs, self.blocks = len(items), blk
+
+    def valid(self):
+        return self.sig == tuple(_gbuf(it[2]).data_ptr() for it in self.items)
+
+    def begin(self):
+        self.arena.zero_()
+
+    def view(self, owner, tag):
+        return self.views[(id(owner), tag)]
+
+    def finish(self):
+        K.unpack_weight_grads_batched(self.jobs_dev, self.njobs, self.blocks)
+
+
+def grad_plan(flow, device):
+    plans = flow.__dict__.setdefault("_grad_plans", {})
+    plan = plans.get(str(device))
+    if plan is None or not plan.valid():
+        plan = GradPlan(flow, device)
+        plans[str(device)] = plan
+    return plan
+
+
+# ------------------------------------------------------------------ FlowStep
+def _mix_params(step, device, reverse, need_inverse):
+    if step.permutation == 'invconv':
+        wmat, winv, logabsdet = step.invconv.prepared(need_inverse=need_inverse or reverse)
+        return (winv if reverse else wmat), None, logabsdet, wmat, winv
+    return None, step.perm_module.device_indices(device, reverse), None, None, None
+
+
+def _step_forward(step, x, n, c, h, w, ld, ws, save):
+    """FlowStep.normal_flow (network/model.py:82-117) on rows x [P][C]."""
+    an = step.actnorm
+    if an.needs_init:
+        an.initialize_from_rows(x)
+    wm, idx, logabsdet, wmat, winv = _mix_params(step, x.device, False, save)
+    b, l = an.bias.detach().reshape(-1), an.logs.detach().reshape(-1)
+    z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
+    net = step.f
+    dt = net.dtype(step.conv_dtype)
+    a1 = K.im2col_rows(z, n, h, w, 0, net.in_channels, 3, dt, net.k1p)
+    sv = {} if save else None
+    p3 = net.tap_rows_from_a1(a1, dt, sv)
+    c3 = net[4]
+    affine = step.coupling == 'affine'
+    ld_out, hrows = K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), z, n, h, w, affine, False,
+                                    c3.logscale_factor, save_h=save, ld_in=ld, want_ld=ld is not None, an_logs=l,
+                                    an_f=an.logscale_factor, logabsdet=logabsdet, sign=1.0, partials=ws.partials,
+                                    tickets=ws.tickets)
+    ctx = None
+    if save:
+        ctx = dict(x=x, y=z, hrows=hrows, a1=sv["a1"], h1=sv["h1"], h2=sv["h2"], wmat=wmat, winv=winv, idx=idx)
+    return z, ld_out, ctx
+
+
+def _step_reverse(step, x, n, c, h, w, ws):
+    """FlowStep.reverse_flow (network/model.py:119-154) on rows; x is clobbered."""
+    an = step.actnorm
+    net = step.f
+    dt = net.dtype(step.conv_dtype)
+    a1 = K.im2col_rows(x, n, h, w, 0, net.in_channels, 3, dt, net.k1p)
+    p3 = net.tap_rows_from_a1(a1, dt)
+    c3 = net[4]
+    K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
+                    c3.logscale_factor)
+    wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
+    return K.rows_actnorm_mix(x, wm, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
+                              an.logscale_factor, reverse=True)
+
+
+def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
+    """Adjoint of _step_forward; accumulates every parameter gradient of the step, returns dx rows."""
+    net = step.f
+    c1, c2, c3 = net[0], net[2], net[4]
+    an, an1, an2 = step.actnorm, c1.actnorm, c2.actnorm
+    hid = net.hidden_channels
+    kh = round_up(hid, 64)
+    affine = step.coupling == 'affine'
+    cout = net.out_channels
+    h1, h2, a1 = ctx["h1"], ctx["h2"], ctx["a1"]
+    dt = _C.BF16 if h1.dtype == torch.bfloat16 else _C.F32
+    dev = dy.device
+    # (1) coupling + Conv2dZeros scale
+    dz, du = K.rows_coupling_bwd(ctx["y"], ctx["hrows"], dy, dld, c3.logs.detach().reshape(-1), n, h * w, affine,
+                                 _gbuf(c3.logs), _gbuf(c3.bias), c3.logscale_factor)
+    # (2) conv3 (tap form): dP3 = flipped im2col of du
+    k3p = round_up(9 * cout, 64)
+    d3col = K.im2col_rows(du, n, h, w, 0, cout, 3, dt, k3p, flip=True)
+    K.gemm_wgrad(d3col, h2, k3p, hid, plan.view(step, "w3"))
+    d2 = K.gemm(d3col, net.packed("w3t", dt), hid, k3p, _C.EPI_RELU_BWD, None, an2.logs.detach().reshape(-1),
+                an2.logscale_factor, y=h2, dlogs=_gbuf(an2.logs), dbias=_gbuf(an2.bias), out_dtype=dt, ldo=kh)
+    # (3) conv2 (1x1)
+    K.gemm_wgrad(d2, h1, hid, hid, _gbuf(c2.weight).view(hid, hid))
+    d1 = K.gemm(d2, net.packed("w2t", dt), hid, hid, _C.EPI_RELU_BWD, None, an1.logs.detach().reshape(-1),
+                an1.logscale_factor, y=h1, dlogs=_gbuf(an1.logs), dbias=_gbuf(an1.bias), out_dtype=dt, ldo=kh)
+    # (4) conv1 (im2col form); its dgrad is gather-summed inside the mix adjoint below
+    k1p = net.k1p
+    K.gemm_wgrad(d1, a1, hid, k1p, plan.view(step, "w1"))
+    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32)
+    # (5) ActNorm + mix
+    dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition
+    gw = _gbuf(step.invconv.weight) if dense else None
+    if step.permutation == 'invconv' and gw is None:
+        gw = torch.zeros(c * c, device=dev, dtype=torch.float32)
+    dx = K.rows_actnorm_mix_bwd(ctx["x"], dz, n, h, w, da1=da1, cin=net.in_channels, weight=ctx["wmat"],
+                                indices=ctx["idx"], bias=an.bias.detach().reshape(-1),
+                                logs=an.logs.detach().reshape(-1), dw=gw, dlogs=_gbuf(an.logs), dbias=_gbuf(an.bias),
+                                logscale_factor=an.logscale_factor)
+    if dld is not None:
+        K.logdet_param_grad(dld, h * w, _gbuf(an.logs), ctx["winv"], gw, an.logscale_factor)
+    if step.permutation == 'invconv' and step.invconv.lu_decomposition:
+        step.invconv.accumulate_lu_grads(gw.view(c, c))
+    return dx
+
+
+# ------------------------------------------------------------------ Split2d
+def _split_conv(sp, x, n, c, h, w):
+    ch = c // 2
+    conv = sp.conv2d_zeros
+    dt = config.resolve_conv_dtype(64, sp.conv_dtype)
+    kp = round_up(9 * ch, 64)
+    a = K.im2col_rows(x, n, h, w, 0, ch, 3, dt, kp)
+    wp = conv._packs.get(("w0", dt), conv.weight,
+                         lambda: K.pack_conv_weight(conv.weight.detach(), 0, dt, round_up(c, 16), kp))
+    hrows = K.gemm(a, wp, c, kp, _C.EPI_ZEROS, conv.bias.detach(), conv.logs.detach().reshape(-1),
+                   conv.logscale_factor, out_dtype=_C.F32)
+    return a, hrows, dt, kp
+
+
+def _split_forward(sp, x, n, c, h, w, ld, save):
+    """Split2d forward (network/module.py:526-530) on rows x [P][C]; z1 stays in place as x[:, :C/2]."""
+    a, hrows, dt, kp = _split_conv(sp, x, n, c, h, w)
+    ld_out = K.rows_gaussian_logp(hrows, x, n, h * w, c // 2, c // 2, ld)
+    return ld_out, (dict(x=x, a=a, hrows=hrows, dt=dt, kp=kp) if save else None)
+
+
+def _split_reverse(sp, z1, n, ch, h, w, eps):
+    """Split2d reverse (module.py:532-536): rows z1 [P][C/2] -> rows [P][C]."""
+    _, hrows, _, _ = _split_conv(sp, z1, n, 2 * ch, h, w)
+    return K.rows_split2d_sample(hrows, z1, ch, eps, n, ch, h * w)
+
+
+def _split_backward(sp, ctx, dx, dld, n, c, h, w, plan):
+    """dx: rows [P][C] whose channels 0..C/2-1 already hold the gradient of the returned z1."""
+    x, hrows, a, dt, kp = ctx["x"], ctx["hrows"], ctx["a"], ctx["dt"], ctx["kp"]
+    ch = c // 2
+    conv = sp.conv2d_zeros
+    if dld is None:
+        dld = torch.zeros(n, device=dx.device, dtype=torch.float32)
+    du = K.rows_split2d_bwd(x, hrows, dld, conv.logs.detach().reshape(-1), dx, _gbuf(conv.logs), _gbuf(conv.bias), n,
+                            h * w, conv.logscale_factor)
+    cp = round_up(c, 64)
+    duc = K.im2col_rows(du, n, h, w, 0, c, 1, dt, cp)                       # convert + zero-pad to the GEMM tiling
+    K.gemm_wgrad(duc, a, cp, kp, plan.view(sp, "w0"))
+    wt = conv._packs.get(("w0t", dt), conv.weight,
+                         lambda: K.pack_conv_weight(conv.weight.detach(), 2, dt, kp, cp))
+    da = K.gemm(duc, wt, kp, cp, _C.EPI_STORE, out_dtype=_C.F32)
+    K.rows_tapsum(da, dx, 0, ch, n, h, w, flip=True, accumulate=True)
+    return dx
+
+
+# ------------------------------------------------------------------ whole model
+def _max_nblk(flow, h, w):
+    from .model import FlowStep
+    best, c = 1, None
+    for layer in flow.layers:
+        if isinstance(layer, module.Squeeze2d):
+            h, w = h // layer.factor, w // layer.factor
+        elif isinstance(layer, FlowStep):
+            best = max(best, K.rows_coupling_nblk(h * w, layer.in_channels))
+    return best
+
+
+def encode(flow, z, ld, tape=None):
+    """FlowModel.encode (network/model.py:263-276).  z: NCHW fp32; ld: [N] fp32 or None.
+    With `tape` (a list) every layer records what its adjoint needs.  Returns (z_out NCHW, ld_out)."""
+    from .model import FlowStep
+    z = z.contiguous()
+    n, c, h, w = z.shape
+    dev = z.device
+    save = tape is not None
+    prepare_packs(flow, save, dev)
+    ws = _workspace(flow, dev, n, _max_nblk(flow, h, w))
+    cur, layout, pitch = z, NCHW, c * h * w
+    for layer in flow.layers:
+        if isinstance(layer, module.Squeeze2d):
+            f = layer.factor
+            if h % f or w % f:
+                raise ValueError("Squeeze2d: H, W = %d, %d not divisible by factor %d" % (h, w, f))
+            dst = torch.empty(n * (h // f) * (w // f), c * f * f, device=dev, dtype=torch.float32)
+            K.rows_squeeze(cur, layout, pitch, dst, ROWS, c * f * f, n, c, h, w, f, False)
+            if save:
+                tape.append(("squeeze", layer, (c, h, w, layout, pitch)))
+            c, h, w = c * f * f, h // f, w // f
+            cur, layout, pitch = dst, ROWS, c
+        elif isinstance(layer, FlowStep):
+            assert layout == ROWS and pitch == c
+            cur, ld, ctx = _step_forward(layer, cur, n, c, h, w, ld, ws, save)
+            if save:
+                tape.append(("step", layer, ctx))
+        else:
+            assert layout == ROWS and pitch == c
+            ld, ctx = _split_forward(layer, cur, n, c, h, w, ld, save)
+            if save:
+                tape.append(("split", layer, ctx))
+            c = c // 2                      # z1 = first half of the same rows (pitch unchanged)
+    out = torch.empty(n, c, h, w, device=dev, dtype=torch.float32)
+    K.rows_squeeze(cur, layout, pitch, out, NCHW, c * h * w, n, c, h, w, 1, False)
+    return out, ld
+
+
+def backward(flow, tape, dz, dld):
+    """Adjoint of `encode` over its tape.  dz: NCHW grad of z_out; dld: [N] grad of ld_out or None.
+    Accumulates parameter gradients into .grad; returns the NCHW gradient of the input."""
+    dz = dz.contiguous()
+    n, c, h, w = dz.shape
+    dev = dz.device
+    plan = grad_plan(flow, dev)
+    plan.begin()
+    cur = torch.empty(n * h * w, c, device=dev, dtype=torch.float32)
+    K.rows_squeeze(dz, NCHW, c * h * w, cur, ROWS, c, n, c, h, w, 1, False)
+    for kind, layer, ctx in reversed(tape):
+        if kind == "step":
+            cur = _step_backward(layer, ctx, cur, dld, n, c, h, w, plan)
+        elif kind == "split":
+            c = c * 2                       # `cur` is the [P][C] buffer the squeeze adjoint below left half-filled
+            cur = _split_backward(layer, ctx, cur, dld, n, c, h, w, plan)
+        else:
+            c0, h0, w0, layout, pitch = ctx
+            if layout == NCHW:
+                dst = torch.empty(n, c0, h0, w0, device=dev, dtype=torch.float32)
+            else:
+                dst = torch.empty(n * h0 * w0, pitch, device=dev, dtype=torch.float32)
+            K.rows_squeeze(cur, ROWS, c, dst, layout, pitch, n, c0, h0, w0, layer.factor, True)
+            cur, c, h, w = dst, c0, h0, w0
+    plan.finish()
+    return cur
+
+
+def decode(flow, z, eps_std=None, eps_list=None):
+    """FlowModel.decode (network/model.py:278-294).  z: NCHW latent; returns the NCHW image batch."""
+    from .model import FlowStep
+    z = z.contiguous()
+    n, c, h, w = z.shape
+    dev = z.device
+    prepare_packs(flow, False, dev)
+    ws = _workspace(flow, dev, n, 1)
+    cur = torch.empty(n * h * w, c, device=dev, dtype=torch.float32)
+    K.rows_squeeze(z, NCHW, c * h * w, cur, ROWS, c, n, c, h, w, 1, False)
+    k = 0
+    layers = list(flow.layers)
+    for li in range(len(layers) - 1, -1, -1):
+        layer = layers[li]
+        if isinstance(layer, FlowStep):
+            cur = _step_reverse(layer, cur, n, c, h, w, ws)
+        elif isinstance(layer, module.Split2d):
+            if eps_list is not None:
+                e = eps_list[k]
+            else:
+                e = module.GaussianDiag.eps(torch.empty(n, c, h, w, device=dev, dtype=torch.float32), eps_std)
+            k += 1
+            cur = _split_reverse(layer, cur, n, c, h, w, e)
+            c = c * 2
+        else:
+            f = layer.factor
+            if c < f * f or c % (f * f):
+                raise ValueError("Squeeze2d: C = %d not divisible by factor^2" % c)
+            c0, h0, w0 = c // (f * f), h * f, w * f
+            if li == 0:
+                dst = torch.empty(n, c0, h0, w0, device=dev, dtype=torch.float32)
+                K.rows_squeeze(cur, ROWS, c, dst, NCHW, c0 * h0 * w0, n, c0, h0, w0, f, True)
+            else:
+                dst = torch.empty(n * h0 * w0, c0, device=dev, dtype=torch.float32)
+                K.rows_squeeze(cur, ROWS, c, dst, ROWS, c0, n, c0, h0, w0, f, True)
+            cur, c, h, w = dst, c0, h0, w0
+    return cur
