@@ -250,11 +250,12 @@ int glowk_rows_coupling_bwd(const float* y, const float* hrows, const float* dy,
 
 /* glowk_actnorm_mix_bwd on rows, with the conv1 dgrad folded into the load of dz:
  * dz[p][c] += sum_tap dA1[nbr(p, 8-tap)][tap*Cin + c] for c < Cin (dA1: [P][ld_a1] fp32, the dgrad GEMM of the
- * coupling net's first conv in im2col form; nullable) -- i.e. glowk_tapsum_to_nchw(flip=1, accumulate=1). */
+ * coupling net's first conv in im2col form; nullable) -- i.e. glowk_tapsum_to_nchw(flip=1, accumulate=1) --
+ * and, if dld ([N], nullable) is given, glowk_logdet_param_grad folded in (winv = W^-1, needed with w). */
 int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const float* dA1, int64_t ld_a1, int64_t Cin,
                                const float* w, const int64_t* idx, const float* bias, const float* logs,
                                float logscale_factor, float* dx, float* dw, float* dlogs, float* dbias, int64_t N,
-                               int64_t C, int64_t H, int64_t W, void* stream);
+                               int64_t C, int64_t H, int64_t W, const float* dld, const float* winv, void* stream);
 
 /* glowk_gaussian_logp on rows: x: [P][ldx], channels c0..c0+Cz; h: [P][ldh] or null (N(0,I)). */
 int glowk_rows_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t ldx, int64_t N, int64_t HW,

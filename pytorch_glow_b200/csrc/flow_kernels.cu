@@ -311,6 +311,47 @@ __global__ void im2col_kernel(const float* __restrict__ src, int64_t ld_src, int
   }
 }
 
+// im2col of a 3x3 SAME conv from a pixel-major fp32 source into bf16 rows, one thread per (pixel, tap): the
+// Cin channels of a tap are contiguous on both sides, so they move as V-float loads and V-bf16 stores
+// (slot 9 of a pixel zero-fills the K-padding columns).  Needs Cin, c0, ld_src multiples of V.
+template <int V>
+__global__ void im2col_rows_tap_kernel(const float* __restrict__ src, int64_t ld_src, int64_t NP, int c0, int Cin,
+                                       int H, int W, int flip, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= NP * 10) return;
+  const int64_t pix = e / 10;
+  const int slot = (int)(e - pix * 10);
+  __nv_bfloat16* drow = dst + pix * ld;
+  const int K = 9 * Cin;
+  if (slot == 9) {
+    for (int k = K; k < ld; k += 2) *reinterpret_cast<uint32_t*>(drow + k) = 0u;
+    return;
+  }
+  const int HW = H * W;
+  const int64_t n = pix / HW;
+  const int p = (int)(pix - n * HW);
+  const int yy = p / W, xx = p - yy * W;
+  const int tt = flip ? 8 - slot : slot;
+  const int ky = tt / 3, kx = tt - ky * 3;
+  const int sy = yy + ky - 1, sx = xx + kx - 1;
+  const bool inb = sy >= 0 && sy < H && sx >= 0 && sx < W;
+  const float* sp = src + (n * HW + (int64_t)(inb ? sy : 0) * W + (inb ? sx : 0)) * ld_src + c0;
+  __nv_bfloat16* d = drow + slot * Cin;
+#pragma unroll 3
+  for (int c = 0; c < Cin; c += V) {
+    if (V == 4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inb) v = *reinterpret_cast<const float4*>(sp + c);
+      __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
+      *reinterpret_cast<uint2*>(d + c) = *reinterpret_cast<uint2*>(h);
+    } else {
+      float2 v = make_float2(0.f, 0.f);
+      if (inb) v = *reinterpret_cast<const float2*>(sp + c);
+      *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(v.x, v.y);
+    }
+  }
+}
+
 template <typename T>
 __global__ void rows_to_nchw_kernel(const T* __restrict__ rows, int64_t ld, float* __restrict__ dst,
                                     int64_t total, int64_t C, int64_t HW) {
@@ -601,6 +642,16 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
   if (NP == 0) return GLOWK_OK;
   const int64_t total = NP * (ld / 8);
   cudaStream_t st = (cudaStream_t)stream;
+  if (rows_src && ksize == 3 && act_dtype == GLOWK_BF16 && Cin % 2 == 0 && c0 % 2 == 0 && ld_src % 2 == 0 &&
+      ((uintptr_t)src) % 16 == 0) {
+    const unsigned g10 = (unsigned)ceil_div(NP * 10, 256);
+    if (Cin % 4 == 0 && c0 % 4 == 0 && ld_src % 4 == 0)
+      im2col_rows_tap_kernel<4><<<g10, 256, 0, st>>>(src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld);
+    else
+      im2col_rows_tap_kernel<2><<<g10, 256, 0, st>>>(src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld);
+    GLOWK_CHECK_LAUNCH("glowk_im2col_rows(tap)");
+    return GLOWK_OK;
+  }
   const unsigned grid = (unsigned)ceil_div(total, 256);
 #define LAUNCH_IM2COL(T, R) im2col_kernel<T, R><<<grid, 256, 0, st>>>(src, ld_src, NP, Ctot, c0, (int)Cin, (int)H, (int)W, ksize, flip, (T*)dst, ld)
   if (act_dtype == GLOWK_BF16) { if (rows_src) LAUNCH_IM2COL(__nv_bfloat16, true); else LAUNCH_IM2COL(__nv_bfloat16, false); }

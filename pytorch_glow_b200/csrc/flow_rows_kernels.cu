@@ -59,20 +59,29 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
     }
   } else {
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    for (int i = 0; i < C; i += 4) {
-      const float4 xv = *reinterpret_cast<const float4*>(xr + i);
-      float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-      if (!reverse && has_an) {
+    for (int i0 = 0; i0 < C; i0 += 24) {
+      float4 xb[6];                            // up to 24 channels in flight: one memory latency per batch
 #pragma unroll
-        for (int u = 0; u < 4; ++u) xa[u] = (xa[u] + bs[i + u]) * sc[i + u];
-      }
+      for (int b = 0; b < 6; ++b)
+        xb[b] = (i0 + 4 * b < C) ? *reinterpret_cast<const float4*>(xr + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
-        acc[0] = fmaf(wv.x, xa[u], acc[0]);
-        acc[1] = fmaf(wv.y, xa[u], acc[1]);
-        acc[2] = fmaf(wv.z, xa[u], acc[2]);
-        acc[3] = fmaf(wv.w, xa[u], acc[3]);
+      for (int b = 0; b < 6; ++b) {
+        const int i = i0 + 4 * b;
+        if (i < C) {
+          float xa[4] = {xb[b].x, xb[b].y, xb[b].z, xb[b].w};
+          if (!reverse && has_an) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) xa[u] = (xa[u] + bs[i + u]) * sc[i + u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
+            acc[0] = fmaf(wv.x, xa[u], acc[0]);
+            acc[1] = fmaf(wv.y, xa[u], acc[1]);
+            acc[2] = fmaf(wv.z, xa[u], acc[2]);
+            acc[3] = fmaf(wv.w, xa[u], acc[3]);
+          }
+        }
       }
     }
     if (reverse && has_an) {
@@ -160,15 +169,15 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
   if (an_logs)
     for (int c = tid; c < C; c += 256) a += an_logs[c] * an_f;
   const float term = block_sum(a, red);
+  float ps = 0.f;
+  if (affine)
+    for (int b = tid; b < nblk; b += 256) ps += __ldcg(partials + n * nblk + b);
+  const float psum = block_sum(ps, red);
   if (tid == 0) {
     float v = ld_in ? ld_in[n] : 0.f;
     v += sign * (term * (float)HW);                              // torch.sum(logs)*HW   (module.py:78-80)
     if (logabsdet) v += sign * (logabsdet[0] * (float)HW);       // log|det W| * HW      (module.py:357)
-    if (affine) {
-      float s = 0.f;
-      for (int b = 0; b < nblk; ++b) s += __ldcg(partials + n * nblk + b);
-      v += s;
-    }
+    v += psum;
     ld_out[n] = v;
     tickets[n] = 0u;                                             // ready for the next launch on this stream
   }
@@ -236,31 +245,33 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------
-// ActNorm + mix backward (model.py:94-103) with the conv1 dgrad tap gather-sum fused into the load:
+// ActNorm + mix backward (model.py:94-103) with the conv1 dgrad tap gather-sum fused into the load and the
+// gradient of the sample-independent logdet terms (module.py:78-82, 357-363) folded into CTA 0:
 //   dz[p][c] += sum_tap dA1[nbr(p,tap)][tap*Cin + c]   (c < Cin; transposed conv => mirrored taps)
 //   a = (x+b)*s ; da = W^T dz ; dx = da*s ; db += sum da*s ; dlogs += f*sum da*a ; dW += sum_p dz a^T
-// Tile of 128 pixels in shared memory, rows padded to C+1 floats (conflict-free column walks).
+//   G = HW*sum_n dld[n] ; dlogs += f*G ; dW += G*W^-T
+// Tile of TP (32..128) pixels in shared memory, rows padded to C+1 floats (conflict-free column walks).
 // ------------------------------------------------------------------------------------------
-constexpr int RMB_TP = 128;
-
 template <bool PERM>
 __global__ void __launch_bounds__(256)
 rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
                     int64_t ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
                     const float* __restrict__ bias, const float* __restrict__ logs, float f,
                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
-                    float* __restrict__ dbias, int64_t NP, int C, int H, int W) {
+                    float* __restrict__ dbias, int NP, int C, int H, int W, int TP,
+                    const float* __restrict__ dld, int Nld, const float* __restrict__ winv) {
   extern __shared__ __align__(16) float smem[];
   const int LD = C + 1;
-  float* a_s = smem;                          // [TP][LD]  a = actnorm(x)
-  float* d_s = a_s + RMB_TP * LD;             // [TP][LD]  dz, later da
-  float* ws = d_s + RMB_TP * LD;              // [C][C]    W (mix only)
-  float* sc = ws + (PERM ? 0 : C * C);        // [C]
+  float* ws = smem;                           // [C][C]    W (mix only; first so that float4 reads stay aligned)
+  float* s_dw = ws + (PERM ? 0 : C * C);      // [C][C]    this CTA's dW partial (mix only)
+  float* a_s = s_dw + (PERM ? 0 : C * C);     // [TP][LD]  a = actnorm(x)
+  float* d_s = a_s + TP * LD;                 // [TP][LD]  dz, later da
+  float* sc = d_s + TP * LD;                  // [C]
   float* bs = sc + C;                         // [C]
   float* s_red = bs + C;                      // [2][C]
   int* sinv = reinterpret_cast<int*>(s_red + 2 * C);   // [C] inverse permutation (perm only)
+  float* red = reinterpret_cast<float*>(sinv + C);      // [32] + [1]
   const int tid = threadIdx.x;
-  const int64_t g0 = (int64_t)blockIdx.x * RMB_TP;
   const bool has_an = bias != nullptr;
   const int HW = H * W;
   for (int c = tid; c < C; c += 256) {
@@ -270,105 +281,141 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     if (PERM) sinv[(int)idx[c]] = c;          // z[o] = a[idx[o]]  =>  da[i] = dz[o] with idx[o] == i
   }
   if (!PERM)
-    for (int e = tid; e < C * C; e += 256) ws[e] = w[e];
+    for (int e = tid; e < C * C; e += 256) { ws[e] = w[e]; s_dw[e] = 0.f; }
   __syncthreads();
-  // ---- stage a and dz (+ conv1 dgrad) : consecutive threads = consecutive channels of a pixel
-  for (int e = tid; e < RMB_TP * C; e += 256) {
-    const int p = e / C, c = e - p * C;
-    const int64_t pix = g0 + p;
-    float av = 0.f, dv = 0.f;
-    if (pix < NP) {
-      av = (x[pix * C + c] + bs[c]) * sc[c];
-      dv = dz[pix * C + c];
-      if (dA1 && c < Cin) {
-        const int64_t n = pix / HW;
-        const int q = (int)(pix - n * HW);
-        const int yy = q / W, xx = q - yy * W;
+  const int ntiles = (NP + TP - 1) / TP;
+  // a CTA walks several pixel tiles and keeps its dW / dbias / dlogs partials in shared memory: one round of
+  // global atomics per CTA (<= 2 CTAs per SM) instead of one per 128 pixels on the same few cache lines
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int g0 = tile * TP;
+    // ---- stage a and dz (+ conv1 dgrad): consecutive threads = consecutive channels of a pixel; four
+    // elements per thread are loaded together so a tile costs ~TP*C/1024 memory latencies
+    for (int e0 = tid; e0 < TP * C; e0 += 4 * 256) {
+      float xv[4], dv[4], rv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        const int p = e / C, c = e - p * C;
+        const int pix = g0 + p;
+        const bool in = e < TP * C && pix < NP;
+        xv[k] = in ? x[(int64_t)pix * C + c] : 0.f;
+        dv[k] = in ? dz[(int64_t)pix * C + c] : 0.f;
         float r = 0.f;
+        if (in && dA1 && c < Cin) {
+          const int n = pix / HW;
+          const int q = pix - n * HW;
+          const int yy = q / W, xx = q - yy * W;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const int tap = 8 - t;
-          const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
-          if (sy >= 0 && sy < H && sx >= 0 && sx < W)
-            r += dA1[(n * HW + (int64_t)sy * W + sx) * ld_a1 + t * Cin + c];
-        }
-        dv = dv + r;
-      }
-    }
-    a_s[p * LD + c] = av;
-    d_s[p * LD + c] = dv;
-  }
-  __syncthreads();
-  // ---- dW[o][i] += sum_p dz[p][o] a[p][i]
-  if (!PERM) {
-    for (int e = tid; e < C * C; e += 256) {
-      const int o = e / C, i = e - o * C;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int p = 0; p < RMB_TP; ++p) acc = fmaf(d_s[p * LD + o], a_s[p * LD + i], acc);
-      atomicAdd(dw + e, acc);
-    }
-  }
-  __syncthreads();                             // dW has read every dz element: da may now overwrite dz in place
-  // ---- da[p][i] = sum_o W[o][i] dz[p][o].  The G = C/4 threads of a pixel sit in ONE warp (32/G pixels per
-  // warp pass), so a pixel's dz row is replaced by its da row between two __syncwarp()s.
-  {
-    const int G = C >> 2;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int ppw = 32 / G;
-    const int pl = lane / G, ig = lane - pl * G;
-    for (int p0 = warp * ppw; p0 < RMB_TP; p0 += 8 * ppw) {
-      const int p = p0 + pl;
-      const bool act = pl < ppw && p < RMB_TP;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      if (act) {
-        if (PERM) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) acc[u] = d_s[p * LD + sinv[ig * 4 + u]];
-        } else {
-          for (int o = 0; o < C; ++o) {
-            const float d = d_s[p * LD + o];
-            const float4 wv = *reinterpret_cast<const float4*>(ws + o * C + ig * 4);
-            acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]);
-            acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
+          for (int t = 0; t < 9; ++t) {
+            const int tap = 8 - t;
+            const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
+            if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+              r += dA1[((int64_t)n * HW + sy * W + sx) * ld_a1 + t * Cin + c];
           }
         }
+        rv[k] = r;
       }
-      __syncwarp();
-      if (act) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) d_s[p * LD + ig * 4 + u] = acc[u];
+      for (int k = 0; k < 4; ++k) {
+        const int e = e0 + k * 256;
+        if (e < TP * C) {
+          const int p = e / C, c = e - p * C;
+          const bool in = g0 + p < NP;
+          a_s[p * LD + c] = in ? (xv[k] + bs[c]) * sc[c] : 0.f;
+          d_s[p * LD + c] = (dA1 && c < Cin) ? dv[k] + rv[k] : dv[k];
+        }
       }
-      __syncwarp();
     }
-  }
-  __syncthreads();
-  // ---- per-channel reductions over the tile's pixels
-  if (has_an) {
-    const int chunks = 256 / C;
-    if (tid < chunks * C) {
-      const int i = tid % C, ch = tid / C;
-      float sg = 0.f, sga = 0.f;
-      for (int p = ch; p < RMB_TP; p += chunks) {
-        const float d = d_s[p * LD + i];
-        sg += d; sga = fmaf(d, a_s[p * LD + i], sga);
-      }
-      atomicAdd(&s_red[i], sg);
-      atomicAdd(&s_red[C + i], sga);
-    }
-  }
-  // ---- dx = da * s, written back as whole pixels
-  for (int e = tid; e < RMB_TP * C; e += 256) {
-    const int p = e / C, c = e - p * C;
-    const int64_t pix = g0 + p;
-    if (pix < NP) dx[pix * C + c] = d_s[p * LD + c] * sc[c];
-  }
-  if (has_an) {
     __syncthreads();
+    // ---- dW[o][i] += sum_p dz[p][o] a[p][i]   (each (o,i) is owned by one thread)
+    if (!PERM) {
+      for (int e = tid; e < C * C; e += 256) {
+        const int o = e / C, i = e - o * C;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int p = 0; p < TP; ++p) acc = fmaf(d_s[p * LD + o], a_s[p * LD + i], acc);
+        s_dw[e] += acc;
+      }
+    }
+    __syncthreads();                           // dW has read every dz element: da may now overwrite dz in place
+    // ---- da[p][i] = sum_o W[o][i] dz[p][o].  The G = C/4 threads of a pixel sit in ONE warp (32/G pixels per
+    // warp pass), so a pixel's dz row is replaced by its da row between two __syncwarp()s.
+    {
+      const int G = C >> 2;
+      const int warp = tid >> 5, lane = tid & 31;
+      const int ppw = 32 / G;
+      const int pl = lane / G, ig = lane - pl * G;
+      for (int p0 = warp * ppw; p0 < TP; p0 += 8 * ppw) {
+        const int p = p0 + pl;
+        const bool act = pl < ppw && p < TP;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (act) {
+          if (PERM) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = d_s[p * LD + sinv[ig * 4 + u]];
+          } else {
+            for (int o = 0; o < C; ++o) {
+              const float d = d_s[p * LD + o];
+              const float4 wv = *reinterpret_cast<const float4*>(ws + o * C + ig * 4);
+              acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]);
+              acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
+            }
+          }
+        }
+        __syncwarp();
+        if (act) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d_s[p * LD + ig * 4 + u] = acc[u];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- per-channel reductions over the tile's pixels
+    if (has_an) {
+      const int chunks = 256 / C;
+      if (tid < chunks * C) {
+        const int i = tid % C, ch = tid / C;
+        float sg = 0.f, sga = 0.f;
+        for (int p = ch; p < TP; p += chunks) {
+          const float d = d_s[p * LD + i];
+          sg += d; sga = fmaf(d, a_s[p * LD + i], sga);
+        }
+        atomicAdd(&s_red[i], sg);
+        atomicAdd(&s_red[C + i], sga);
+      }
+    }
+    // ---- dx = da * s, written back as whole pixels
+    for (int e = tid; e < TP * C; e += 256) {
+      const int p = e / C, c = e - p * C;
+      const int pix = g0 + p;
+      if (pix < NP) dx[(int64_t)pix * C + c] = d_s[p * LD + c] * sc[c];
+    }
+    __syncthreads();                           // the tile buffers are free for the next tile
+  }
+  // ---- one round of global atomics per CTA
+  if (!PERM)
+    for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, s_dw[e]);
+  if (has_an)
     for (int c = tid; c < C; c += 256) {
       atomicAdd(dbias + c, s_red[c] * sc[c]);
       atomicAdd(dlogs + c, f * s_red[C + c]);
     }
+  // ---- sample-independent logdet terms (one CTA)
+  if (blockIdx.x == 0 && dld) {
+    float a = 0.f;
+    for (int n = tid; n < Nld; n += 256) a += dld[n];
+    const float tot = block_sum(a, red);
+    if (tid == 0) red[32] = tot * (float)HW;
+    __syncthreads();
+    const float Gs = red[32];
+    if (has_an)
+      for (int c = tid; c < C; c += 256) atomicAdd(dlogs + c, f * Gs);
+    if (!PERM && winv)
+      for (int e = tid; e < C * C; e += 256) {
+        const int o = e / C, i = e - o * C;
+        atomicAdd(dw + e, Gs * winv[i * C + o]);
+      }
   }
 }
 
@@ -480,22 +527,23 @@ __device__ __forceinline__ int64_t layout_off(int layout, int64_t ld, int64_t n,
 }
 
 __global__ void rows_squeeze_kernel(const float* __restrict__ src, int src_layout, int64_t src_ld,
-                                    float* __restrict__ dst, int dst_layout, int64_t dst_ld, int64_t total,
+                                    float* __restrict__ dst, int dst_layout, int64_t dst_ld, int total,
                                     int C, int H, int W, int f, int reverse) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int Cs = C * f * f, Hs = H / f, Ws = W / f;
-  // decode e in the DESTINATION's own element order so that writes are coalesced
-  int64_t n; int c, y, x;     // logical coordinates in the destination tensor
+  // decode e in the DESTINATION's own element order so that writes are coalesced (32-bit arithmetic)
+  int n, c, y, x;     // logical coordinates in the destination tensor
   const int Cd = reverse ? C : Cs, Hd = reverse ? H : Hs, Wd = reverse ? W : Ws;
+  int r = e;
   if (dst_layout == 0) {
-    x = (int)(e % Wd); y = (int)((e / Wd) % Hd); c = (int)((e / ((int64_t)Wd * Hd)) % Cd); n = e / ((int64_t)Wd * Hd * Cd);
+    x = r % Wd; r /= Wd; y = r % Hd; r /= Hd; c = r % Cd; n = r / Cd;
   } else {
-    c = (int)(e % Cd); x = (int)((e / Cd) % Wd); y = (int)((e / ((int64_t)Cd * Wd)) % Hd); n = e / ((int64_t)Cd * Wd * Hd);
+    c = r % Cd; r /= Cd; x = r % Wd; r /= Wd; y = r % Hd; n = r / Hd;
   }
   int64_t so, dofs;
   if (!reverse) {   // destination = squeezed (c = cf*f*f + fh*f + fw), source = full
-    const int cf = c / (f * f), r = c - cf * f * f, fh = r / f, fw = r - fh * f;
+    const int cf = c / (f * f), rr = c - cf * f * f, fh = rr / f, fw = rr - fh * f;
     so = layout_off(src_layout, src_ld, n, cf, y * f + fh, x * f + fw, C, H, W);
     dofs = layout_off(dst_layout, dst_ld, n, c, y, x, Cs, Hs, Ws);
   } else {          // destination = full, source = squeezed
@@ -659,7 +707,7 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
                                           int64_t Cin, const float* w, const int64_t* idx, const float* bias,
                                           const float* logs, float logscale_factor, float* dx, float* dw,
                                           float* dlogs, float* dbias, int64_t N, int64_t C, int64_t H, int64_t W,
-                                          void* stream) {
+                                          const float* dld, const float* winv, void* stream) {
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(x && dz && dx, "glowk_rows_actnorm_mix_bwd: null pointer");
   GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_rows_actnorm_mix_bwd: exactly one of w / idx");
@@ -667,18 +715,24 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr) && (!bias || (dlogs && dbias)), "glowk_rows_actnorm_mix_bwd: actnorm args");
   GLOWK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= ROWS_MAX_C, "glowk_rows_actnorm_mix_bwd: bad channel count");
   GLOWK_CHECK_ARG(!dA1 || (Cin > 0 && Cin <= C && ld_a1 >= 9 * Cin), "glowk_rows_actnorm_mix_bwd: bad conv1 dgrad operand");
+  GLOWK_CHECK_ARG(!dld || !w || winv, "glowk_rows_actnorm_mix_bwd: the logdet gradient of a 1x1 conv needs W^-1");
+  GLOWK_CHECK_ARG(N < (1ll << 31), "glowk_rows_actnorm_mix_bwd: batch too large");
   const int64_t NP = N * H * W;
-  const size_t smem = sizeof(float) * (2 * (size_t)RMB_TP * (C + 1) + (w ? (size_t)C * C : 0) + 5 * (size_t)C);
-  const unsigned grid = (unsigned)ceil_div(NP, RMB_TP);
+  GLOWK_CHECK_ARG(NP * C < (1ll << 31), "glowk_rows_actnorm_mix_bwd: tensor too large for 32-bit indexing");
+  int TP = 128;                                                  // smaller tiles until every SM has two CTAs
+  while (TP > 32 && ceil_div(NP, TP) < 2 * sm_count()) TP >>= 1;
+  const size_t smem = sizeof(float) * (2 * (size_t)TP * (C + 1) + (w ? 2 * (size_t)C * C : 0) + 5 * (size_t)C + 33);
+  int64_t tiles = ceil_div(NP, TP);
+  const unsigned grid = (unsigned)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
   cudaStream_t st = (cudaStream_t)stream;
   if (w) {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_mix_bwd_kernel<false><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                        dx, dw, dlogs, dbias, NP, (int)C, (int)H, (int)W);
+                                                        dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv);
   } else {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rows_mix_bwd_kernel<true><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                       dx, dw, dlogs, dbias, NP, (int)C, (int)H, (int)W);
+                                                       dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv);
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd");
   return GLOWK_OK;
@@ -737,8 +791,9 @@ extern "C" int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_
   GLOWK_CHECK_ARG(src_ld >= (src_layout ? c_src : C * H * W) && dst_ld >= (dst_layout ? c_dst : C * H * W), "glowk_rows_squeeze: pitch too small");
   const int64_t total = N * C * H * W;
   if (total == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(total < (1ll << 31), "glowk_rows_squeeze: tensor too large for 32-bit indexing");
   rows_squeeze_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, src_layout, src_ld, dst, dst_layout, dst_ld, total, (int)C, (int)H, (int)W, factor, reverse);
+      src, src_layout, src_ld, dst, dst_layout, dst_ld, (int)total, (int)C, (int)H, (int)W, factor, reverse);
   GLOWK_CHECK_LAUNCH("glowk_rows_squeeze");
   return GLOWK_OK;
 }

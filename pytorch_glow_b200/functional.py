@@ -252,6 +252,7 @@ def split2d_sample(h_rows, z1, eps):
     z1 = _f32c(z1)
     eps = _f32c(eps)
     n, ch, h, w = z1.shape
+    assert eps.numel() == z1.numel(), "eps must have the shape of z1 %s, got %s" % (tuple(z1.shape), tuple(eps.shape))
     out = torch.empty(n, 2 * ch, h, w, device=z1.device, dtype=torch.float32)
     call("glowk_split2d_sample", ptr(h_rows), h_rows.shape[1], ptr(z1), ptr(eps), ptr(out), n, ch, h * w)
     return out
@@ -383,13 +384,13 @@ def rows_coupling_bwd(y, hrows, dy, dld, logs3, n, hw, affine, dlogs3, dbias3, l
 
 
 def rows_actnorm_mix_bwd(x, dz, n, h, w, da1=None, cin=0, weight=None, indices=None, bias=None, logs=None, dw=None,
-                         dlogs=None, dbias=None, logscale_factor=3.0):
-    check_cuda(x, dz, da1, weight, indices, bias, logs, dw, dlogs, dbias)
+                         dlogs=None, dbias=None, logscale_factor=3.0, dld=None, winv=None):
+    check_cuda(x, dz, da1, weight, indices, bias, logs, dw, dlogs, dbias, dld, winv)
     c = x.shape[1]
     dx = torch.empty_like(x)
     call("glowk_rows_actnorm_mix_bwd", ptr(x), ptr(dz), ptr(da1), 0 if da1 is None else da1.shape[1], int(cin),
          ptr(weight), ptr(indices), ptr(bias), ptr(logs), float(logscale_factor), ptr(dx), ptr(dw), ptr(dlogs),
-         ptr(dbias), n, c, h, w)
+         ptr(dbias), n, c, h, w, ptr(dld), ptr(winv))
     return dx
 
 
@@ -403,6 +404,7 @@ def rows_gaussian_logp(h_rows, x, n, hw, c0, cz, logdet_in=None):
 
 def rows_split2d_sample(h_rows, z1, ldz1, eps, n, ch, hw):
     check_cuda(h_rows, z1, eps)
+    assert eps.numel() == n * ch * hw, "eps must be [N, C/2, H, W] = %s, got %s" % ((n, ch, hw), tuple(eps.shape))
     out = torch.empty(n * hw, 2 * ch, device=z1.device, dtype=torch.float32)
     call("glowk_rows_split2d_sample", ptr(h_rows), h_rows.shape[1], z1.data_ptr(), int(ldz1), ptr(_f32c(eps)), ptr(out),
          n, ch, hw)

@@ -275,9 +275,7 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     dx = K.rows_actnorm_mix_bwd(ctx["x"], dz, n, h, w, da1=da1, cin=net.in_channels, weight=ctx["wmat"],
                                 indices=ctx["idx"], bias=an.bias.detach().reshape(-1),
                                 logs=an.logs.detach().reshape(-1), dw=gw, dlogs=_gbuf(an.logs), dbias=_gbuf(an.bias),
-                                logscale_factor=an.logscale_factor)
-    if dld is not None:
-        K.logdet_param_grad(dld, h * w, _gbuf(an.logs), ctx["winv"], gw, an.logscale_factor)
+                                logscale_factor=an.logscale_factor, dld=dld, winv=ctx["winv"])
     if step.permutation == 'invconv' and step.invconv.lu_decomposition:
         step.invconv.accumulate_lu_grads(gw.view(c, c))
     return dx

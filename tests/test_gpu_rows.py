@@ -203,6 +203,18 @@ def test_rows_mix_bwd_matches_nchw(shape, mode, with_da1):
     assert_close(db, db_ref, 1e-4, 1e-4, "dbias")
     if mode == "mix":
         assert_close(dw, dw_ref, 1e-4, 1e-4, "dW")
+    # with the gradient of the sample-independent logdet terms folded in (glowk_logdet_param_grad)
+    dld = cu(torch.randn(n, generator=g(48)))
+    winv = torch.linalg.inv(wgt.double()).float().contiguous() if mode == "mix" else None
+    K.logdet_param_grad(dld, h * w, dl_ref, winv, dw_ref, 3.0)
+    dw2 = torch.zeros(c * c, device=DEV) if mode == "mix" else None
+    dl2, db2 = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    dx2 = K.rows_actnorm_mix_bwd(to_rows(x), to_rows(dz), n, h, w, da1=da1, cin=cin if with_da1 else 0, weight=wgt,
+                                 indices=idx, bias=bias, logs=logs, dw=dw2, dlogs=dl2, dbias=db2, dld=dld, winv=winv)
+    assert torch.equal(dx2, dx)
+    assert_close(dl2, dl_ref, 1e-4, 2e-4, "dlogs + logdet term")
+    if mode == "mix":
+        assert_close(dw2, dw_ref, 1e-4, 2e-4, "dW + logdet term")
 
 
 # ---------------------------------------------------------------- Split2d pieces
@@ -251,7 +263,10 @@ def test_rows_split2d_pieces(shape):
 
 # ---------------------------------------------------------------- im2col on rows == im2col on NCHW
 @pytest.mark.parametrize("shape,c0,cin,ks,flip", [((2, 12, 8, 8), 0, 6, 3, False), ((2, 12, 8, 8), 0, 12, 3, True),
-                                                  ((3, 24, 4, 4), 0, 24, 1, False), ((1, 6, 5, 7), 2, 3, 3, True)])
+                                                  ((3, 24, 4, 4), 0, 24, 1, False), ((1, 6, 5, 7), 2, 3, 3, True),
+                                                  ((2, 24, 4, 4), 0, 12, 3, False), ((2, 48, 4, 4), 0, 48, 3, True),
+                                                  ((3, 4, 3, 5), 0, 2, 3, False), ((2, 8, 6, 6), 4, 4, 3, True),
+                                                  ((2, 8, 6, 6), 2, 4, 3, False), ((40, 12, 32, 32), 0, 6, 3, False)])
 @pytest.mark.parametrize("dt", [_C.F32, _C.BF16])
 def test_im2col_rows_equals_nchw(shape, c0, cin, ks, flip, dt):
     n, c, h, w = shape
@@ -328,7 +343,7 @@ def test_flowmodel_rows_equals_nchw_path(perm, coup, dtype):
     assert rows_path.supported(flow, x)
     with torch.no_grad():
         z_r, ld_r = flow(x, logdet=ld0)
-        eps = [cu(torch.randn(4, 24, 2, 2, generator=g(72))), cu(torch.randn(4, 12, 4, 4, generator=g(73)))]
+        eps = [cu(torch.randn(4, 12, 4, 4, generator=g(72))), cu(torch.randn(4, 6, 8, 8, generator=g(73)))]
         x_r = flow.decode(z_r.clone(), eps_list=eps)
         config.use_rows_path = False
         try:
