@@ -28,7 +28,7 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (image_shape HWC, K, L, hidden, coupling, default per-GPU batch, fwd GFLOP/img)
-    "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 64, 32.06),
+    "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 256, 32.06),
     "cifar32": ((32, 32, 3), 32, 3, 512, "affine", 256, 8.02),
     "tiny": ((32, 32, 3), 4, 3, 64, "affine", 16, None),
 }
@@ -186,6 +186,85 @@ def timed(fn, steps, dist_on, device):
     return float(ms) / 1e3, w0, w1
 
 
+def kernel_rooflines(device, B, shape, hidden, peaks):
+    """Stand-alone timing of the level-1 kernels of one flow step against their roofline.
+
+    bound "hbm": achieved = algorithmic bytes / time vs the measured copy bandwidth (MEASURED_PEAKS.json hbm_gbs);
+    bound "tensor": achieved = 2*M*N*K / time vs the measured bf16 burst rate.  Buffers rotate over >= 3 copies
+    (> 126 MB L2 in total) so that no launch finds its inputs in L2."""
+    from pytorch_glow_b200 import _C
+    from pytorch_glow_b200 import functional as KF
+    hbm = peaks.get("hbm_gbs", 6500.0)
+    tfl = peaks.get("bf16_tflops", 1590.0)
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    H, W = shape[0] // 2, shape[1] // 2
+    C = shape[2] * 4
+    M = B * H * W
+    R = 3
+    bf = torch.bfloat16
+    rnd = lambda *s: torch.randn(*s, device=device)
+    hs = [rnd(M, hidden).to(bf) for _ in range(R)]                  # h1 / h2 / d2 stand-ins (3 x 2*M*512 bytes)
+    outs = [torch.empty(M, hidden, device=device, dtype=bf) for _ in range(R)]
+    w2 = (rnd(hidden, hidden) * 0.05).to(bf)
+    bias = torch.zeros(hidden, device=device); logs = torch.zeros(hidden, device=device)
+    dlogs = torch.zeros(hidden, device=device); dbias = torch.zeros(hidden, device=device)
+    dw = torch.zeros(hidden, hidden, device=device)
+    n3p = (9 * C + 15) // 16 * 16
+    p3 = [rnd(M, n3p) * 0.1 for _ in range(R)]
+    zs = [rnd(M, C) for _ in range(R)]
+    b3 = torch.zeros(C, device=device); l3 = torch.zeros(C, device=device)
+    nblk = KF.rows_coupling_nblk(H * W, C)
+    tickets = torch.zeros(B, dtype=torch.int32, device=device)
+    parts = torch.empty(B * nblk, device=device)
+    ld_in = torch.zeros(B, device=device)
+    wmix = torch.eye(C, device=device) + 0.01 * rnd(C, C)
+    mb = torch.zeros(C, device=device)
+
+    def t_us(fn, reps=9):
+        for i in range(R):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(reps):
+            fn(i % R)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    gemm_flops = 2.0 * M * hidden * hidden
+    cases = [
+        ("dgrad2", "gemm_tc_kernel<RELU_BWD,bf16>: dgrad of conv2 + ReLU/ActNorm backward epilogue (M=%d N=K=%d)" % (M, hidden),
+         lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_RELU_BWD, None, logs, 3.0, y=hs[(i + 1) % R], dlogs=dlogs,
+                           dbias=dbias, out_dtype=_C.BF16, out=outs[i]),
+         "hbm", 3.0 * M * hidden * 2, gemm_flops),
+        ("wgrad2", "wgrad_tc_kernel: dW2 += d2^T h1 (P=%d, 512x512)" % M,
+         lambda i: KF.gemm_wgrad(hs[i], hs[(i + 1) % R], hidden, hidden, dw),
+         "hbm", 2.0 * M * hidden * 2, gemm_flops),
+        ("conv2", "gemm_tc_kernel<ACTNORM_RELU,bf16>: conv2 1x1 + ActNorm + ReLU (M=%d N=K=%d)" % (M, hidden),
+         lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i]),
+         "tensor", 2.0 * M * hidden * 2, gemm_flops),
+        ("coupling", "rows_coupling_kernel: tap gather-sum + affine coupling + logdet (M=%d C=%d)" % (M, C),
+         lambda i: KF.rows_coupling(p3[i], b3, l3, zs[i], B, H, W, True, False, 3.0, save_h=True, ld_in=ld_in,
+                                    want_ld=True, an_logs=mb, logabsdet=ld_in[:1], partials=parts, tickets=tickets),
+         "hbm", 4.0 * M * (9 * C + C // 2 * 2 + C), None),
+        ("actnorm_mix", "rows_mix_kernel: ActNorm + invertible 1x1 conv (M=%d C=%d)" % (M, C),
+         lambda i: KF.rows_actnorm_mix(zs[i], wmix, None, mb, mb, 3.0, False),
+         "hbm", 8.0 * M * C, None),
+    ]
+    out = []
+    for kid, name, fn, bound, nbytes, flops in cases:
+        us = t_us(fn)
+        if bound == "hbm":
+            ach, peak, unit = nbytes / us / 1e3, hbm, "GB/s"
+        else:
+            ach, peak, unit = flops / us / 1e6, tfl, "TFLOP/s"
+        out.append({"id": kid, "kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                    "frac": ach / peak, "traffic": None, "us_per_launch": us, "algorithmic_bytes": nbytes,
+                    "peak_source": src + (" hbm_gbs (copy bandwidth)" if bound == "hbm" else " bf16_tflops (burst; kernel timed alone)")})
+    return out
+
+
 def run_b200(args):
     import torch.distributed as dist
     import pytorch_glow_b200 as G
@@ -290,38 +369,27 @@ def run_b200(args):
                   "eps_std": 0.7, "collective": "none"}
         del glow_s
 
-    # ---- roofline of the dominant kernel: the 512x512 1x1 conv as a tcgen05 GEMM (76% of the step's FLOPs)
+    # ---- rooflines of the kernels that dominate the step (level 1: C=12, 32x32, M = B*1024 pixels), each timed
+    # alone with CUDA events on the launch stream over rotating buffers larger than L2.  "roofline" is the kernel
+    # with the largest share of the step in profiles/ (the conv2 dgrad with the fused ReLU/ActNorm-backward
+    # epilogue); "roofline_all" lists the others.  Algorithmic bytes / flops per launch: DESIGN.md section 4.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except (OSError, ValueError):
         pass
-    roof = None
+    roof, roof_all = None, None
     if rank == 0 and args.conv_dtype == "bf16":
-        M = B * (shape[0] // 2) * (shape[1] // 2)
-        a = [torch.randn(M, hidden, device=device).bfloat16() for _ in range(3)]     # 3 x 64 MB: larger than L2
-        wgt = (torch.randn(hidden, hidden, device=device) * 0.05).bfloat16()
-        bias = torch.zeros(hidden, device=device); logs = torch.zeros(hidden, device=device)
-        outs = [torch.empty(M, hidden, device=device, dtype=torch.bfloat16) for _ in range(3)]
-        for i in range(3):
-            KF.gemm(a[i], wgt, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i])
-        torch.cuda.synchronize()
-        reps = 12
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(reps):
-            KF.gemm(a[i % 3], wgt, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i % 3])
-        e1.record()
-        torch.cuda.synchronize()
-        t = e0.elapsed_time(e1) / reps / 1e3
-        flops = 2.0 * M * hidden * hidden
-        peak = peaks.get("bf16_tflops", 1590.0)
-        roof = {"kernel": "gemm_tc_kernel<ACTNORM_RELU,bf16> (coupling conv2, M=%d N=K=%d)" % (M, hidden),
-                "bound": "tensor", "achieved": flops / t / 1e12, "peak": peak, "unit": "TFLOP/s",
-                "frac": flops / t / 1e12 / peak, "traffic": None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)" if peaks else "fallback 1590",
-                "us_per_launch": t * 1e6}
-        del a, outs
+        roof_all = kernel_rooflines(device, B, shape, hidden, peaks)
+        roof = dict(roof_all[0])
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            ent = tr.get(roof["id"])
+            if ent and ent.get("per_gpu_batch") == B:
+                roof["traffic"] = ent["dram_bytes"]
+                roof["traffic_source"] = ent.get("source")
+        except (OSError, ValueError):
+            pass
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload through the oracle port
     cpu = None
@@ -345,7 +413,7 @@ def run_b200(args):
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": x_host[0].numel() * 4 * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": gpu_launches, "clocks": clocks, "loss_bits_per_dim": last_loss,
-            "roofline": roof, "cpu_baseline": cpu, "sample": sample,
+            "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "sample": sample,
         }
         if gflop:
             tf = value * gflop * 3 / 1e3          # fwd + dgrad + wgrad

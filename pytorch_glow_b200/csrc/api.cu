@@ -1,5 +1,6 @@
 // C-ABI plumbing: error reporting, device queries, GEMM dispatch.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
@@ -16,6 +17,13 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  // measured on B200 (gpurun_out/ab1_bench.log): inside the captured train-step graph PDL edges cost
+  // ~1.2 us MORE per kernel than plain edges (37.8 vs 36.0 ms/step), so the attribute is opt-in (GLOWK_PDL=1)
+  static const bool on = []() { const char* e = getenv("GLOWK_PDL"); return e && e[0] == '1'; }();
+  return on;
 }
 
 int sm_count() {

@@ -38,6 +38,31 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // Number of SMs of the current device (cached per device id, read-only after first query).
 int sm_count();
 
+// Programmatic dependent launch (PDL).  The per-step kernels are short (a K=32, L=3 Glow launches ~1500 of them
+// per training step, many of a few microseconds), so each one is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: it may be scheduled while its predecessor drains, does its
+// memory-free set-up (shared-memory carve-up, mbarrier init, TMEM allocation, tensor-map prefetch) and then blocks
+// in pdl_wait() until every earlier grid has completed and flushed.  Rules kept by every kernel that uses it:
+// NO global-memory access before pdl_wait(); kernels that write parameters / packed weights never trigger early.
+// The attribute is OFF unless GLOWK_PDL=1 is set in the environment (read once): see pdl_enabled() in api.cu.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

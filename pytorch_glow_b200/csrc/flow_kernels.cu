@@ -317,6 +317,8 @@ __global__ void im2col_kernel(const float* __restrict__ src, int64_t ld_src, int
 template <int V>
 __global__ void im2col_rows_tap_kernel(const float* __restrict__ src, int64_t ld_src, int64_t NP, int c0, int Cin,
                                        int H, int W, int flip, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= NP * 10) return;
   const int64_t pix = e / 10;
@@ -646,9 +648,9 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
       ((uintptr_t)src) % 16 == 0) {
     const unsigned g10 = (unsigned)ceil_div(NP * 10, 256);
     if (Cin % 4 == 0 && c0 % 4 == 0 && ld_src % 4 == 0)
-      im2col_rows_tap_kernel<4><<<g10, 256, 0, st>>>(src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld);
+      GLOWK_CUDA(launch_pdl(im2col_rows_tap_kernel<4>, g10, 256, 0, st, src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld));
     else
-      im2col_rows_tap_kernel<2><<<g10, 256, 0, st>>>(src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld);
+      GLOWK_CUDA(launch_pdl(im2col_rows_tap_kernel<2>, g10, 256, 0, st, src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld));
     GLOWK_CHECK_LAUNCH("glowk_im2col_rows(tap)");
     return GLOWK_OK;
   }

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256)
 rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
                 const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
                 float f, int64_t P, int C, int reverse) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* wt = smem;                               // [C][C]: wt[i*C + o] = W[o][i]   (mix only)
   float* sc = wt + (PERM ? 0 : C * C);            // [C] exp(+-f*logs)
@@ -106,6 +108,8 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
                      const float* __restrict__ ld_in, float* __restrict__ ld_out,
                      const float* __restrict__ an_logs, float an_f, const float* __restrict__ logabsdet,
                      float sign, float* __restrict__ partials, unsigned int* __restrict__ tickets) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
   __shared__ int s_last;
@@ -194,6 +198,8 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
                          const float* __restrict__ logs3, float f, float* __restrict__ dz,
                          float* __restrict__ du, float* __restrict__ dlogs3, float* __restrict__ dbias3,
                          int64_t NP, int C, int HW, int affine, int iters) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_part[4][256];
   __shared__ float s_e[2 * ROWS_MAX_C];
   const int Ch = C >> 1, Cout = affine ? C : Ch;
@@ -260,6 +266,8 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
                     float* __restrict__ dbias, int NP, int C, int H, int W, int TP,
                     const float* __restrict__ dld, int Nld, const float* __restrict__ winv) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   const int LD = C + 1;
   float* ws = smem;                           // [C][C]    W (mix only; first so that float4 reads stay aligned)
@@ -426,6 +434,7 @@ __global__ void __launch_bounds__(256)
 rows_gaussian_logp_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ x, int64_t ldx,
                           int HW, int c0, int Cz, const float* __restrict__ logdet_in,
                           float* __restrict__ logdet_out) {
+  pdl_wait();
   __shared__ float red[32];
   const int64_t n = blockIdx.x;
   const float log2pi = 1.8378770664093453f;
@@ -451,6 +460,7 @@ rows_gaussian_logp_kernel(const float* __restrict__ h, int64_t ldh, const float*
 __global__ void rows_split2d_sample_kernel(const float* __restrict__ h, int64_t ldh, const float* __restrict__ z1,
                                            int64_t ldz1, const float* __restrict__ eps, float* __restrict__ out,
                                            int64_t total, int Ch, int HW) {
+  pdl_wait();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int C = 2 * Ch;
@@ -476,6 +486,7 @@ rows_split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h
                         float* __restrict__ dx, float* __restrict__ du, int64_t ldu,
                         float* __restrict__ dlogs_p, float* __restrict__ dbias_p, int64_t NP, int C, int HW,
                         int iters) {
+  pdl_wait();
   __shared__ float s_part[4][256];
   __shared__ float s_e[2 * ROWS_MAX_C];
   const int Ch = C >> 1;
@@ -529,6 +540,7 @@ __device__ __forceinline__ int64_t layout_off(int layout, int64_t ld, int64_t n,
 __global__ void rows_squeeze_kernel(const float* __restrict__ src, int src_layout, int64_t src_ld,
                                     float* __restrict__ dst, int dst_layout, int64_t dst_ld, int total,
                                     int C, int H, int W, int f, int reverse) {
+  pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int Cs = C * f * f, Hs = H / f, Ws = W / f;
@@ -590,6 +602,7 @@ __device__ __forceinline__ bool packed_coords(int layout, int O, int I, int T2, 
 
 template <typename T>
 __global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  pdl_wait();
   __shared__ int s_job;
   if (threadIdx.x == 0) s_job = find_job(jobs, njobs, blockIdx.x);
   __syncthreads();
@@ -605,6 +618,7 @@ __global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, in
 }
 
 __global__ void unpack_grads_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  pdl_wait();
   __shared__ int s_job;
   if (threadIdx.x == 0) s_job = find_job(jobs, njobs, blockIdx.x);
   __syncthreads();
@@ -654,10 +668,10 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   cudaStream_t st = (cudaStream_t)stream;
   if (w) {
     const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
-    rows_mix_kernel<false><<<grid, 256, smem, st>>>(x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse);
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, 256, smem, st, x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse));
   } else {
     const size_t smem = sizeof(float) * (3 * (size_t)C);
-    rows_mix_kernel<true><<<grid, 256, smem, st>>>(x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse);
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, 256, smem, st, x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse));
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
   return GLOWK_OK;
@@ -678,10 +692,10 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
   GLOWK_CHECK_ARG(!ld_out || (partials && tickets), "glowk_rows_coupling: logdet output needs partials and tickets");
   GLOWK_CHECK_ARG(N <= 65535 && H * W * C < (1ll << 30), "glowk_rows_coupling: shape out of range");
   dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
-  rows_coupling_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(P3, ldp, bias3, logs3, logscale_factor, z, h_save,
+  GLOWK_CUDA(launch_pdl(rows_coupling_kernel, grid, 256, 0, (cudaStream_t)stream, P3, ldp, bias3, logs3, logscale_factor, z, h_save,
                                                                 (int)C, (int)H, (int)W, affine, reverse, ld_in, ld_out,
                                                                 an_logs, an_logscale_factor, logabsdet, sign, partials,
-                                                                (unsigned int*)tickets);
+                                                                (unsigned int*)tickets));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling");
   return GLOWK_OK;
 }
@@ -697,8 +711,8 @@ extern "C" int glowk_rows_coupling_bwd(const float* y, const float* hrows, const
   const int ppb = 256 / (int)(C / 2);
   const int iters = bwd_iters(NP, ppb);
   const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
-  rows_coupling_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, hrows, dy, dld, logs3, logscale_factor, dz, du,
-                                                                    dlogs3, dbias3, NP, (int)C, (int)HW, affine, iters);
+  GLOWK_CUDA(launch_pdl(rows_coupling_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, y, hrows, dy, dld, logs3, logscale_factor, dz, du,
+                                                                    dlogs3, dbias3, NP, (int)C, (int)HW, affine, iters));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling_bwd");
   return GLOWK_OK;
 }
@@ -727,12 +741,12 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   cudaStream_t st = (cudaStream_t)stream;
   if (w) {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rows_mix_bwd_kernel<false><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                        dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv);
+    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<false>, grid, 256, smem, st, x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                                                        dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv));
   } else {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rows_mix_bwd_kernel<true><<<grid, 256, smem, st>>>(x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                       dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv);
+    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<true>, grid, 256, smem, st, x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                                                       dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv));
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd");
   return GLOWK_OK;
@@ -822,6 +836,7 @@ extern "C" int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs
 namespace glowk {
 __global__ void rows_tapsum_kernel(const float* __restrict__ P, int64_t ldp, float* __restrict__ dst, int64_t ld_dst,
                                    int64_t total, int c0, int C, int H, int W, int flip, int accumulate) {
+  pdl_wait();
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int64_t pix = e / C;

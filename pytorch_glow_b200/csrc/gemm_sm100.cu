@@ -250,6 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint16_t mask_all = mask_a | mask_b;
   const bool small_n = N <= EPI_NMAX;
 
+  pdl_trigger();                             // the next kernel may be scheduled as SMs free up (it waits for us)
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_o);
@@ -270,6 +271,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (csize > 1) cluster_sync_all();        // peers' barriers must be initialised before any remote arrive / multicast
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  pdl_wait();                                // everything above touched no global memory (PDL, common.cuh)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -518,6 +520,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   const int k_items = (total_kb + kb_per_item - 1) / kb_per_item;
   const int num_items = m_blocks * n_blocks * k_items;
 
+  pdl_trigger();
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_d);
@@ -533,6 +536,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -701,11 +705,20 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)csize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (csize > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)csize; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = csize > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   const char* dbg_env = getenv("GLOWK_GEMM_DEBUG");      // profiling aid (1: no loads, 2: no MMA, 4: no epilogue)
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
   GLOWK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, ty, M, N, K, block_n, stages, cm, cn, dbg, ep));
@@ -813,7 +826,7 @@ int wgrad_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_
   GLOWK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int items = tiles * k_items;
   const int grid = items < sm_count() ? items : sm_count();
-  wgrad_tc_kernel<<<grid, GEMM_THREADS, smem, st>>>(ta, tb, td, (int)P, (int)Mo, (int)No, block_n, stages, kb_per_item);
+  GLOWK_CUDA(launch_pdl(wgrad_tc_kernel, grid, GEMM_THREADS, smem, st, ta, tb, td, (int)P, (int)Mo, (int)No, block_n, stages, kb_per_item));
   GLOWK_CHECK_LAUNCH("glowk_gemm_wgrad(tcgen05)");
   return GLOWK_OK;
 }

@@ -28,6 +28,26 @@ def noam_lr(base_lr, global_step, warmup_steps=4000, min_lr=None):
     return lr
 
 
+def allreduce_mean_(t, group=None):
+    """In-place mean over the ranks of `group` (NCCL: one AVG all-reduce over NVLink; gloo has no AVG: SUM then
+    divide).  Gradients are averaged BEFORE clipping so that every rank clips identical tensors."""
+    if dist.get_backend(group) == "nccl":
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(dist.get_world_size(group))
+    return t
+
+
+def shard_batch(x, rank, world_size):
+    """This rank's contiguous slice of a global batch (DataParallel's scatter on dim 0, trainer.py:118-123)."""
+    n = x.shape[0]
+    if n % world_size:
+        raise ValueError("global batch %d is not divisible by %d ranks (model.py:350-353)" % (n, world_size))
+    per = n // world_size
+    return x[rank * per:(rank + 1) * per]
+
+
 class FlatArena:
     """Re-homes a module's trainable parameters (and their .grad) into flat fp32 buffers."""
 
@@ -120,8 +140,7 @@ class FusedTrainStep:
 
     def _allreduce(self):
         if self.world_size > 1:
-            # average BEFORE clipping so every rank clips identical tensors
-            dist.all_reduce(self.arena.grad, op=dist.ReduceOp.AVG, group=self.pg)
+            allreduce_mean_(self.arena.grad, self.pg)
 
     def step(self, x):
         """One training iteration on the device batch x [B,3,H,W] in [0,1).  Returns the loss (bits/dim)
