@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--conv-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off ...)")
     ap.add_argument("--profile-step", action="store_true",
                     help="for ncu --profile-from-start off: run ONE eager train step (and one sampling pass) "
                          "between cudaProfilerStart/Stop after warm-up, print nothing, exit")
@@ -333,7 +335,12 @@ def run_b200(args):
     for attempt in range(2):
         sampler.start()
         c0 = _C.launch_count
+        if args.profiler_range:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
         sec, w0, w1 = timed(resident, args.steps, dist_on, device)
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStop()
         c1 = _C.launch_count
         clocks = sampler.stop(w0, w1)
         if not (set(clocks["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}):

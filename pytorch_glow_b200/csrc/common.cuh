@@ -63,6 +63,28 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Division by a launch-constant divisor without the ~20-instruction integer-divide sequence (the flow kernels
+// move a few bytes per thread, so their index arithmetic is a first-order cost): q = umulhi(n, mul) >> shr,
+// exact for 0 <= n < 2^31 (Granlund-Montgomery round-up method).
+struct FastDiv {
+  uint32_t d, mul, shr;
+};
+static inline FastDiv make_fastdiv(int64_t d) {
+  FastDiv f;
+  f.d = (uint32_t)d; f.mul = 0; f.shr = 0;
+  if (d > 1) {
+    int lg = 0;
+    while ((1ll << lg) < d) ++lg;                      // ceil(log2 d)
+    const int p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + (uint64_t)d - 1) / (uint64_t)d);
+    f.shr = (uint32_t)(p - 32);
+  }
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.d == 1 ? n : (int)(__umulhi((uint32_t)n, f.mul) >> f.shr);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

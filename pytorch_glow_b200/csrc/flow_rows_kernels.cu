@@ -15,14 +15,14 @@ constexpr int ROWS_MAX_C = 96;   // shared-memory tiles below are sized for C <=
 
 // ------------------------------------------------------------------------------------------
 // ActNorm + channel mix / permutation (model.py:94-103 fwd, 142-152 rev).
-// thread = (pixel, group of 4 output channels); the G = C/4 lanes of a pixel read the same
-// 16-byte chunks of x (one transaction) and W^T from shared memory.
+// block = (G = C/4 output-channel groups, PPB pixels): thread (og, slot) produces 4 output channels of one
+// pixel; the G lanes of a pixel read the same 16-byte chunks of x (one transaction) and W^T from shared memory.
 // ------------------------------------------------------------------------------------------
 template <bool PERM>
 __global__ void __launch_bounds__(256)
 rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
                 const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
-                float f, int64_t P, int C, int reverse) {
+                float f, int P, int C, int reverse) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
@@ -30,26 +30,24 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
   float* sc = wt + (PERM ? 0 : C * C);            // [C] exp(+-f*logs)
   float* bs = sc + C;                             // [C] bias
   int* sidx = reinterpret_cast<int*>(bs + C);     // [C] (perm only)
-  const int tid = threadIdx.x;
+  const int og = threadIdx.x, slot = threadIdx.y;
+  const int nthr = blockDim.x * blockDim.y;
+  const int tid = slot * blockDim.x + og;
   const bool has_an = bias != nullptr;
-  for (int c = tid; c < C; c += 256) {
+  for (int c = tid; c < C; c += nthr) {
     const float l = has_an ? logs[c] * f : 0.f;
     sc[c] = has_an ? expf(reverse ? -l : l) : 1.f;
     bs[c] = has_an ? bias[c] : 0.f;
     if (PERM) sidx[c] = (int)idx[c];
   }
   if (!PERM)
-    for (int e = tid; e < C * C; e += 256) {
-      const int o = e / C, i = e - o * C;
-      wt[i * C + o] = w[e];
-    }
+    for (int o = slot; o < C; o += blockDim.y)      // thread (og, slot) transposes 4 elements of row o
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wt[(og * 4 + u) * C + o] = w[o * C + og * 4 + u];
   __syncthreads();
-  const int G = C >> 2;
-  const int64_t gid = (int64_t)blockIdx.x * 256 + tid;
-  if (gid >= P * G) return;
-  const int64_t pix = gid / G;
-  const int og = (int)(gid - pix * G);
-  const float* xr = x + pix * C;
+  const int pix = blockIdx.x * blockDim.y + slot;
+  if (pix >= P) return;
+  const float* xr = x + (int64_t)pix * C;
   float acc[4];
   if (PERM) {
 #pragma unroll
@@ -72,8 +70,10 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
         if (i < C) {
           float xa[4] = {xb[b].x, xb[b].y, xb[b].z, xb[b].w};
           if (!reverse && has_an) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) xa[u] = (xa[u] + bs[i + u]) * sc[i + u];
+            const float4 b4 = *reinterpret_cast<const float4*>(bs + i);
+            const float4 s4 = *reinterpret_cast<const float4*>(sc + i);
+            xa[0] = (xa[0] + b4.x) * s4.x; xa[1] = (xa[1] + b4.y) * s4.y;
+            xa[2] = (xa[2] + b4.z) * s4.z; xa[3] = (xa[3] + b4.w) * s4.w;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
@@ -91,20 +91,22 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
       for (int a = 0; a < 4; ++a) acc[a] = acc[a] * sc[og * 4 + a] - bs[og * 4 + a];
     }
   }
-  *reinterpret_cast<float4*>(z + pix * C + og * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(z + (int64_t)pix * C + og * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // ------------------------------------------------------------------------------------------
 // Tap gather-sum (second half of Conv2dZeros as nine pointwise GEMMs, module.py:295-296) + coupling
 // (model.py:105-115 fwd, 131-140 rev) + this step's logdet (module.py:77-82, 357-367; model.py:114,140).
-// grid = (nblk, N), thread = (pixel, j): lanes of a pixel read 8*Ch (affine) contiguous bytes per tap.
-// The last CTA of a sample (atomic ticket, self-resetting) sums the per-CTA partials in a fixed order:
+// grid = (nblk, N), block = (Ch, PPB): thread (j, slot) owns channel pair j of one pixel; the Ch lanes of a
+// pixel read 8*Ch (affine) contiguous bytes per tap.  Tap addresses are base + uniform offsets; the four
+// border predicates are computed once.  The last CTA of a sample (atomic ticket, self-resetting) sums the
+// per-CTA partials with a fixed-shape tree:
 //   ld_out[n] = ld_in[n] + sign*HW*(sum_c f*an_logs[c] + logabsdet[0]) + sum_b partial[n][b]
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __restrict__ bias3,
+rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restrict__ bias3,
                      const float* __restrict__ logs3, float f, float* __restrict__ z,
-                     float* __restrict__ h_save, int C, int H, int W, int affine, int reverse,
+                     float* __restrict__ h_save, int C, int H, int W, FastDiv divW, FastDiv divCh, int affine, int reverse,
                      const float* __restrict__ ld_in, float* __restrict__ ld_out,
                      const float* __restrict__ an_logs, float an_f, const float* __restrict__ logabsdet,
                      float sign, float* __restrict__ partials, unsigned int* __restrict__ tickets) {
@@ -114,24 +116,30 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
   __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
   __shared__ int s_last;
   const int HW = H * W, Ch = C >> 1, Cout = affine ? C : Ch;
-  const int64_t n = blockIdx.y;
-  const int tid = threadIdx.x;
-  for (int c = tid; c < Cout; c += 256) { s_b[c] = bias3[c]; s_e[c] = expf(logs3[c] * f); }
+  const int n = blockIdx.y;
+  // 256 threads = PPB pixels x Ch channel pairs (+ a few idle lanes, so that every warp is complete for the
+  // shuffle reductions below)
+  const int tid = threadIdx.x, nthr = 256;
+  const int slot = fdiv(tid, divCh), j = tid - slot * Ch;
+  const int ppb = 256 / Ch;
+  for (int c = tid; c < Cout; c += nthr) { s_b[c] = bias3[c]; s_e[c] = expf(logs3[c] * f); }
   __syncthreads();
   float lsum = 0.f;
-  const int e = blockIdx.x * 256 + tid;
-  if (e < HW * Ch) {
-    const int pix = e / Ch, j = e - pix * Ch;
-    const int yy = pix / W, xx = pix - yy * W;
-    const float* Pn = P3 + n * HW * ldp;
-    float* zp = z + (n * HW + pix) * C + Ch + j;
+  const int pix = blockIdx.x * ppb + slot;
+  if (slot < ppb && pix < HW) {
+    const int yy = fdiv(pix, divW), xx = pix - yy * W;
+    const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
+    const int64_t row = (int64_t)n * HW + pix;
+    float* zp = z + row * C + Ch + j;
     if (affine) {
+      const float* Pp = P3 + row * ldp + 2 * j;
       float u0 = 0.f, u1 = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-          const float2 v = *reinterpret_cast<const float2*>(Pn + (int64_t)(sy * W + sx) * ldp + t * Cout + 2 * j);
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+        if (ok) {
+          const float2 v = *reinterpret_cast<const float2*>(Pp + (dy * W + dx) * ldp + t * Cout);
           u0 += v.x; u1 += v.y;
         }
       }
@@ -142,19 +150,21 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
       if (!reverse) { v = (v + shift) * scale; lsum += logf(scale); }
       else { v = v / scale - shift; lsum -= logf(scale); }
       *zp = v;
-      if (h_save) *reinterpret_cast<float2*>(h_save + (n * HW + pix) * (int64_t)Cout + 2 * j) = make_float2(shift, hsc);
+      if (h_save) *reinterpret_cast<float2*>(h_save + row * Cout + 2 * j) = make_float2(shift, hsc);
     } else {
+      const float* Pp = P3 + row * ldp + j;
       float u = 0.f;
 #pragma unroll
       for (int t = 0; t < 9; ++t) {
-        const int sy = yy + t / 3 - 1, sx = xx + t % 3 - 1;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) u += Pn[(int64_t)(sy * W + sx) * ldp + t * Cout + j];
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+        if (ok) u += Pp[(dy * W + dx) * ldp + t * Cout];
       }
       const float h = (u + s_b[j]) * s_e[j];
       float v = *zp;
       v = reverse ? v - h : v + h;
       *zp = v;
-      if (h_save) h_save[(n * HW + pix) * (int64_t)Cout + j] = h;
+      if (h_save) h_save[row * Cout + j] = h;
     }
   }
   if (!ld_out) return;
@@ -171,11 +181,11 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
   __threadfence();
   float a = 0.f;
   if (an_logs)
-    for (int c = tid; c < C; c += 256) a += an_logs[c] * an_f;
+    for (int c = tid; c < C; c += nthr) a += an_logs[c] * an_f;
   const float term = block_sum(a, red);
   float ps = 0.f;
   if (affine)
-    for (int b = tid; b < nblk; b += 256) ps += __ldcg(partials + n * nblk + b);
+    for (int b = tid; b < nblk; b += nthr) ps += __ldcg(partials + n * nblk + b);
   const float psum = block_sum(ps, red);
   if (tid == 0) {
     float v = ld_in ? ld_in[n] : 0.f;
@@ -189,7 +199,7 @@ rows_coupling_kernel(const float* __restrict__ P3, int64_t ldp, const float* __r
 
 // ------------------------------------------------------------------------------------------
 // Coupling backward (see coupling_bwd_kernel in flow_bwd_kernels.cu for the formulas).
-// thread = (pixel slot, j) with j fixed over `iters` pixel groups, so the per-channel sums for
+// block = (Ch, PPB): thread (j, slot) keeps j over `iters` pixel groups, so the per-channel sums for
 // dlogs3 / dbias3 are accumulated in registers and reduced once per CTA.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -197,43 +207,39 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
                          const float* __restrict__ dy, const float* __restrict__ dld,
                          const float* __restrict__ logs3, float f, float* __restrict__ dz,
                          float* __restrict__ du, float* __restrict__ dlogs3, float* __restrict__ dbias3,
-                         int64_t NP, int C, int HW, int affine, int iters) {
+                         int NP, int C, FastDiv divHW, int affine, int iters) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_part[4][256];
   __shared__ float s_e[2 * ROWS_MAX_C];
   const int Ch = C >> 1, Cout = affine ? C : Ch;
-  const int tid = threadIdx.x;
-  const int ppb = 256 / Ch;
-  for (int c = tid; c < Cout; c += 256) s_e[c] = expf(logs3[c] * f);
+  const int j = threadIdx.x, slot = threadIdx.y, ppb = blockDim.y;
+  const int tid = slot * Ch + j;
+  for (int c = tid; c < Cout; c += Ch * ppb) s_e[c] = expf(logs3[c] * f);
   __syncthreads();
-  const int j = tid % Ch, slot = tid / Ch;
   float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f;
-  if (slot < ppb) {
-    for (int it = 0; it < iters; ++it) {
-      const int64_t pix = ((int64_t)blockIdx.x * iters + it) * ppb + slot;
-      if (pix >= NP) break;
-      const int64_t n = pix / HW;
-      const float g = dld ? dld[n] : 0.f;
-      const int64_t o1 = pix * C + j, o2 = o1 + Ch;
-      dz[o1] = dy[o1];
-      const float dy2 = dy[o2];
-      if (affine) {
-        const float2 hv = *reinterpret_cast<const float2*>(hrows + pix * Cout + 2 * j);
-        const float h0 = hv.x, h1 = hv.y;
-        const float scale = 1.f / (1.f + expf(-(h1 + 2.f)));
-        const float zs = y[o2] / scale;            // z2 + shift
-        dz[o2] = dy2 * scale;
-        const float dh0 = dy2 * scale;
-        const float dh1 = (dy2 * zs + g / scale) * scale * (1.f - scale);
-        *reinterpret_cast<float2*>(du + pix * Cout + 2 * j) = make_float2(dh0 * s_e[2 * j], dh1 * s_e[2 * j + 1]);
-        a0 += dh0 * h0; b0 += dh0; a1 += dh1 * h1; b1 += dh1;
-      } else {
-        const float h0 = hrows[pix * Cout + j];
-        dz[o2] = dy2;
-        du[pix * Cout + j] = dy2 * s_e[j];
-        a0 += dy2 * h0; b0 += dy2;
-      }
+  for (int it = 0; it < iters; ++it) {
+    const int pix = (blockIdx.x * iters + it) * ppb + slot;
+    if (pix >= NP) break;
+    const float g = dld ? dld[fdiv(pix, divHW)] : 0.f;
+    const int64_t o1 = (int64_t)pix * C + j, o2 = o1 + Ch;
+    dz[o1] = dy[o1];
+    const float dy2 = dy[o2];
+    if (affine) {
+      const float2 hv = *reinterpret_cast<const float2*>(hrows + (int64_t)pix * Cout + 2 * j);
+      const float h0 = hv.x, h1 = hv.y;
+      const float scale = 1.f / (1.f + expf(-(h1 + 2.f)));
+      const float zs = y[o2] / scale;            // z2 + shift
+      dz[o2] = dy2 * scale;
+      const float dh0 = dy2 * scale;
+      const float dh1 = (dy2 * zs + g / scale) * scale * (1.f - scale);
+      *reinterpret_cast<float2*>(du + (int64_t)pix * Cout + 2 * j) = make_float2(dh0 * s_e[2 * j], dh1 * s_e[2 * j + 1]);
+      a0 += dh0 * h0; b0 += dh0; a1 += dh1 * h1; b1 += dh1;
+    } else {
+      const float h0 = hrows[(int64_t)pix * Cout + j];
+      dz[o2] = dy2;
+      du[(int64_t)pix * Cout + j] = dy2 * s_e[j];
+      a0 += dy2 * h0; b0 += dy2;
     }
   }
   s_part[0][tid] = a0; s_part[1][tid] = b0; s_part[2][tid] = a1; s_part[3][tid] = b1;
@@ -256,32 +262,34 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
 //   dz[p][c] += sum_tap dA1[nbr(p,tap)][tap*Cin + c]   (c < Cin; transposed conv => mirrored taps)
 //   a = (x+b)*s ; da = W^T dz ; dx = da*s ; db += sum da*s ; dlogs += f*sum da*a ; dW += sum_p dz a^T
 //   G = HW*sum_n dld[n] ; dlogs += f*G ; dW += G*W^-T
-// Tile of TP (32..128) pixels in shared memory, rows padded to C+1 floats (conflict-free column walks).
+// A CTA walks tiles of TP (32..128) pixels staged in shared memory as [TP][C] (16-byte rows: every global and
+// most shared accesses are float4).  dW is accumulated in registers over ALL the CTA's tiles as 4x4 blocks
+// (x a split of the tile's pixels, so that all 256 threads work) and leaves the CTA once, like dbias / dlogs.
 // ------------------------------------------------------------------------------------------
+constexpr int RMB_MAXIT = 3;     // 4x4 dW blocks per thread: (C/4)^2 <= 3*256  (C <= 96 -> 576)
+
 template <bool PERM>
 __global__ void __launch_bounds__(256)
 rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
-                    int64_t ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
+                    int ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
                     const float* __restrict__ bias, const float* __restrict__ logs, float f,
                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
-                    float* __restrict__ dbias, int NP, int C, int H, int W, int TP,
-                    const float* __restrict__ dld, int Nld, const float* __restrict__ winv) {
+                    float* __restrict__ dbias, int NP, int C, int H, int W, FastDiv divW, FastDiv divHW,
+                    FastDiv divG, int TP, const float* __restrict__ dld, int Nld, const float* __restrict__ winv) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
-  const int LD = C + 1;
-  float* ws = smem;                           // [C][C]    W (mix only; first so that float4 reads stay aligned)
-  float* s_dw = ws + (PERM ? 0 : C * C);      // [C][C]    this CTA's dW partial (mix only)
-  float* a_s = s_dw + (PERM ? 0 : C * C);     // [TP][LD]  a = actnorm(x)
-  float* d_s = a_s + TP * LD;                 // [TP][LD]  dz, later da
-  float* sc = d_s + TP * LD;                  // [C]
+  float* ws = smem;                           // [C][C]    W, later this CTA's dW (mix only)
+  float* a_s = ws + (PERM ? 0 : C * C);       // [TP][C]   a = actnorm(x)
+  float* d_s = a_s + TP * C;                  // [TP][C]   dz, later da
+  float* sc = d_s + TP * C;                   // [C]
   float* bs = sc + C;                         // [C]
   float* s_red = bs + C;                      // [2][C]
   int* sinv = reinterpret_cast<int*>(s_red + 2 * C);   // [C] inverse permutation (perm only)
   float* red = reinterpret_cast<float*>(sinv + C);      // [32] + [1]
   const int tid = threadIdx.x;
   const bool has_an = bias != nullptr;
-  const int HW = H * W;
+  const int HW = H * W, G = C >> 2;
   for (int c = tid; c < C; c += 256) {
     sc[c] = has_an ? expf(logs[c] * f) : 1.f;
     bs[c] = has_an ? bias[c] : 0.f;
@@ -289,70 +297,98 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     if (PERM) sinv[(int)idx[c]] = c;          // z[o] = a[idx[o]]  =>  da[i] = dz[o] with idx[o] == i
   }
   if (!PERM)
-    for (int e = tid; e < C * C; e += 256) { ws[e] = w[e]; s_dw[e] = 0.f; }
+    for (int e = tid; e < C * C; e += 256) ws[e] = w[e];
   __syncthreads();
+  // (pixel slot, channel quad) of this thread in the staging / copy-out passes
+  const int slot = fdiv(tid, divG), quad = tid - slot * G;
+  const int ppb = 256 / G;
+  // 4x4 dW blocks of this thread: item = (block, pixel split); persistent register accumulators
+  const int nb4 = G * G;
+  int psplit = 256 / nb4;
+  if (psplit < 1) psplit = 1;
+  const int nitems = nb4 * psplit;
+  float dwacc[RMB_MAXIT][16];
+#pragma unroll
+  for (int k = 0; k < RMB_MAXIT; ++k)
+#pragma unroll
+    for (int u = 0; u < 16; ++u) dwacc[k][u] = 0.f;
+
   const int ntiles = (NP + TP - 1) / TP;
-  // a CTA walks several pixel tiles and keeps its dW / dbias / dlogs partials in shared memory: one round of
-  // global atomics per CTA (<= 2 CTAs per SM) instead of one per 128 pixels on the same few cache lines
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int g0 = tile * TP;
-    // ---- stage a and dz (+ conv1 dgrad): consecutive threads = consecutive channels of a pixel; four
-    // elements per thread are loaded together so a tile costs ~TP*C/1024 memory latencies
-    for (int e0 = tid; e0 < TP * C; e0 += 4 * 256) {
-      float xv[4], dv[4], rv[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int e = e0 + k * 256;
-        const int p = e / C, c = e - p * C;
+    // ---- stage a and dz (+ conv1 dgrad), one float4 of one pixel per thread and pass
+    if (slot < ppb) {
+      for (int p = slot; p < TP; p += ppb) {
         const int pix = g0 + p;
-        const bool in = e < TP * C && pix < NP;
-        xv[k] = in ? x[(int64_t)pix * C + c] : 0.f;
-        dv[k] = in ? dz[(int64_t)pix * C + c] : 0.f;
-        float r = 0.f;
-        if (in && dA1 && c < Cin) {
-          const int n = pix / HW;
-          const int q = pix - n * HW;
-          const int yy = q / W, xx = q - yy * W;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
+        if (pix < NP) {
+          xv = *reinterpret_cast<const float4*>(x + (int64_t)pix * C + quad * 4);
+          dv = *reinterpret_cast<const float4*>(dz + (int64_t)pix * C + quad * 4);
+          const int c0 = quad * 4;
+          if (dA1 && c0 < Cin) {
+            const int n = fdiv(pix, divHW);
+            const int q = pix - n * HW;
+            const int yy = fdiv(q, divW), xx = q - yy * W;
+            const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
+            const bool hi = c0 + 2 < Cin;                       // channels c0+2, c0+3 also belong to z1
+            const float* ap = dA1 + (int64_t)pix * ld_a1 + c0;
+            float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
 #pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const int tap = 8 - t;
-            const int sy = yy + tap / 3 - 1, sx = xx + tap % 3 - 1;
-            if (sy >= 0 && sy < H && sx >= 0 && sx < W)
-              r += dA1[((int64_t)n * HW + sy * W + sx) * ld_a1 + t * Cin + c];
+            for (int t = 0; t < 9; ++t) {
+              const int tap = 8 - t;
+              const int dy = tap / 3 - 1, dxx = tap % 3 - 1;
+              const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dxx < 0 ? lf : (dxx > 0 ? rt : true));
+              if (ok) {
+                const float* tp = ap + (dy * W + dxx) * ld_a1 + t * Cin;
+                const float2 v0 = *reinterpret_cast<const float2*>(tp);
+                r0 += v0.x; r1 += v0.y;
+                if (hi) {
+                  const float2 v1 = *reinterpret_cast<const float2*>(tp + 2);
+                  r2 += v1.x; r3 += v1.y;
+                }
+              }
+            }
+            dv.x = dv.x + r0; dv.y = dv.y + r1;
+            if (hi) { dv.z = dv.z + r2; dv.w = dv.w + r3; }
           }
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + quad * 4);
+          const float4 s4 = *reinterpret_cast<const float4*>(sc + quad * 4);
+          xv.x = (xv.x + b4.x) * s4.x; xv.y = (xv.y + b4.y) * s4.y;
+          xv.z = (xv.z + b4.z) * s4.z; xv.w = (xv.w + b4.w) * s4.w;
         }
-        rv[k] = r;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int e = e0 + k * 256;
-        if (e < TP * C) {
-          const int p = e / C, c = e - p * C;
-          const bool in = g0 + p < NP;
-          a_s[p * LD + c] = in ? (xv[k] + bs[c]) * sc[c] : 0.f;
-          d_s[p * LD + c] = (dA1 && c < Cin) ? dv[k] + rv[k] : dv[k];
-        }
+        *reinterpret_cast<float4*>(a_s + p * C + quad * 4) = xv;
+        *reinterpret_cast<float4*>(d_s + p * C + quad * 4) = dv;
       }
     }
     __syncthreads();
-    // ---- dW[o][i] += sum_p dz[p][o] a[p][i]   (each (o,i) is owned by one thread)
+    // ---- dW[o][i] += sum_p dz[p][o] a[p][i] on 4x4 register blocks
     if (!PERM) {
-      for (int e = tid; e < C * C; e += 256) {
-        const int o = e / C, i = e - o * C;
-        float acc = 0.f;
-#pragma unroll 8
-        for (int p = 0; p < TP; ++p) acc = fmaf(d_s[p * LD + o], a_s[p * LD + i], acc);
-        s_dw[e] += acc;
+#pragma unroll
+      for (int k = 0; k < RMB_MAXIT; ++k) {
+        const int it = tid + k * 256;
+        if (it < nitems) {
+          const int ps = it / nb4, blk = it - ps * nb4;
+          const int bo = fdiv(blk, divG), bi = blk - bo * G;
+          for (int p = ps; p < TP; p += psplit) {
+            const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + bo * 4);
+            const float4 a4 = *reinterpret_cast<const float4*>(a_s + p * C + bi * 4);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) dwacc[k][u * 4 + v] = fmaf(dd[u], aa[v], dwacc[k][u * 4 + v]);
+          }
+        }
       }
     }
     __syncthreads();                           // dW has read every dz element: da may now overwrite dz in place
-    // ---- da[p][i] = sum_o W[o][i] dz[p][o].  The G = C/4 threads of a pixel sit in ONE warp (32/G pixels per
-    // warp pass), so a pixel's dz row is replaced by its da row between two __syncwarp()s.
+    // ---- da[p][i] = sum_o W[o][i] dz[p][o].  The G threads of a pixel sit in ONE warp (32/G pixels per warp
+    // pass), so a pixel's dz row is replaced by its da row between two __syncwarp()s.
     {
-      const int G = C >> 2;
       const int warp = tid >> 5, lane = tid & 31;
       const int ppw = 32 / G;
-      const int pl = lane / G, ig = lane - pl * G;
+      const int pl = fdiv(lane, divG), ig = lane - pl * G;
       for (int p0 = warp * ppw; p0 < TP; p0 += 8 * ppw) {
         const int p = p0 + pl;
         const bool act = pl < ppw && p < TP;
@@ -360,21 +396,22 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
         if (act) {
           if (PERM) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] = d_s[p * LD + sinv[ig * 4 + u]];
+            for (int u = 0; u < 4; ++u) acc[u] = d_s[p * C + sinv[ig * 4 + u]];
           } else {
-            for (int o = 0; o < C; ++o) {
-              const float d = d_s[p * LD + o];
-              const float4 wv = *reinterpret_cast<const float4*>(ws + o * C + ig * 4);
-              acc[0] = fmaf(wv.x, d, acc[0]); acc[1] = fmaf(wv.y, d, acc[1]);
-              acc[2] = fmaf(wv.z, d, acc[2]); acc[3] = fmaf(wv.w, d, acc[3]);
+            for (int o = 0; o < C; o += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + o);
+              const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 wv = *reinterpret_cast<const float4*>(ws + (o + u) * C + ig * 4);
+                acc[0] = fmaf(wv.x, dd[u], acc[0]); acc[1] = fmaf(wv.y, dd[u], acc[1]);
+                acc[2] = fmaf(wv.z, dd[u], acc[2]); acc[3] = fmaf(wv.w, dd[u], acc[3]);
+              }
             }
           }
         }
         __syncwarp();
-        if (act) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) d_s[p * LD + ig * 4 + u] = acc[u];
-        }
+        if (act) *reinterpret_cast<float4*>(d_s + p * C + ig * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         __syncwarp();
       }
     }
@@ -383,27 +420,49 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     if (has_an) {
       const int chunks = 256 / C;
       if (tid < chunks * C) {
-        const int i = tid % C, ch = tid / C;
+        const int ch = tid / C, i = tid - ch * C;
         float sg = 0.f, sga = 0.f;
         for (int p = ch; p < TP; p += chunks) {
-          const float d = d_s[p * LD + i];
-          sg += d; sga = fmaf(d, a_s[p * LD + i], sga);
+          const float d = d_s[p * C + i];
+          sg += d; sga = fmaf(d, a_s[p * C + i], sga);
         }
         atomicAdd(&s_red[i], sg);
         atomicAdd(&s_red[C + i], sga);
       }
     }
     // ---- dx = da * s, written back as whole pixels
-    for (int e = tid; e < TP * C; e += 256) {
-      const int p = e / C, c = e - p * C;
-      const int pix = g0 + p;
-      if (pix < NP) dx[(int64_t)pix * C + c] = d_s[p * LD + c] * sc[c];
+    if (slot < ppb) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + quad * 4);
+      for (int p = slot; p < TP; p += ppb) {
+        const int pix = g0 + p;
+        if (pix < NP) {
+          const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + quad * 4);
+          *reinterpret_cast<float4*>(dx + (int64_t)pix * C + quad * 4) =
+              make_float4(d4.x * s4.x, d4.y * s4.y, d4.z * s4.z, d4.w * s4.w);
+        }
+      }
     }
     __syncthreads();                           // the tile buffers are free for the next tile
   }
-  // ---- one round of global atomics per CTA
-  if (!PERM)
-    for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, s_dw[e]);
+  // ---- one round of global atomics per CTA: dW blocks are first combined in shared memory (W is dead now)
+  if (!PERM) {
+    for (int e = tid; e < C * C; e += 256) ws[e] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RMB_MAXIT; ++k) {
+      const int it = tid + k * 256;
+      if (it < nitems) {
+        const int ps = it / nb4, blk = it - ps * nb4;
+        const int bo = fdiv(blk, divG), bi = blk - bo * G;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) atomicAdd(&ws[(bo * 4 + u) * C + bi * 4 + v], dwacc[k][u * 4 + v]);
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, ws[e]);
+  }
   if (has_an)
     for (int c = tid; c < C; c += 256) {
       atomicAdd(dbias + c, s_red[c] * sc[c]);
@@ -663,21 +722,23 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr), "glowk_rows_actnorm_mix: bias and logs go together");
   GLOWK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= ROWS_MAX_C, "glowk_rows_actnorm_mix: C=%lld must be a multiple of 4, <= %d", (long long)C, ROWS_MAX_C);
   GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)z) & 15) == 0, "glowk_rows_actnorm_mix: rows must be 16-byte aligned");
-  const int64_t threads = P * (C / 4);
-  const unsigned grid = (unsigned)ceil_div(threads, 256);
+  GLOWK_CHECK_ARG(P * C < (1ll << 31), "glowk_rows_actnorm_mix: tensor too large for 32-bit indexing");
+  const int G = (int)C / 4, ppb = 256 / G;
+  const dim3 block((unsigned)G, (unsigned)ppb);
+  const unsigned grid = (unsigned)ceil_div(P, ppb);
   cudaStream_t st = (cudaStream_t)stream;
   if (w) {
     const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, 256, smem, st, x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse));
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse));
   } else {
     const size_t smem = sizeof(float) * (3 * (size_t)C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, 256, smem, st, x, z, w, idx, bias, logs, logscale_factor, P, (int)C, reverse));
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse));
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
   return GLOWK_OK;
 }
 
-extern "C" int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C) { return ceil_div(HW * (C / 2), 256); }
+extern "C" int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C) { return ceil_div(HW, 256 / (C / 2)); }
 
 extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bias3, const float* logs3,
                                    float logscale_factor, float* z, float* h_save, int64_t N, int64_t C, int64_t H,
@@ -691,11 +752,13 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
   GLOWK_CHECK_ARG(ldp >= 9 * Cout && ldp % 2 == 0, "glowk_rows_coupling: ldp=%lld too small for 9*Cout=%lld", (long long)ldp, (long long)(9 * Cout));
   GLOWK_CHECK_ARG(!ld_out || (partials && tickets), "glowk_rows_coupling: logdet output needs partials and tickets");
   GLOWK_CHECK_ARG(N <= 65535 && H * W * C < (1ll << 30), "glowk_rows_coupling: shape out of range");
-  dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
-  GLOWK_CUDA(launch_pdl(rows_coupling_kernel, grid, 256, 0, (cudaStream_t)stream, P3, ldp, bias3, logs3, logscale_factor, z, h_save,
-                                                                (int)C, (int)H, (int)W, affine, reverse, ld_in, ld_out,
-                                                                an_logs, an_logscale_factor, logabsdet, sign, partials,
-                                                                (unsigned int*)tickets));
+  GLOWK_CHECK_ARG(N * H * W * ldp < (1ll << 31), "glowk_rows_coupling: P3 too large for 32-bit tap offsets");
+  const int Ch = (int)C / 2, ppb = 256 / Ch;
+  const dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
+  (void)ppb;
+  GLOWK_CUDA(launch_pdl(rows_coupling_kernel, grid, 256, 0, (cudaStream_t)stream, P3, (int)ldp, bias3, logs3, logscale_factor, z, h_save,
+                        (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch), affine, reverse, ld_in, ld_out,
+                        an_logs, an_logscale_factor, logabsdet, sign, partials, (unsigned int*)tickets));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling");
   return GLOWK_OK;
 }
@@ -708,11 +771,12 @@ extern "C" int glowk_rows_coupling_bwd(const float* y, const float* hrows, const
   GLOWK_CHECK_ARG(y && hrows && dy && logs3 && dz && du && dlogs3 && dbias3, "glowk_rows_coupling_bwd: null pointer");
   GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling_bwd: bad channel count");
   const int64_t NP = N * HW;
-  const int ppb = 256 / (int)(C / 2);
+  GLOWK_CHECK_ARG(NP * C < (1ll << 31), "glowk_rows_coupling_bwd: tensor too large for 32-bit indexing");
+  const int Ch = (int)(C / 2), ppb = 256 / Ch;
   const int iters = bwd_iters(NP, ppb);
   const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
-  GLOWK_CUDA(launch_pdl(rows_coupling_bwd_kernel, grid, 256, 0, (cudaStream_t)stream, y, hrows, dy, dld, logs3, logscale_factor, dz, du,
-                                                                    dlogs3, dbias3, NP, (int)C, (int)HW, affine, iters));
+  GLOWK_CUDA(launch_pdl(rows_coupling_bwd_kernel, grid, dim3((unsigned)Ch, (unsigned)ppb), 0, (cudaStream_t)stream, y, hrows, dy, dld,
+                        logs3, logscale_factor, dz, du, dlogs3, dbias3, (int)NP, (int)C, make_fastdiv(HW), affine, iters));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling_bwd");
   return GLOWK_OK;
 }
@@ -735,18 +799,22 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   GLOWK_CHECK_ARG(NP * C < (1ll << 31), "glowk_rows_actnorm_mix_bwd: tensor too large for 32-bit indexing");
   int TP = 128;                                                  // smaller tiles until every SM has two CTAs
   while (TP > 32 && ceil_div(NP, TP) < 2 * sm_count()) TP >>= 1;
-  const size_t smem = sizeof(float) * (2 * (size_t)TP * (C + 1) + (w ? 2 * (size_t)C * C : 0) + 5 * (size_t)C + 33);
+  const size_t smem = sizeof(float) * (2 * (size_t)TP * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
   int64_t tiles = ceil_div(NP, TP);
   const unsigned grid = (unsigned)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
   cudaStream_t st = (cudaStream_t)stream;
+  GLOWK_CHECK_ARG(NP * (ld_a1 > C ? ld_a1 : C) < (1ll << 31), "glowk_rows_actnorm_mix_bwd: operands too large for 32-bit offsets");
+  GLOWK_CHECK_ARG(!dA1 || (Cin % 2 == 0 && ld_a1 % 2 == 0 && ((uintptr_t)dA1) % 8 == 0), "glowk_rows_actnorm_mix_bwd: dA1 needs even Cin / pitch");
+  GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)dz | (uintptr_t)dx) & 15) == 0, "glowk_rows_actnorm_mix_bwd: rows must be 16-byte aligned");
+  const FastDiv dW_ = make_fastdiv(W), dHW = make_fastdiv(H * W), dG = make_fastdiv(C / 4);
   if (w) {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<false>, grid, 256, smem, st, x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                        dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv));
+    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<false>, grid, 256, smem, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                          dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, TP, dld, (int)N, winv));
   } else {
     if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<true>, grid, 256, smem, st, x, dz, dA1, ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                                                       dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, TP, dld, (int)N, winv));
+    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<true>, grid, 256, smem, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
+                          dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, TP, dld, (int)N, winv));
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd");
   return GLOWK_OK;
