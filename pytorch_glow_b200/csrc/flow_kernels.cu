@@ -311,46 +311,56 @@ __global__ void im2col_kernel(const float* __restrict__ src, int64_t ld_src, int
   }
 }
 
-// im2col of a 3x3 SAME conv from a pixel-major fp32 source into bf16 rows, one thread per (pixel, tap): the
-// Cin channels of a tap are contiguous on both sides, so they move as V-float loads and V-bf16 stores
-// (slot 9 of a pixel zero-fills the K-padding columns).  Needs Cin, c0, ld_src multiples of V.
+// im2col of a 3x3 SAME conv from a pixel-major fp32 source into bf16 rows, ONE WARP PER PIXEL: lane l owns
+// V consecutive output columns k = (pass*32 + l)*V .. +V-1 (V in {2,4,8} divides Cin, so the V values of a lane
+// belong to one tap and are contiguous on both sides: one vector load, one vector store, and the pixel's whole
+// row is written as coalesced 32*V*2-byte segments).  Pixel coordinates are warp-uniform; columns >= 9*Cin are
+// written as zeros by the same instruction stream (no divergent padding loop).
 template <int V>
-__global__ void im2col_rows_tap_kernel(const float* __restrict__ src, int64_t ld_src, int64_t NP, int c0, int Cin,
-                                       int H, int W, int flip, __nv_bfloat16* __restrict__ dst, int64_t ld) {
+__global__ void __launch_bounds__(256)
+im2col_rows_warp_kernel(const float* __restrict__ src, int ld_src, int NP, int c0, int Cin, int H, int W,
+                        FastDiv divW, FastDiv divHW, FastDiv divCin, int flip, __nv_bfloat16* __restrict__ dst, int ld) {
   pdl_trigger();
   pdl_wait();
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= NP * 10) return;
-  const int64_t pix = e / 10;
-  const int slot = (int)(e - pix * 10);
-  __nv_bfloat16* drow = dst + pix * ld;
-  const int K = 9 * Cin;
-  if (slot == 9) {
-    for (int k = K; k < ld; k += 2) *reinterpret_cast<uint32_t*>(drow + k) = 0u;
-    return;
-  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * 8 + warp;
+  if (pix >= NP) return;
   const int HW = H * W;
-  const int64_t n = pix / HW;
-  const int p = (int)(pix - n * HW);
-  const int yy = p / W, xx = p - yy * W;
-  const int tt = flip ? 8 - slot : slot;
-  const int ky = tt / 3, kx = tt - ky * 3;
-  const int sy = yy + ky - 1, sx = xx + kx - 1;
-  const bool inb = sy >= 0 && sy < H && sx >= 0 && sx < W;
-  const float* sp = src + (n * HW + (int64_t)(inb ? sy : 0) * W + (inb ? sx : 0)) * ld_src + c0;
-  __nv_bfloat16* d = drow + slot * Cin;
-#pragma unroll 3
-  for (int c = 0; c < Cin; c += V) {
-    if (V == 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (inb) v = *reinterpret_cast<const float4*>(sp + c);
-      __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
-      *reinterpret_cast<uint2*>(d + c) = *reinterpret_cast<uint2*>(h);
-    } else {
-      float2 v = make_float2(0.f, 0.f);
-      if (inb) v = *reinterpret_cast<const float2*>(sp + c);
-      *reinterpret_cast<__nv_bfloat162*>(d + c) = __floats2bfloat162_rn(v.x, v.y);
+  const int n = fdiv(pix, divHW);
+  const int p = pix - n * HW;
+  const int yy = fdiv(p, divW), xx = p - yy * W;
+  const int K = 9 * Cin;
+  const float* sbase = src + (int64_t)pix * ld_src + c0;            // this pixel; taps are +-W, +-1 rows away
+  __nv_bfloat16* drow = dst + (int64_t)pix * ld;
+  for (int k = lane * V; k < ld; k += 32 * V) {
+    float v[V];
+#pragma unroll
+    for (int u = 0; u < V; ++u) v[u] = 0.f;
+    if (k < K) {
+      const int tap = fdiv(k, divCin), ci = k - tap * Cin;
+      const int tt = flip ? 8 - tap : tap;
+      const int ky = tt / 3, kx = tt - ky * 3;
+      const int sy = yy + ky - 1, sx = xx + kx - 1;
+      if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+        const float* sp = sbase + ((ky - 1) * W + (kx - 1)) * ld_src + ci;
+        if (V == 2) {
+          const float2 t = *reinterpret_cast<const float2*>(sp);
+          v[0] = t.x; v[1] = t.y;
+        } else {
+#pragma unroll
+          for (int q = 0; q < V / 4; ++q) {
+            const float4 t = *reinterpret_cast<const float4*>(sp + 4 * q);
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+          }
+        }
+      }
     }
+    __nv_bfloat162 h[V / 2];
+#pragma unroll
+    for (int u = 0; u < V / 2; ++u) h[u] = __floats2bfloat162_rn(v[2 * u], v[2 * u + 1]);
+    if (V == 2) *reinterpret_cast<__nv_bfloat162*>(drow + k) = h[0];
+    else if (V == 4) *reinterpret_cast<uint2*>(drow + k) = *reinterpret_cast<uint2*>(h);
+    else *reinterpret_cast<uint4*>(drow + k) = *reinterpret_cast<uint4*>(h);
   }
 }
 
@@ -645,13 +655,17 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
   const int64_t total = NP * (ld / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (rows_src && ksize == 3 && act_dtype == GLOWK_BF16 && Cin % 2 == 0 && c0 % 2 == 0 && ld_src % 2 == 0 &&
-      ((uintptr_t)src) % 16 == 0) {
-    const unsigned g10 = (unsigned)ceil_div(NP * 10, 256);
-    if (Cin % 4 == 0 && c0 % 4 == 0 && ld_src % 4 == 0)
-      GLOWK_CUDA(launch_pdl(im2col_rows_tap_kernel<4>, g10, 256, 0, st, src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld));
+      ((uintptr_t)src) % 16 == 0 && NP * (ld > ld_src ? ld : ld_src) < (1ll << 31)) {
+    const unsigned gw = (unsigned)ceil_div(NP, 8);
+    const FastDiv dW_ = make_fastdiv(W), dHW = make_fastdiv(H * W), dC = make_fastdiv(Cin);
+    __nv_bfloat16* d = (__nv_bfloat16*)dst;
+    if (Cin % 8 == 0 && c0 % 4 == 0 && ld_src % 4 == 0)
+      GLOWK_CUDA(launch_pdl(im2col_rows_warp_kernel<8>, gw, 256, 0, st, src, (int)ld_src, (int)NP, (int)c0, (int)Cin, (int)H, (int)W, dW_, dHW, dC, flip, d, (int)ld));
+    else if (Cin % 4 == 0 && c0 % 4 == 0 && ld_src % 4 == 0)
+      GLOWK_CUDA(launch_pdl(im2col_rows_warp_kernel<4>, gw, 256, 0, st, src, (int)ld_src, (int)NP, (int)c0, (int)Cin, (int)H, (int)W, dW_, dHW, dC, flip, d, (int)ld));
     else
-      GLOWK_CUDA(launch_pdl(im2col_rows_tap_kernel<2>, g10, 256, 0, st, src, ld_src, NP, (int)c0, (int)Cin, (int)H, (int)W, flip, (__nv_bfloat16*)dst, ld));
-    GLOWK_CHECK_LAUNCH("glowk_im2col_rows(tap)");
+      GLOWK_CUDA(launch_pdl(im2col_rows_warp_kernel<2>, gw, 256, 0, st, src, (int)ld_src, (int)NP, (int)c0, (int)Cin, (int)H, (int)W, dW_, dHW, dC, flip, d, (int)ld));
+    GLOWK_CHECK_LAUNCH("glowk_im2col_rows(warp)");
     return GLOWK_OK;
   }
   const unsigned grid = (unsigned)ceil_div(total, 256);

@@ -106,7 +106,8 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 __global__ void __launch_bounds__(256)
 rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restrict__ bias3,
                      const float* __restrict__ logs3, float f, float* __restrict__ z,
-                     float* __restrict__ h_save, int C, int H, int W, FastDiv divW, FastDiv divCh, int affine, int reverse,
+                     float* __restrict__ h_save, int C, int H, int W, FastDiv divW, FastDiv divCh, int ppb, int iters,
+                     int affine, int reverse,
                      const float* __restrict__ ld_in, float* __restrict__ ld_out,
                      const float* __restrict__ an_logs, float an_f, const float* __restrict__ logabsdet,
                      float sign, float* __restrict__ partials, unsigned int* __restrict__ tickets) {
@@ -121,12 +122,12 @@ rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restr
   // shuffle reductions below)
   const int tid = threadIdx.x, nthr = 256;
   const int slot = fdiv(tid, divCh), j = tid - slot * Ch;
-  const int ppb = 256 / Ch;
   for (int c = tid; c < Cout; c += nthr) { s_b[c] = bias3[c]; s_e[c] = expf(logs3[c] * f); }
   __syncthreads();
   float lsum = 0.f;
-  const int pix = blockIdx.x * ppb + slot;
-  if (slot < ppb && pix < HW) {
+  for (int it = 0; it < iters; ++it) {
+    const int pix = (blockIdx.x * iters + it) * ppb + slot;
+    if (slot >= ppb || pix >= HW) break;
     const int yy = fdiv(pix, divW), xx = pix - yy * W;
     const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
     const int64_t row = (int64_t)n * HW + pix;
@@ -266,9 +267,8 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
 // most shared accesses are float4).  dW is accumulated in registers over ALL the CTA's tiles as 4x4 blocks
 // (x a split of the tile's pixels, so that all 256 threads work) and leaves the CTA once, like dbias / dlogs.
 // ------------------------------------------------------------------------------------------
-constexpr int RMB_MAXIT = 3;     // 4x4 dW blocks per thread: (C/4)^2 <= 3*256  (C <= 96 -> 576)
-
-template <bool PERM>
+// RMB_MAXIT = 4x4 dW blocks per thread: 1 while (C/4)^2 <= 256 (C <= 64), 3 up to C = 96 (576 blocks)
+template <bool PERM, int RMB_MAXIT>
 __global__ void __launch_bounds__(256)
 rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
                     int ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
@@ -312,6 +312,10 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
   for (int k = 0; k < RMB_MAXIT; ++k)
 #pragma unroll
     for (int u = 0; u < 16; ++u) dwacc[k][u] = 0.f;
+  // channel reductions: thread (channel i, pixel chunk ch) keeps its partial sums over all tiles
+  const int chunks = 256 / C;
+  const int red_ch = tid / C, red_i = tid - red_ch * C;
+  float sg_acc = 0.f, sga_acc = 0.f;
 
   const int ntiles = (NP + TP - 1) / TP;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -416,18 +420,11 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
       }
     }
     __syncthreads();
-    // ---- per-channel reductions over the tile's pixels
-    if (has_an) {
-      const int chunks = 256 / C;
-      if (tid < chunks * C) {
-        const int ch = tid / C, i = tid - ch * C;
-        float sg = 0.f, sga = 0.f;
-        for (int p = ch; p < TP; p += chunks) {
-          const float d = d_s[p * C + i];
-          sg += d; sga = fmaf(d, a_s[p * C + i], sga);
-        }
-        atomicAdd(&s_red[i], sg);
-        atomicAdd(&s_red[C + i], sga);
+    // ---- per-channel reductions over the tile's pixels (registers; flushed once per CTA)
+    if (has_an && red_ch < chunks) {
+      for (int p = red_ch; p < TP; p += chunks) {
+        const float d = d_s[p * C + red_i];
+        sg_acc += d; sga_acc = fmaf(d, a_s[p * C + red_i], sga_acc);
       }
     }
     // ---- dx = da * s, written back as whole pixels
@@ -444,7 +441,11 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     }
     __syncthreads();                           // the tile buffers are free for the next tile
   }
-  // ---- one round of global atomics per CTA: dW blocks are first combined in shared memory (W is dead now)
+  // ---- one round of global atomics per CTA: partials are first combined in shared memory (W is dead now)
+  if (has_an && red_ch < chunks) {
+    atomicAdd(&s_red[red_i], sg_acc);
+    atomicAdd(&s_red[C + red_i], sga_acc);
+  }
   if (!PERM) {
     for (int e = tid; e < C * C; e += 256) ws[e] = 0.f;
     __syncthreads();
@@ -463,6 +464,7 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     __syncthreads();
     for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, ws[e]);
   }
+  __syncthreads();
   if (has_an)
     for (int c = tid; c < C; c += 256) {
       atomicAdd(dbias + c, s_red[c] * sc[c]);
@@ -738,7 +740,14 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   return GLOWK_OK;
 }
 
-extern "C" int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C) { return ceil_div(HW, 256 / (C / 2)); }
+// pixel groups per CTA: enough to amortise the per-CTA reduction tail, few enough to keep >= ~4 CTAs per SM busy
+static inline int coupling_iters(int64_t HW, int64_t C) {
+  const int64_t groups = ceil_div(HW, 256 / (C / 2));
+  return groups >= 16 ? 4 : (groups >= 4 ? 2 : 1);
+}
+extern "C" int64_t glowk_rows_coupling_nblk(int64_t HW, int64_t C) {
+  return ceil_div(ceil_div(HW, 256 / (C / 2)), coupling_iters(HW, C));
+}
 
 extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bias3, const float* logs3,
                                    float logscale_factor, float* z, float* h_save, int64_t N, int64_t C, int64_t H,
@@ -755,9 +764,8 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
   GLOWK_CHECK_ARG(N * H * W * ldp < (1ll << 31), "glowk_rows_coupling: P3 too large for 32-bit tap offsets");
   const int Ch = (int)C / 2, ppb = 256 / Ch;
   const dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
-  (void)ppb;
   GLOWK_CUDA(launch_pdl(rows_coupling_kernel, grid, 256, 0, (cudaStream_t)stream, P3, (int)ldp, bias3, logs3, logscale_factor, z, h_save,
-                        (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch), affine, reverse, ld_in, ld_out,
+                        (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch), ppb, coupling_iters(H * W, C), affine, reverse, ld_in, ld_out,
                         an_logs, an_logscale_factor, logabsdet, sign, partials, (unsigned int*)tickets));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling");
   return GLOWK_OK;
@@ -801,21 +809,28 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   while (TP > 32 && ceil_div(NP, TP) < 2 * sm_count()) TP >>= 1;
   const size_t smem = sizeof(float) * (2 * (size_t)TP * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
   int64_t tiles = ceil_div(NP, TP);
-  const unsigned grid = (unsigned)(tiles < 2 * sm_count() ? tiles : 2 * sm_count());
   cudaStream_t st = (cudaStream_t)stream;
   GLOWK_CHECK_ARG(NP * (ld_a1 > C ? ld_a1 : C) < (1ll << 31), "glowk_rows_actnorm_mix_bwd: operands too large for 32-bit offsets");
   GLOWK_CHECK_ARG(!dA1 || (Cin % 2 == 0 && ld_a1 % 2 == 0 && ((uintptr_t)dA1) % 8 == 0), "glowk_rows_actnorm_mix_bwd: dA1 needs even Cin / pitch");
   GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)dz | (uintptr_t)dx) & 15) == 0, "glowk_rows_actnorm_mix_bwd: rows must be 16-byte aligned");
   const FastDiv dW_ = make_fastdiv(W), dHW = make_fastdiv(H * W), dG = make_fastdiv(C / 4);
-  if (w) {
-    if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<false>, grid, 256, smem, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                          dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, TP, dld, (int)N, winv));
-  } else {
-    if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(rows_mix_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GLOWK_CUDA(launch_pdl(rows_mix_bwd_kernel<true>, grid, 256, smem, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs, logscale_factor,
-                          dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, TP, dld, (int)N, winv));
-  }
+  const bool big = (C / 4) * (C / 4) > 256;
+#define GLOWK_RMB_LAUNCH(PERM_, IT_)                                                                                     \
+  do {                                                                                                                   \
+    auto kern = rows_mix_bwd_kernel<PERM_, IT_>;                                                                         \
+    if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    int occ = 1;                                                                                                         \
+    GLOWK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));                                    \
+    if (occ < 1) occ = 1;                                                                                                \
+    const int64_t cap = (int64_t)occ * sm_count();            /* persistent: every CTA resident, walks several tiles */ \
+    const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);                                                         \
+    GLOWK_CUDA(launch_pdl(kern, grid, 256, smem, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs,               \
+                          logscale_factor, dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, TP, dld, \
+                          (int)N, winv));                                                                                \
+  } while (0)
+  if (w) { if (big) GLOWK_RMB_LAUNCH(false, 3); else GLOWK_RMB_LAUNCH(false, 1); }
+  else { if (big) GLOWK_RMB_LAUNCH(true, 3); else GLOWK_RMB_LAUNCH(true, 1); }
+#undef GLOWK_RMB_LAUNCH
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd");
   return GLOWK_OK;
 }

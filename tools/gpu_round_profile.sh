@@ -16,6 +16,6 @@ COMMON="--profile-from-start off --set full --import-source on --clock-control n
 timeout 600 ncu $COMMON -k regex:"gemm_tc_kernel<4" -s 129 -c 1 -o gpurun_out/${R}_dgrad2 python $ARGS > gpurun_out/${R}_ncu_full.log 2>&1
 timeout 600 ncu $COMMON -k regex:wgrad_tc_kernel -s 195 -c 1 -o gpurun_out/${R}_wgrad2 python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
 timeout 600 ncu $COMMON -k regex:"gemm_tc_kernel<1" -s 1 -c 1 -o gpurun_out/${R}_conv2 python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
-timeout 600 ncu $COMMON -k regex:"rows_coupling_kernel|rows_mix_kernel|im2col_rows_tap" -c 3 -o gpurun_out/${R}_flow_fwd python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
+timeout 600 ncu $COMMON -k regex:"rows_coupling_kernel|rows_mix_kernel|im2col_rows_warp" -c 3 -o gpurun_out/${R}_flow_fwd python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
 grep -E "Report|rror" gpurun_out/${R}_ncu_full.log
 ls -la gpurun_out/${R}_*.ncu-rep
