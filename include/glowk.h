@@ -284,8 +284,10 @@ int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* 
 
 /* One launch for many glowk_pack_conv_weight / glowk_unpack_weight_grad calls.  jobs: device array of
  *   struct { const float* w; void* packed; int32 O, I, ks, layout, rows, ld; int64 block0; }   (48 bytes)
- * sorted by block0 = index of the job's first CTA (256 elements per CTA: rows*ld elements when packing,
- * O*I*ks*ks when unpacking); total_blocks = sum over jobs.  Unpack ACCUMULATES into w (a gradient). */
+ * sorted by block0 = index of the job's first CTA; total_blocks = sum over jobs.  Packing uses one CTA per
+ * 32 x 32 (out x in channel) tile, i.e. ceil(O/32)*ceil(I/32) CTAs per job, and writes only the O*I*ks*ks data
+ * elements (the padding of `packed` must already be zero); unpacking uses one CTA per 256 of the O*I*ks*ks
+ * gradient elements and ACCUMULATES into w (a gradient). */
 int glowk_pack_conv_weights_batched(const void* jobs, int64_t njobs, int64_t total_blocks, int act_dtype, void* stream);
 int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs, int64_t total_blocks, void* stream);
 

@@ -22,7 +22,7 @@ template <bool PERM>
 __global__ void __launch_bounds__(256)
 rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
                 const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
-                float f, int P, int C, int reverse) {
+                float f, int P, int C, int reverse, int iters) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float smem[];
@@ -45,7 +45,8 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 #pragma unroll
       for (int u = 0; u < 4; ++u) wt[(og * 4 + u) * C + o] = w[o * C + og * 4 + u];
   __syncthreads();
-  const int pix = blockIdx.x * blockDim.y + slot;
+  for (int it = 0; it < iters; ++it) {
+  const int pix = (blockIdx.x * iters + it) * blockDim.y + slot;
   if (pix >= P) return;
   const float* xr = x + (int64_t)pix * C;
   float acc[4];
@@ -92,6 +93,7 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
     }
   }
   *reinterpret_cast<float4*>(z + (int64_t)pix * C + og * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -636,7 +638,7 @@ struct PackJob {           // 48 bytes, mirrored by pytorch_glow_b200/rows_path.
   void* packed;            // GEMM-layout copy   (unpack: fp32 source)
   int32_t O, I, ks, layout;
   int32_t rows, ld;
-  int64_t block0;          // first CTA of this job (256 elements per CTA)
+  int64_t block0;          // first CTA of this job (pack: one CTA per 32x32 channel tile; unpack: 256 elements per CTA)
 };
 
 __device__ __forceinline__ int find_job(const PackJob* jobs, int njobs, int64_t blk) {
@@ -661,21 +663,52 @@ __device__ __forceinline__ bool packed_coords(int layout, int O, int I, int T2, 
   return false;
 }
 
+// One CTA packs a 32 (out channels) x 32 (in channels) x k*k tile: coalesced reads of the fp32 parameter (the
+// 32*k*k values of an output channel's tile are contiguous), staged in shared memory, written as 64-byte runs
+// of whichever index is contiguous in the destination layout.  Padding rows / columns of the destination are
+// never written: the arena they live in is zero-filled once (rows_path.PackPlan).
+constexpr int PK_T = 32;
+
 template <typename T>
-__global__ void pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
   pdl_wait();
   __shared__ int s_job;
+  __shared__ float tile[PK_T * (PK_T * 9 + 1)];
   if (threadIdx.x == 0) s_job = find_job(jobs, njobs, blockIdx.x);
   __syncthreads();
   const PackJob jb = jobs[s_job];
-  const int64_t e = ((int64_t)blockIdx.x - jb.block0) * 256 + threadIdx.x;
-  if (e >= (int64_t)jb.rows * jb.ld) return;
-  const int64_t r = e / jb.ld, col = e - r * jb.ld;
   const int T2 = jb.ks * jb.ks;
-  int o, i, tap;
-  float v = 0.f;
-  if (packed_coords(jb.layout, jb.O, jb.I, T2, r, col, &o, &i, &tap)) v = jb.w[((int64_t)o * jb.I + i) * T2 + tap];
-  reinterpret_cast<T*>(jb.packed)[e] = from_f32<T>(v);
+  const int tiles_i = (jb.I + PK_T - 1) / PK_T;
+  const int tb = (int)(blockIdx.x - jb.block0);
+  const int o0 = (tb / tiles_i) * PK_T, i0 = (tb % tiles_i) * PK_T;
+  const int no = min(PK_T, jb.O - o0), ni = min(PK_T, jb.I - i0);
+  const int run = ni * T2;                          // contiguous source floats per output channel
+  const int ostride = PK_T * T2 + 1;                // +1: conflict-free when o is the fast index below
+  for (int e = threadIdx.x; e < no * run; e += 256) {
+    const int o = e / run, r = e - o * run;
+    tile[o * ostride + r] = jb.w[((int64_t)(o0 + o) * jb.I + i0) * T2 + r];
+  }
+  __syncthreads();
+  T* dst = reinterpret_cast<T*>(jb.packed);
+  const int64_t ld = jb.ld;
+  if (jb.layout == 0 || jb.layout == 1) {           // i contiguous: dst[o][tap*I + i] / dst[tap*O + o][i]
+    for (int e = threadIdx.x; e < no * T2 * ni; e += 256) {
+      const int i = e % ni, q = e / ni, tap = q % T2, o = q / T2;
+      const float v = tile[o * ostride + i * T2 + tap];
+      const int64_t d = jb.layout == 0 ? (int64_t)(o0 + o) * ld + (int64_t)tap * jb.I + i0 + i
+                                       : ((int64_t)tap * jb.O + o0 + o) * ld + i0 + i;
+      dst[d] = from_f32<T>(v);
+    }
+  } else {                                          // o contiguous: dst[tap*I + i][o] / dst[i][tap*O + o]
+    for (int e = threadIdx.x; e < no * T2 * ni; e += 256) {
+      const int o = e % no, q = e / no, tap = q % T2, i = q / T2;
+      const float v = tile[o * ostride + i * T2 + tap];
+      const int64_t d = jb.layout == 2 ? ((int64_t)tap * jb.I + i0 + i) * ld + o0 + o
+                                       : (int64_t)(i0 + i) * ld + (int64_t)tap * jb.O + o0 + o;
+      dst[d] = from_f32<T>(v);
+    }
+  }
 }
 
 __global__ void unpack_grads_batched_kernel(const PackJob* __restrict__ jobs, int njobs) {
@@ -727,14 +760,17 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   GLOWK_CHECK_ARG(P * C < (1ll << 31), "glowk_rows_actnorm_mix: tensor too large for 32-bit indexing");
   const int G = (int)C / 4, ppb = 256 / G;
   const dim3 block((unsigned)G, (unsigned)ppb);
-  const unsigned grid = (unsigned)ceil_div(P, ppb);
+  int iters = (int)(ceil_div(P, ppb) / (8 * (int64_t)sm_count()));       // >= 8 CTAs per SM before CTAs start looping
+  if (iters < 1) iters = 1;
+  if (iters > 8) iters = 8;
+  const unsigned grid = (unsigned)ceil_div(P, (int64_t)ppb * iters);
   cudaStream_t st = (cudaStream_t)stream;
   if (w) {
     const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse));
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse, iters));
   } else {
     const size_t smem = sizeof(float) * (3 * (size_t)C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse));
+    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse, iters));
   }
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
   return GLOWK_OK;

@@ -98,7 +98,7 @@ class PackPlan:
         for dt in sorted(set(e[6] for e in entries)):
             mine = [e for e in entries if e[6] == dt]
             numel = sum(e[4] * e[5] for e in mine)
-            arena = torch.empty(numel, device=device, dtype=K.TORCH_DTYPE[dt])
+            arena = torch.zeros(numel, device=device, dtype=K.TORCH_DTYPE[dt])     # padding stays zero for good
             jobs = np.zeros(len(mine), dtype=_JOB)
             views, off, blk = [], 0, 0
             esz = arena.element_size()
@@ -108,7 +108,7 @@ class PackPlan:
                 jobs[i] = (prm.data_ptr(), arena.data_ptr() + off * esz, prm.shape[0], prm.shape[1], prm.shape[2],
                            layout, rows, ld, blk)
                 off += rows * ld
-                blk += (rows * ld + 255) // 256
+                blk += ((prm.shape[0] + 31) // 32) * ((prm.shape[1] + 31) // 32)     # one CTA per 32x32 channel tile
             jobs_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(device)
             self.groups[dt] = (mine, views, arena, jobs_dev, len(mine), blk)
 

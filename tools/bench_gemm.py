@@ -34,13 +34,13 @@ def run(kind, cluster, M=65536):
     torch.manual_seed(0)
     nb = 3
     hid = 512
-    if kind in ("fwd", "bwd", "c1", "c3"):
-        n, k = {"fwd": (512, 512), "bwd": (512, 512), "c1": (512, 64), "c3": (108, 512)}[kind]
+    if kind in ("fwd", "bwd", "bwd3", "c1", "c3"):
+        n, k = {"fwd": (512, 512), "bwd": (512, 512), "bwd3": (512, 128), "c1": (512, 64), "c3": (108, 512)}[kind]
         a = [(torch.randn(M, k, device=DEV) * 0.5).bfloat16() for _ in range(nb)]
         w = (torch.randn((n + 15) // 16 * 16, k, device=DEV) * 0.05).bfloat16()
         bias = torch.randn(n, device=DEV) * 0.1
         logs = torch.randn(n, device=DEV) * 0.05
-        if kind == "bwd":
+        if kind in ("bwd", "bwd3"):
             y = [torch.randn(M, n, device=DEV).clamp_min(0).bfloat16() for _ in range(nb)]
             outs = [torch.empty(M, n, device=DEV, dtype=torch.bfloat16) for _ in range(nb)]
             dl, db = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
