@@ -28,7 +28,7 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (image_shape HWC, K, L, hidden, coupling, default per-GPU batch, fwd GFLOP/img)
-    "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 256, 32.06),
+    "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 512, 32.06),
     "cifar32": ((32, 32, 3), 32, 3, 512, "affine", 256, 8.02),
     "tiny": ((32, 32, 3), 4, 3, 64, "affine", 16, None),
 }

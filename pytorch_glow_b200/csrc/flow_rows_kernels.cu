@@ -18,13 +18,16 @@ constexpr int ROWS_MAX_C = 96;   // shared-memory tiles below are sized for C <=
 // block = (G = C/4 output-channel groups, PPB pixels): thread (og, slot) produces 4 output channels of one
 // pixel; the G lanes of a pixel read the same 16-byte chunks of x (one transaction) and W^T from shared memory.
 // ------------------------------------------------------------------------------------------
-template <bool PERM>
+// CT = compile-time channel count (12 / 24 / 48: the CelebA / CIFAR levels; loops fully unrolled, no predicates),
+// 0 = run-time C.
+template <bool PERM, int CT>
 __global__ void __launch_bounds__(256)
 rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
                 const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
-                float f, int P, int C, int reverse, int iters) {
+                float f, int P, int C_rt, int reverse, int iters) {
   pdl_trigger();
   pdl_wait();
+  const int C = CT ? CT : C_rt;
   extern __shared__ __align__(16) float smem[];
   float* wt = smem;                               // [C][C]: wt[i*C + o] = W[o][i]   (mix only)
   float* sc = wt + (PERM ? 0 : C * C);            // [C] exp(+-f*logs)
@@ -60,6 +63,7 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
     }
   } else {
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll
     for (int i0 = 0; i0 < C; i0 += 24) {
       float4 xb[6];                            // up to 24 channels in flight: one memory latency per batch
 #pragma unroll
@@ -765,13 +769,20 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   if (iters > 8) iters = 8;
   const unsigned grid = (unsigned)ceil_div(P, (int64_t)ppb * iters);
   cudaStream_t st = (cudaStream_t)stream;
+#define GLOWK_MIX_LAUNCH(PERM_, CT_, SMEM_)                                                                          \
+  GLOWK_CUDA(launch_pdl(rows_mix_kernel<PERM_, CT_>, grid, block, SMEM_, st, x, z, w, idx, bias, logs, logscale_factor, \
+                        (int)P, (int)C, reverse, iters))
   if (w) {
     const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<false>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse, iters));
+    if (C == 12) GLOWK_MIX_LAUNCH(false, 12, smem);
+    else if (C == 24) GLOWK_MIX_LAUNCH(false, 24, smem);
+    else if (C == 48) GLOWK_MIX_LAUNCH(false, 48, smem);
+    else GLOWK_MIX_LAUNCH(false, 0, smem);
   } else {
     const size_t smem = sizeof(float) * (3 * (size_t)C);
-    GLOWK_CUDA(launch_pdl(rows_mix_kernel<true>, grid, block, smem, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, reverse, iters));
+    GLOWK_MIX_LAUNCH(true, 0, smem);
   }
+#undef GLOWK_MIX_LAUNCH
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
   return GLOWK_OK;
 }

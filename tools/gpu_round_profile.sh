@@ -13,9 +13,10 @@ python tools/summarize_launches.py gpurun_out/${R}_launches.csv 30 | tee gpurun_
 # full captures (eager step so that launch indices are stable): level-1 instances of the heaviest kernels
 ARGS="bench.py --profile-step --no-graphs --warmup 3"
 COMMON="--profile-from-start off --set full --import-source on --clock-control none -f"
-timeout 600 ncu $COMMON -k regex:"gemm_tc_kernel<4" -s 129 -c 1 -o gpurun_out/${R}_dgrad2 python $ARGS > gpurun_out/${R}_ncu_full.log 2>&1
+timeout 600 ncu $COMMON -k regex:gemm_tc_kernel -s 485 -c 1 -o gpurun_out/${R}_dgrad2 python $ARGS > gpurun_out/${R}_ncu_full.log 2>&1
 timeout 600 ncu $COMMON -k regex:wgrad_tc_kernel -s 195 -c 1 -o gpurun_out/${R}_wgrad2 python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
-timeout 600 ncu $COMMON -k regex:"gemm_tc_kernel<1" -s 1 -c 1 -o gpurun_out/${R}_conv2 python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
+timeout 600 ncu $COMMON -k regex:gemm_tc_kernel -s 1 -c 1 -o gpurun_out/${R}_conv2 python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
 timeout 600 ncu $COMMON -k regex:"rows_coupling_kernel|rows_mix_kernel|im2col_rows_warp" -c 3 -o gpurun_out/${R}_flow_fwd python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
+timeout 600 ncu $COMMON -k regex:"rows_mix_bwd|rows_coupling_bwd" -s 140 -c 2 -o gpurun_out/${R}_flow_bwd python $ARGS >> gpurun_out/${R}_ncu_full.log 2>&1
 grep -E "Report|rror" gpurun_out/${R}_ncu_full.log
 ls -la gpurun_out/${R}_*.ncu-rep
