@@ -6,7 +6,8 @@ same names, signatures and state_dict keys.  All arithmetic runs in hand-written
 CUDA kernels behind the C ABI of include/glowk.h (libglowk.so); there is no CPU
 or eager-PyTorch fallback.
 """
-from . import config
+from . import config, snapshot
+from .inferer import Inferer
 from .model import FlowStep, FlowModel, FlowNet, Glow
 from .module import (ActNorm, LinearZeros, Conv2d, Conv2dZeros, CouplingNet, f, Invertible1x1Conv,
                      Permutation2d, GaussianDiag, Split2d, Squeeze2d)
@@ -18,5 +19,5 @@ SqueezeLayer = Squeeze2d
 __all__ = [
     "FlowStep", "FlowModel", "FlowNet", "Glow", "ActNorm", "LinearZeros", "Conv2d", "Conv2dZeros",
     "CouplingNet", "f", "Invertible1x1Conv", "InvertibleConv1x1", "Permutation2d", "GaussianDiag",
-    "Split2d", "Squeeze2d", "SqueezeLayer", "config",
+    "Split2d", "Squeeze2d", "SqueezeLayer", "config", "snapshot", "Inferer",
 ]
