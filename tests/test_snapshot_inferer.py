@@ -80,7 +80,7 @@ def test_inferer_batched_paths_match_per_sample_loops():
     imgs = torch.rand(10, 3, 16, 16, generator=gen)
     torch.manual_seed(0)
     zs = inf.encode_batch(imgs)                                   # 10 images through batches of h_top.shape[0] = 4
-    assert zs.shape == (10, 12, 4, 4)
+    assert zs.shape == (10, 24, 4, 4)
     # the dequantisation noise makes encode stochastic at the 1/256 level: compare with a tolerance on z
     torch.manual_seed(0)
     z0 = inf.encode(imgs[0])
@@ -91,7 +91,7 @@ def test_inferer_batched_paths_match_per_sample_loops():
     torch.manual_seed(1)
     delta = inf.compute_attribute_delta(batches)
     torch.manual_seed(1)
-    pos = np.zeros((3, 12, 4, 4)); neg = np.zeros_like(pos); npos = np.zeros(3); nneg = np.zeros(3)
+    pos = np.zeros((3, 24, 4, 4)); neg = np.zeros_like(pos); npos = np.zeros(3); nneg = np.zeros(3)
     with torch.no_grad():
         for b in batches:
             z, _, _ = g(b["x"].to(dev))
