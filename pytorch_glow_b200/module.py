@@ -493,6 +493,10 @@ class GaussianDiag:
     def eps(shape_tensor, eps_std=None):
         # torch's own generator on purpose: keeps the noise stream identical to the reference
         eps_std = eps_std or 1.
+        if shape_tensor.is_cuda and torch.cuda.is_current_stream_capturing():
+            # torch.normal(Tensor, Tensor) validates std on the host (a device sync): not capturable.  Same
+            # generator stream and the same arithmetic (N(0,1) draw times std).
+            return torch.randn_like(shape_tensor) * eps_std
         return torch.normal(mean=torch.zeros_like(shape_tensor), std=torch.ones_like(shape_tensor) * eps_std)
 
     @staticmethod
