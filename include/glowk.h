@@ -46,6 +46,10 @@ const char* glowk_last_error(void);
 int glowk_version(void);
 /* 1 if the tcgen05/TMA (bf16) GEMM path is usable on the current device. */
 int glowk_has_tcgen05(void);
+/* Profiling aid: with GLOWK_GEMM_DEBUG=64 in the environment CTA 0 of the tcgen05 GEMM records how many cycles its
+ * TMA / MMA / epilogue roles spent waiting on each other; this copies the 16 counters to a HOST array (it
+ * synchronises the device; see gemm_sm100.cu for the meaning of each slot). */
+int glowk_debug_gemm_trace(unsigned long long* out16_host);
 
 /* ---- ActNorm: network/module.py:34-84,122-149 ------------------------------------------
  * fwd: y = (x + bias[c]) * exp(f*logs[c]);  rev: y = x * exp(-f*logs[c]) - bias[c].

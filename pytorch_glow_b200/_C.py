@@ -24,6 +24,7 @@ SIGNATURES = {
     "glowk_last_error": [],
     "glowk_version": [],
     "glowk_has_tcgen05": [],
+    "glowk_debug_gemm_trace": [_p],
     "glowk_actnorm": [_p, _p, _p, _p, _f32, _i64, _i64, _i64, _i32, _p],
     "glowk_actnorm_init": [_p, _i32, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _p, _p, _p],
     "glowk_invconv_prepare": [_p, _i64, _p, _p, _p],

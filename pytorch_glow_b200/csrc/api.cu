@@ -45,6 +45,7 @@ using namespace glowk;
 extern "C" const char* glowk_last_error(void) { return last_error_buf(); }
 extern "C" int glowk_version(void) { return 100; }
 extern "C" int glowk_has_tcgen05(void) { return tc_available() ? 1 : 0; }
+extern "C" int glowk_debug_gemm_trace(unsigned long long* out16_host) { return gemm_debug_trace(out16_host); }
 
 extern "C" int glowk_gemm(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype, int64_t M,
                           int64_t N, int64_t K, int epilogue, const float* bias, const float* logs,

@@ -57,5 +57,6 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
 int wgrad_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t P, int64_t Mo, int64_t No,
                   float* dW, int64_t lddw, cudaStream_t st);
 bool tc_available();
+int gemm_debug_trace(unsigned long long* out16);
 
 }  // namespace glowk

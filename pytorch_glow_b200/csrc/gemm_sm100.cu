@@ -82,6 +82,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Profiling aid (GLOWK_GEMM_DEBUG bit 64): per-role wait-cycle counters of CTA 0, read back by glowk_debug_gemm_trace.
+//   [0] producer: cycles waiting for free slots   [1] producer: total
+//   [2] MMA: waiting for operands (full)          [3] MMA: waiting for a free accumulator   [4] MMA: total
+//   [5] epilogue warp 0: waiting for accumulators [6] ... for the y box   [7] ... for the staging box (store read)
+//   [8] epilogue warp 0: total                    [9] tiles of CTA 0
+__device__ unsigned long long g_gemm_trace[16];
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, bool on, unsigned long long& acc) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* tm, uint64_t* bar, void* dst, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -207,6 +220,36 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) 
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// ---- CTA pair (cta_group::2): two CTAs of a cluster run ONE 256 x N UMMA; each holds its 128 rows of A and its
+// half of B, the leader (rank 0) issues the MMAs, both epilogues drain their own 128 TMEM lanes.
+__device__ __forceinline__ uint32_t mapa_cluster(const void* local_smem, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem)), "r"(rank));
+  return r;
+}
+// TMA load into MY shared memory whose completion bytes are signalled on an mbarrier of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* tm, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                      uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {      // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 constexpr int EPI_NMAX = 1024;   // column sums of RELU_BWD are kept in shared memory up to this N
 
 // ---------------------------------------------------------------------------------------------
@@ -216,14 +259,18 @@ constexpr int EPI_NMAX = 1024;   // column sums of RELU_BWD are kept in shared m
 // and 1/CM of its B tile and TMA-multicasts the slice to its row / column mates (L2 -> SM traffic per CTA
 // drops from A+B to A/CN + B/CM).
 // ---------------------------------------------------------------------------------------------
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_y, int M, int N,
                int K, int block_n, int num_stages, int CM, int CN, int dbg, EpiParams ep) {
+  // PAIR is a template parameter on purpose: a kernel that contains cta_group::2 instructions can only be launched
+  // as a cluster of an even number of CTAs ("cluster misconfiguration" otherwise)
+  constexpr bool pair = PAIR;
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
-  const uint32_t b_bytes = (uint32_t)block_n * BLOCK_K * 2;
+  // pair mode (CM = 2, CN = 1, cta_group::2): this CTA keeps only ITS half of the B tile (block_n/2 rows)
+  const uint32_t b_bytes = (uint32_t)(pair ? block_n / 2 : block_n) * BLOCK_K * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint8_t* staging = smem + (size_t)num_stages * stage_bytes;
   uint8_t* ybuf = staging + STAGING_BYTES;                                        // RELU_BWD: one 4 KB y box per epilogue warp
@@ -255,14 +302,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_o);
     if (EPI == GLOWK_EPI_RELU_BWD) prefetch_tensormap(&tm_y);
-    for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], (uint32_t)(CM + CN - 1)); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], EPI_WARPS); }
+    // pair mode: one multicast tcgen05.commit frees a slot in both CTAs; the leader's accumulator is free once the
+    // epilogue warps of BOTH CTAs have drained it
+    for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], pair ? 1u : (uint32_t)(CM + CN - 1)); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], pair ? 2 * EPI_WARPS : EPI_WARPS); }
     for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: 512 columns (two accumulator stages), allocated and freed by this warp
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   if (EPI == GLOWK_EPI_RELU_BWD)
     for (int i = threadIdx.x; i < 2 * EPI_NMAX; i += GEMM_THREADS) s_gy[i] = 0.f;
@@ -278,13 +332,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const int a_rows = BLOCK_M / CN, b_rows = block_n / CM;
+      const bool tr = (dbg & 64) && blockIdx.x == 0;
+      unsigned long long w_empty = 0;
+      const long long t_begin = clock64();
       for (int st = cluster_id; st < num_super && !(dbg & 8); st += num_clusters) {
         const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&sh->empty_bar[stage], phase ^ 1);     // every CTA I write into has drained this slot
+          mbar_wait_timed(&sh->empty_bar[stage], phase ^ 1, tr, w_empty);     // every CTA I write into has drained this slot
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           if ((dbg & 1) && (st != cluster_id || kb >= num_stages)) {     // profiling aid: no operand traffic
             mbar_arrive(&sh->full_bar[stage]);
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          if constexpr (PAIR) {
+            // both CTAs' bytes are counted on the LEADER's barrier; the leader alone arms it (2 x stage_bytes)
+            const uint32_t lead_full = mapa_cluster(&sh->full_bar[stage], 0);
+            if (crank == 0) mbar_arrive_expect_tx(&sh->full_bar[stage], 2 * stage_bytes);
+            tma_load_2d_pair(&tm_a, lead_full, sa, kb * BLOCK_K, m_blk * BLOCK_M);
+            tma_load_2d_pair(&tm_b, lead_full, sa + a_bytes, kb * BLOCK_K, n_blk * block_n + cm * (block_n / 2));
             if (++stage == num_stages) { stage = 0; phase ^= 1; }
             continue;
           }
@@ -301,23 +367,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (tr) { g_gemm_trace[0] = w_empty; g_gemm_trace[1] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(block_n, 0, 0);
+    if (lane == 0 && !(pair && crank != 0)) {      // pair mode: the leader CTA issues for both
+      // M field: 128 for one CTA, 256 for the pair
+      const uint32_t idesc = make_idesc(block_n, 0, 0) + (pair ? ((uint32_t)(BLOCK_M >> 4) << 24) : 0u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      const bool tr = (dbg & 64) && blockIdx.x == 0;
+      unsigned long long w_full = 0, w_acc = 0, ntile = 0;
+      const long long t_begin = clock64();
       for (int st = cluster_id; st < num_super; st += num_clusters) {
-        mbar_wait(&sh->tmem_empty_bar[acc], acc_phase ^ 1);
+        ++ntile;
+        mbar_wait_timed(&sh->tmem_empty_bar[acc], acc_phase ^ 1, tr, w_acc);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_STAGE_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (!(dbg & 8)) mbar_wait(&sh->full_bar[stage], phase);   // dbg 8: free-running MMA issue (raw tensor rate)
+          if (!(dbg & 8)) mbar_wait_timed(&sh->full_bar[stage], phase, tr, w_full);   // dbg 8: free-running MMA issue (raw tensor rate)
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + a_bytes, 16, 1024);
+          if constexpr (PAIR) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              tcgen05_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            tcgen05_commit_pair(&sh->empty_bar[stage]);            // frees the slot in both CTAs
+            if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (!(dbg & 2)) {
 #pragma unroll
             for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
@@ -331,9 +411,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           else tcgen05_commit_mc(&sh->empty_bar[stage], mask_all);
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&sh->tmem_full_bar[acc]);        // accumulator complete
+        if constexpr (PAIR) tcgen05_commit_pair(&sh->tmem_full_bar[acc]);        // accumulator complete (both CTAs' halves)
+        else tcgen05_commit(&sh->tmem_full_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (tr) { g_gemm_trace[2] = w_full; g_gemm_trace[3] = w_acc; g_gemm_trace[4] = (unsigned long long)(clock64() - t_begin); g_gemm_trace[9] = ntile; }
     }
   } else {
     // ===================== epilogue warps =====================
@@ -348,6 +430,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint8_t* yrow = my_y + lane * 128;
     int acc = 0; uint32_t acc_phase = 0;
     int cached_nblk = -1;
+    const bool tr = (dbg & 64) && blockIdx.x == 0 && ew == 0;
+    unsigned long long w_tfull = 0, w_y = 0, w_st = 0;
+    const long long t_begin = clock64();
     uint32_t yit = 0;                       // RELU_BWD: y boxes consumed so far by this warp (mbarrier parity)
     auto issue_y = [&](int st, int c0) {
       if (lane == 0) {
@@ -381,7 +466,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         epi_bar_sync();
         cached_nblk = n_blk;
       }
-      mbar_wait(&sh->tmem_full_bar[acc], acc_phase);
+      mbar_wait_timed(&sh->tmem_full_bar[acc], acc_phase, tr, w_tfull);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_STAGE_COLS;
       for (int c0 = half * BOX; c0 < block_n; c0 += 2 * BOX) {
@@ -390,9 +475,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         uint32_t raw[NSUB][32];
 #pragma unroll
         for (int sub = 0; sub < NSUB; ++sub) tmem_ld32_async(t_row + (uint32_t)(c0 + sub * 32), raw[sub]);
-        if (EPI == GLOWK_EPI_RELU_BWD) mbar_wait(&sh->y_bar[ew], yit & 1);
+        if (EPI == GLOWK_EPI_RELU_BWD) mbar_wait_timed(&sh->y_bar[ew], yit & 1, tr, w_y);
         // the TMA store that last read the staging box must have finished reading it
-        if (lane == 0) tma_store_wait_read<0>();
+        {
+          const long long t0 = tr ? clock64() : 0;
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          if (tr) w_st += (unsigned long long)(clock64() - t0);
+        }
         tmem_ld_wait();
         __syncwarp();
 #pragma unroll
@@ -474,7 +564,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(&sh->tmem_empty_bar[acc], 0));     // the leader issues the MMAs
+        else mbar_arrive(&sh->tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (EPI == GLOWK_EPI_RELU_BWD && small_n) {
@@ -485,6 +578,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (a != 0.f || b != 0.f) epilogue_commit_colsums(ep, n, a, b);
       }
     }
+    if (tr && lane == 0) {
+      g_gemm_trace[5] = w_tfull; g_gemm_trace[6] = w_y; g_gemm_trace[7] = w_st;
+      g_gemm_trace[8] = (unsigned long long)(clock64() - t_begin);
+    }
     if (lane == 0) tma_store_wait_all();
   }
 
@@ -493,7 +590,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (csize > 1) cluster_sync_all();        // no CTA may exit while peers still multicast into it
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -691,12 +789,13 @@ static size_t gemm_fixed_smem(int epilogue) {
          (epilogue == GLOWK_EPI_RELU_BWD ? STAGING_BYTES + 2 * EPI_NMAX * sizeof(float) : 0);
 }
 
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, bool PAIR>
 static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& ty,
                           int M, int N, int K, int block_n, int stages, int cm, int cn, const EpiParams& ep,
                           cudaStream_t st) {
-  const size_t smem = (size_t)stages * (BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2) + gemm_fixed_smem(EPI);
-  auto kern = gemm_tc_kernel<EPI, OutT>;
+  const size_t b_rows = PAIR ? block_n / 2 : block_n;
+  const size_t smem = (size_t)stages * (BLOCK_M * BLOCK_K * 2 + b_rows * BLOCK_K * 2) + gemm_fixed_smem(EPI);
+  auto kern = gemm_tc_kernel<EPI, OutT, PAIR>;
   GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int csize = cm * cn;
   const int64_t supers = ceil_div(ceil_div(M, BLOCK_M), cm) * ceil_div(ceil_div(N, block_n), cn);
@@ -730,6 +829,12 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 }
 
 }  // namespace tc
+
+int gemm_debug_trace(unsigned long long* out16) {
+  GLOWK_CUDA(cudaDeviceSynchronize());
+  GLOWK_CUDA(cudaMemcpyFromSymbol(out16, tc::g_gemm_trace, 16 * sizeof(unsigned long long)));
+  return GLOWK_OK;
+}
 
 bool tc_available() {
   int dev = 0, major = 0;
@@ -767,10 +872,19 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
   const int n_blocks = (int)ceil_div(npad, 256);
   int block_n = n_blocks == 1 ? npad : (int)ceil_div(ceil_div(npad, n_blocks), box_cols) * box_cols;
   GLOWK_CHECK_ARG(block_n <= 256 && block_n % 16 == 0, "glowk_gemm(bf16): cannot tile N=%lld", (long long)N);
+  // CTA pairs (tcgen05 cta_group::2): a 256 x 256 tile per pair of SMs, each CTA holding its 128 rows of A and HALF
+  // of the B tile, so the B traffic from L2 (2/3 of a 512 x 512 conv's operand stream, which sits at the L2 cap) is
+  // halved and the ring is 6 x 32 KB deep instead of 4 x 48 KB.  Opt-in while it is being validated: GLOWK_GEMM_PAIR=1.
+  bool pair = false;
+  {
+    const char* penv = getenv("GLOWK_GEMM_PAIR");
+    const bool epi_ok = (epilogue == GLOWK_EPI_ACTNORM_RELU && out_dtype == GLOWK_BF16) || epilogue == GLOWK_EPI_RELU_BWD;
+    if ((cm <= 0 || cn <= 0) && penv && penv[0] == '1' && epi_ok && block_n == 256 && M >= 2 * BLOCK_M) { pair = true; cm = 2; cn = 1; }
+  }
   if (cm <= 0 || cn <= 0) default_cluster(ceil_div(M, BLOCK_M), n_blocks, block_n, &cm, &cn);
   GLOWK_CHECK_ARG(cm * cn <= 8 && (cm & (cm - 1)) == 0 && (cn & (cn - 1)) == 0 && block_n % (8 * cm) == 0 && cn <= 16,
                   "glowk_gemm(bf16): bad cluster shape %dx%d for block_n=%d", cm, cn, block_n);
-  const size_t stage_bytes = BLOCK_M * BLOCK_K * 2 + (size_t)block_n * BLOCK_K * 2;
+  const size_t stage_bytes = BLOCK_M * BLOCK_K * 2 + (size_t)(pair ? block_n / 2 : block_n) * BLOCK_K * 2;
   const int stages = pick_stages(stage_bytes, gemm_fixed_smem(epilogue));
   GLOWK_CHECK_ARG(stages >= 2, "glowk_gemm(bf16): not enough shared memory for a 2-stage pipeline");
 
@@ -787,15 +901,19 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
 #define GLOWK_TC_CASE(E)                                                                                                  \
   case E:                                                                                                                 \
     return out_dtype == GLOWK_BF16                                                                                        \
-               ? launch_gemm_tc<E, __nv_bfloat16>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st) \
-               : launch_gemm_tc<E, float>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
+               ? launch_gemm_tc<E, __nv_bfloat16, false>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st) \
+               : launch_gemm_tc<E, float, false>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
+  if (pair && epilogue == GLOWK_EPI_ACTNORM_RELU && out_dtype == GLOWK_BF16)
+    return launch_gemm_tc<GLOWK_EPI_ACTNORM_RELU, __nv_bfloat16, true>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
+  if (pair && epilogue == GLOWK_EPI_RELU_BWD)
+    return launch_gemm_tc<GLOWK_EPI_RELU_BWD, __nv_bfloat16, true>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
   switch (epilogue) {
     GLOWK_TC_CASE(GLOWK_EPI_STORE)
     GLOWK_TC_CASE(GLOWK_EPI_ACTNORM_RELU)
     GLOWK_TC_CASE(GLOWK_EPI_ACTNORM)
     GLOWK_TC_CASE(GLOWK_EPI_ZEROS)
     case GLOWK_EPI_RELU_BWD:
-      return launch_gemm_tc<GLOWK_EPI_RELU_BWD, __nv_bfloat16>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
+      return launch_gemm_tc<GLOWK_EPI_RELU_BWD, __nv_bfloat16, false>(ta, tb, to, ty, (int)M, (int)N, (int)K, block_n, stages, cm, cn, ep, st);
   }
 #undef GLOWK_TC_CASE
   return fail(GLOWK_EINVAL, "glowk_gemm: unknown epilogue %d", epilogue);

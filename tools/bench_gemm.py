@@ -81,6 +81,15 @@ def run(kind, cluster, M=65536):
     t = timeit(fn)
     print("%-5s cluster=%s M=%d: %8.1f us  %7.1f TFLOP/s  %7.1f GB/s(alg)  max rel err %.2e" % (
         kind, cluster, M, t * 1e6, flops / t / 1e12, byts / t / 1e9, err), flush=True)
+    if int(os.environ.get("GLOWK_GEMM_DEBUG", "0")) & 64:
+        import ctypes
+        buf = (ctypes.c_ulonglong * 16)()
+        _C.lib().glowk_debug_gemm_trace(ctypes.cast(buf, ctypes.c_void_p))
+        v = list(buf)
+        tiles = max(v[9], 1)
+        print("      CTA0 cycles: producer wait-empty %d / total %d | MMA wait-operands %d, wait-accumulator %d / total %d | "
+              "epilogue warp0 wait-acc %d, wait-y %d, wait-staging %d / total %d | tiles %d (%.0f cycles per tile)" % (
+                  v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[4] / tiles), flush=True)
 
 
 if __name__ == "__main__":
