@@ -217,6 +217,52 @@ mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, const 
   }
 }
 
+// Fallback of mix_bwd_kernel for channel counts whose tiles do not fit in shared memory (C >= ~150: levels 5-6 of
+// the 256x256 L=6 configuration).  Correct for any C, not tuned: (a) one thread per (n, i, p) for dx and the
+// per-channel sums, (b) one thread per (o, i) for dW.
+__global__ void mix_bwd_wide_dx_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                       const float* __restrict__ w, const int64_t* __restrict__ idx,
+                                       const float* __restrict__ bias, const float* __restrict__ logs, float f,
+                                       float* __restrict__ dx, float* __restrict__ dlogs, float* __restrict__ dbias,
+                                       int64_t total, int C, int64_t HW) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t p = e % HW;
+  const int i = (int)((e / HW) % C);
+  const int64_t n = e / (HW * C);
+  const bool has_an = bias != nullptr;
+  const float s = has_an ? expf(logs[i] * f) : 1.f;
+  const float a = has_an ? (x[e] + bias[i]) * s : x[e];
+  const float* dzb = dz + n * C * HW + p;
+  float da = 0.f;
+  if (w) {
+    for (int o = 0; o < C; ++o) da = fmaf(w[(int64_t)o * C + i], dzb[(int64_t)o * HW], da);
+  } else {
+    int o = 0;
+    for (int k = 0; k < C; ++k) if ((int)idx[k] == i) o = k;
+    da = dzb[(int64_t)o * HW];
+  }
+  dx[e] = da * s;
+  if (has_an) { atomicAdd(dbias + i, da * s); atomicAdd(dlogs + i, f * da * a); }
+}
+
+__global__ void mix_bwd_wide_dw_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                       const float* __restrict__ bias, const float* __restrict__ logs, float f,
+                                       float* __restrict__ dw, int64_t N, int C, int64_t HW) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)C * C) return;
+  const int o = (int)(e / C), i = (int)(e - (int64_t)o * C);
+  const bool has_an = bias != nullptr;
+  const float s = has_an ? expf(logs[i] * f) : 1.f, b = has_an ? bias[i] : 0.f;
+  float acc = 0.f;
+  for (int64_t n = 0; n < N; ++n) {
+    const float* xr = x + (n * C + i) * HW;
+    const float* dr = dz + (n * C + o) * HW;
+    for (int64_t p = 0; p < HW; ++p) acc = fmaf(dr[p], has_an ? (xr[p] + b) * s : xr[p], acc);
+  }
+  dw[e] += acc;
+}
+
 // Gradient of the sample-independent logdet terms wrt their parameters (module.py:78-82, 357-363):
 //   logdet[n] += HW*(sum_c f*logs_c + log|det W|)  =>  dlogs_c += f*HW*G,  dW += HW*G*W^-T,  G = sum_n dld[n]
 __global__ void logdet_param_grad_kernel(const float* __restrict__ dld, int64_t N, float hw, float f,
@@ -375,9 +421,16 @@ extern "C" int glowk_actnorm_mix_bwd(const float* x, const float* dz, const floa
   GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_actnorm_mix_bwd: exactly one of w / idx");
   GLOWK_CHECK_ARG(!w || dw, "glowk_actnorm_mix_bwd: dw required with w");
   GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr) && (!bias || (dlogs && dbias)), "glowk_actnorm_mix_bwd: actnorm args");
-  GLOWK_CHECK_ARG(HW % 4 == 0, "glowk_actnorm_mix_bwd: H*W must be a multiple of 4");
   const size_t smem = sizeof(float) * (2 * (size_t)C * MB_LD + (w ? (size_t)C * C : 0) + 2 * (size_t)C);
-  GLOWK_CHECK_ARG(smem <= 220 * 1024, "glowk_actnorm_mix_bwd: C=%lld too wide for the shared-memory tile", (long long)C);
+  if (smem > 220 * 1024 || HW % 4 != 0) {      // wide / odd shapes: generic fallback kernels
+    const int64_t total = N * C * HW;
+    cudaStream_t st = (cudaStream_t)stream;
+    mix_bwd_wide_dx_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(x, dz, w, idx, bias, logs, logscale_factor, dx, dlogs, dbias,
+                                                                         total, (int)C, HW);
+    if (w) mix_bwd_wide_dw_kernel<<<(unsigned)ceil_div(C * C, 256), 256, 0, st>>>(x, dz, bias, logs, logscale_factor, dw, N, (int)C, HW);
+    GLOWK_CHECK_LAUNCH("glowk_actnorm_mix_bwd(wide)");
+    return GLOWK_OK;
+  }
   if (smem > 48 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(mix_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t NP = N * HW;
   int groups = (int)C < 8 ? (int)C : 8;

@@ -76,7 +76,9 @@ def _oracle_step_grads(sd, x, ld_w, z_w, perm, coup, perms=None):
     ("invconv", "affine", 12, 16, 32, "fp32", 2e-3), ("invconv", "additive", 24, 8, 32, "fp32", 2e-3),
     ("shuffle", "affine", 8, 4, 16, "fp32", 2e-3), ("reverse", "additive", 48, 4, 32, "fp32", 2e-3),
     ("invconv", "affine", 12, 16, 64, "bf16", 3e-1), ("invconv", "affine", 48, 8, 128, "bf16", 3e-1),
-    ("invconv", "additive", 24, 16, 512, "bf16", 3e-1)])
+    ("invconv", "additive", 24, 16, 512, "bf16", 3e-1),
+    # channel counts of levels 5-6 of the 256x256 L=6 configuration (wide fall-back kernels), and H*W = 1
+    ("invconv", "affine", 192, 2, 32, "fp32", 2e-3), ("shuffle", "additive", 384, 1, 32, "fp32", 2e-3)])
 def test_flowstep_gradients_vs_oracle(perm, coup, c, hw, hidden, mode, tol):
     """fp32 path: every gradient within 2e-3 of max (measured ~5e-7).  bf16 tensor-core path: operands,
     saved activations and the inter-layer gradient signal are bf16, and ReLU masks near zero can flip
@@ -134,6 +136,36 @@ def test_split2d_and_flowmodel_gradients_vs_oracle():
         worst = max(worst, e)
         assert e < 2e-3, "%s: rel err %.3e" % (k, e)
     print("flowmodel grads: worst rel err %.2e" % worst)
+
+
+def test_six_level_flowmodel_trains_through_the_wide_channel_fallback():
+    """BASELINE config 5 shape family (L=6: 12 ... 384 channels) at a small image: the levels wider than the
+    pixel-major kernels' 96 channels run on the per-layer NCHW kernels; z, logdet and every gradient vs the oracle."""
+    from pytorch_glow_b200 import rows_path
+    np.random.seed(5)
+    torch.manual_seed(5)
+    fm = G.FlowModel((64, 64, 3), 16, K=1, L=6, permutation="invconv", coupling="affine")
+    sd = randomize_({k: v.clone() for k, v in fm.state_dict().items()}, 11)
+    adopt(fm, sd)
+    fm.set_conv_dtype("fp32")
+    fm = fm.to(DEV).train()
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(2, 3, 64, 64, generator=g)
+    assert not rows_path.supported(fm, cu(x))
+    z_w = torch.randn(2, 384, 1, 1, generator=g) * 0.1
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    z_ref, ld_ref = O.flow_encode(x, torch.zeros(2), p, (64, 64, 3), 1, 6, "invconv", "affine", prefix="")
+    ((z_ref * z_w).sum() + ld_ref.sum() * 0.01).backward()
+    z, ld = fm(cu(x), torch.zeros(2, device=DEV))
+    assert z.shape == (2, 384, 1, 1)
+    assert rel_err(z, z_ref) < 1e-4 and rel_err(ld, ld_ref) < 1e-4
+    ((z * cu(z_w)).sum() + ld.sum() * 0.01).backward()
+    worst = 0.0
+    for k, prm in fm.named_parameters():
+        e = grad_rel(prm.grad, p[k].grad)
+        worst = max(worst, e)
+        assert e < 2e-3, "%s: rel err %.3e" % (k, e)
+    print("L=6 flowmodel grads: worst rel err %.2e" % worst)
 
 
 def test_lu_flowstep_gradients():
