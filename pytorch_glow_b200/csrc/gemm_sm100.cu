@@ -26,6 +26,13 @@ constexpr int BLOCK_K = 64;          // one 128-byte swizzle span of bf16
 constexpr int UMMA_K = 16;
 constexpr int GEMM_THREADS = 320;         // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
+// The ReLU-backward epilogue is ~1200 dependent instructions per 32x64 chunk (mask, scale, two transposing
+// shuffle reductions): with 8 warps it bounds the dgrad GEMMs (the MMA warp idles 76 % of the time at K = 128).
+// That instance therefore runs 16 epilogue warps (4 per TMEM lane quarter) on 32-column chunks (<= 113 registers).
+constexpr int EPI_WARPS_RB = 16;
+constexpr int GEMM_THREADS_RB = 64 + 32 * EPI_WARPS_RB;
+template <int EPI> struct EpiCfg { static constexpr int WARPS = EPI_WARPS, THREADS = GEMM_THREADS; };
+template <> struct EpiCfg<GLOWK_EPI_RELU_BWD> { static constexpr int WARPS = EPI_WARPS_RB, THREADS = GEMM_THREADS_RB; };
 constexpr int ACC_STAGE_COLS = 256;  // TMEM columns per accumulator stage (2 stages = 512 columns)
 constexpr int MAX_STAGES = 8;
 constexpr int STAGING_BYTES = 8 * 4096;      // one (32 rows x 128 B) TMA-store box per epilogue warp
@@ -35,7 +42,7 @@ struct Shared {
   uint64_t empty_bar[MAX_STAGES];
   uint64_t tmem_full_bar[2];
   uint64_t tmem_empty_bar[2];
-  uint64_t y_bar[8];
+  uint64_t y_bar[16];
   uint32_t tmem_base;
 };
 
@@ -218,7 +225,8 @@ __device__ __forceinline__ void tcgen05_commit_mc(uint64_t* bar, uint16_t mask) 
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NTHREADS>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory"); }
 
 // ---- CTA pair (cta_group::2): two CTAs of a cluster run ONE 256 x N UMMA; each holds its 128 rows of A and its
 // half of B, the leader (rank 0) issues the MMAs, both epilogues drain their own 128 TMEM lanes.
@@ -260,7 +268,7 @@ constexpr int EPI_NMAX = 1024;   // column sums of RELU_BWD are kept in shared m
 // drops from A+B to A/CN + B/CM).
 // ---------------------------------------------------------------------------------------------
 template <int EPI, typename OutT, bool PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<EPI>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ CUtensorMap tm_o, const __grid_constant__ CUtensorMap tm_y, int M, int N,
                int K, int block_n, int num_stages, int CM, int CN, int dbg, EpiParams ep) {
@@ -305,8 +313,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // pair mode: one multicast tcgen05.commit frees a slot in both CTAs; the leader's accumulator is free once the
     // epilogue warps of BOTH CTAs have drained it
     for (int s = 0; s < num_stages; ++s) { mbar_init(&sh->full_bar[s], 1); mbar_init(&sh->empty_bar[s], pair ? 1u : (uint32_t)(CM + CN - 1)); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], pair ? 2 * EPI_WARPS : EPI_WARPS); }
-    for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
+    constexpr int EW = EpiCfg<EPI>::WARPS;
+    for (int s = 0; s < 2; ++s) { mbar_init(&sh->tmem_full_bar[s], 1); mbar_init(&sh->tmem_empty_bar[s], pair ? 2 * EW : EW); }
+    for (int q = 0; q < EW; ++q) mbar_init(&sh->y_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM: 512 columns (two accumulator stages), allocated and freed by this warp
@@ -319,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   }
   if (EPI == GLOWK_EPI_RELU_BWD)
-    for (int i = threadIdx.x; i < 2 * EPI_NMAX; i += GEMM_THREADS) s_gy[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * EPI_NMAX; i += EpiCfg<EPI>::THREADS) s_gy[i] = 0.f;
   tcgen05_fence_before();
   __syncthreads();
   if (csize > 1) cluster_sync_all();        // peers' barriers must be initialised before any remote arrive / multicast
@@ -417,6 +426,138 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
       if (tr) { g_gemm_trace[2] = w_full; g_gemm_trace[3] = w_acc; g_gemm_trace[4] = (unsigned long long)(clock64() - t_begin); g_gemm_trace[9] = ntile; }
     }
+  } else if constexpr (EPI == GLOWK_EPI_RELU_BWD) {
+    // ===================== ReLU-backward epilogue: 16 warps, 32-column chunks =====================
+    // warp -> (TMEM lane quarter = warp % 4, column group = (warp-2)/4 in 0..3); chunk c0 = grp*32 + k*128.
+    // y / output boxes are [32 rows][32 bf16] = 2 KB, SWIZZLE_64B: 16-byte piece j of row r lives at
+    // r*64 + ((j ^ ((r >> 1) & 3)) * 16).  Rows >= M need no masking: the y box is zero-filled there (TMA OOB).
+    constexpr int EW = EPI_WARPS_RB, BOX = 32, BOXB = 2048;
+    const int quarter = warp & 3;
+    const int ew = warp - 2, grp = ew >> 2;
+    const int et = (int)threadIdx.x - 64;
+    uint8_t* sbuf = staging + (size_t)ew * BOXB;
+    uint8_t* my_y = ybuf + (size_t)ew * BOXB;
+    const uint8_t* yrow = my_y + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const bool want_gy = ep.dlogs != nullptr;
+    int acc = 0; uint32_t acc_phase = 0;
+    int cached_nblk = -1;
+    const bool tr = (dbg & 64) && blockIdx.x == 0 && ew == 0;
+    unsigned long long w_tfull = 0, w_y = 0, w_st = 0;
+    const long long t_begin = clock64();
+    uint32_t yit = 0;                       // y boxes consumed so far by this warp (mbarrier parity)
+    auto issue_y = [&](int st, int c0) {
+      if (lane == 0) {
+        const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
+        mbar_arrive_expect_tx(&sh->y_bar[ew], BOXB);
+        tma_load_2d(&tm_y, &sh->y_bar[ew], my_y, n_blk * block_n + c0, m_blk * BLOCK_M + quarter * 32);
+      }
+    };
+    auto next_valid = [&](int st) {
+      while (st < num_super && ((st % sup_n) * CN + cn) * block_n + grp * BOX >= N) st += num_clusters;
+      return st;
+    };
+    {
+      const int st0 = next_valid(cluster_id);
+      if (st0 < num_super) issue_y(st0, grp * BOX);
+    }
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int m_blk = (st / sup_n) * CM + cm, n_blk = (st % sup_n) * CN + cn;
+      const int row0 = m_blk * BLOCK_M + quarter * 32;
+      if (n_blk != cached_nblk) {
+        epi_bar_sync<32 * EW>();
+        if (et < block_n) {
+          const int n = n_blk * block_n + et;
+          s_scale[et] = n < N ? expf(ep.logs[n] * ep.f) : 1.f;
+        }
+        epi_bar_sync<32 * EW>();
+        cached_nblk = n_blk;
+      }
+      mbar_wait_timed(&sh->tmem_full_bar[acc], acc_phase, tr, w_tfull);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * ACC_STAGE_COLS;
+      for (int c0 = grp * BOX; c0 < block_n; c0 += 4 * BOX) {
+        const int ncol0 = n_blk * block_n + c0;
+        if (ncol0 >= N) break;
+        uint32_t raw[32];
+        tmem_ld32_async(t_row + (uint32_t)c0, raw);
+        mbar_wait_timed(&sh->y_bar[ew], yit & 1, tr, w_y);
+        {
+          const long long t0 = tr ? clock64() : 0;
+          if (lane == 0) tma_store_wait_read<0>();      // the store that last read the staging box is done with it
+          __syncwarp();
+          if (tr) w_st += (unsigned long long)(clock64() - t0);
+        }
+        tmem_ld_wait();
+        float v[32], ga[32];
+        const float* scl = s_scale + c0;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const uint4 yraw = *reinterpret_cast<const uint4*>(yrow + ((j4 ^ sw) * 16));
+          const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&yraw);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 yv = __bfloat1622float2(yp[u]);
+            const int j = j4 * 8 + u * 2;
+            const float g0 = yv.x > 0.f ? __uint_as_float(raw[j]) : 0.f;
+            const float g1 = yv.y > 0.f ? __uint_as_float(raw[j + 1]) : 0.f;
+            ga[j] = g0 * yv.x; ga[j + 1] = g1 * yv.y;
+            v[j] = g0 * scl[j]; v[j + 1] = g1 * scl[j + 1];
+          }
+        }
+        // stage the output row (bf16) first: the reductions below consume v and ga in place
+        uint8_t* srow = sbuf + lane * 64;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __nv_bfloat162 h[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) h[u] = __floats2bfloat162_rn(v[8 * j + 2 * u], v[8 * j + 2 * u + 1]);
+          *reinterpret_cast<uint4*>(srow + ((j ^ sw) * 16)) = *reinterpret_cast<uint4*>(h);
+        }
+        // y consumed: fetch this warp's next box (same tile or the next one) behind the reductions and the store
+        ++yit;
+        __syncwarp();
+        {
+          int nst = st, nc0 = c0 + 4 * BOX;
+          if (nc0 >= block_n || n_blk * block_n + nc0 >= N) { nst = next_valid(st + num_clusters); nc0 = grp * BOX; }
+          if (nst < num_super) issue_y(nst, nc0);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tm_o, sbuf, ncol0, row0);   // rows >= M and columns >= N are clipped by TMA
+          tma_store_commit();
+        }
+        // column sums over this warp's 32 rows: dbias += sum of the scaled gradient, dlogs += f * sum g*y
+        const float sb = warp_colsum32(v, lane);
+        float sa = 0.f;
+        if (want_gy) sa = warp_colsum32(ga, lane);
+        if (ncol0 + lane < N) {
+          if (small_n) { atomicAdd(&s_g[ncol0 + lane], sb); if (want_gy) atomicAdd(&s_gy[ncol0 + lane], sa); }
+          else { atomicAdd(ep.dbias + ncol0 + lane, sb); if (want_gy) atomicAdd(ep.dlogs + ncol0 + lane, ep.f * sa); }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_cluster(&sh->tmem_empty_bar[acc], 0));
+        else mbar_arrive(&sh->tmem_empty_bar[acc]);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (small_n) {
+      epi_bar_sync<32 * EW>();
+      for (int n = et; n < N; n += 32 * EW) {
+        const float a = s_gy[n], b = s_g[n];
+        if (b != 0.f) atomicAdd(ep.dbias + n, b);
+        if (want_gy && a != 0.f) atomicAdd(ep.dlogs + n, ep.f * a);
+      }
+    }
+    if (tr && lane == 0) {
+      g_gemm_trace[5] = w_tfull; g_gemm_trace[6] = w_y; g_gemm_trace[7] = w_st;
+      g_gemm_trace[8] = (unsigned long long)(clock64() - t_begin);
+    }
+    if (lane == 0) tma_store_wait_all();
   } else {
     // ===================== epilogue warps =====================
     // TMEM lane quarter = warp % 4 (hardware rule); the two warps of a quarter take alternate column chunks.
@@ -456,14 +597,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int64_t m = row0 + lane;
       if (EPI != GLOWK_EPI_STORE && n_blk != cached_nblk) {
         // per-column scale = exp(f*logs), shift = bias*scale for this n-tile (ActNorm / Conv2dZeros epilogue)
-        epi_bar_sync();
+        epi_bar_sync<32 * EPI_WARPS>();
         if (et < block_n) {
           const int n = n_blk * block_n + et;
           float sc = 1.f, sf = 0.f;
           if (n < N) { sc = expf(ep.logs[n] * ep.f); sf = ep.bias ? ep.bias[n] * sc : 0.f; }
           s_scale[et] = sc; s_shift[et] = sf;
         }
-        epi_bar_sync();
+        epi_bar_sync<32 * EPI_WARPS>();
         cached_nblk = n_blk;
       }
       mbar_wait_timed(&sh->tmem_full_bar[acc], acc_phase, tr, w_tfull);
@@ -572,7 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     if (EPI == GLOWK_EPI_RELU_BWD && small_n) {
       // one global atomic per column per CTA: dlogs += f * sum g*y ; dbias += exp(f*logs) * sum g
-      epi_bar_sync();
+      epi_bar_sync<32 * EPI_WARPS>();
       for (int n = et; n < N; n += 32 * EPI_WARPS) {
         const float a = s_gy[n], b = s_g[n];
         if (a != 0.f || b != 0.f) epilogue_commit_colsums(ep, n, a, b);
@@ -762,7 +903,8 @@ static EncodeTiledFn encode_fn() {
 
 // 2-D row-major tensor [rows][cols] with leading dimension ld (elements); box = [box_rows][box_cols].
 static int make_map_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int elsize, uint64_t cols,
-                       uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows) {
+                       uint64_t rows, uint64_t ld, uint32_t box_cols, uint32_t box_rows,
+                       CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(GLOWK_EUNSUP, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[2] = {cols, rows};
@@ -770,7 +912,7 @@ static int make_map_2d(CUtensorMap* tm, const void* base, CUtensorMapDataType dt
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(GLOWK_ECUDA, "cuTensorMapEncodeTiled failed (%d): base=%p cols=%llu rows=%llu ld=%llu box=%ux%u", (int)r,
                 base, (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)ld, box_cols, box_rows);
@@ -804,7 +946,7 @@ static int launch_gemm_tc(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(clusters * csize), 1, 1);
-  cfg.blockDim = dim3(GEMM_THREADS, 1, 1);
+  cfg.blockDim = dim3(EpiCfg<EPI>::THREADS, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[2];
@@ -892,11 +1034,15 @@ int gemm_bf16_tc(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t
   int rc;
   if ((rc = make_map_2d(&ta, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, (uint32_t)(BLOCK_M / cn)))) return rc;
   if ((rc = make_map_2d(&tb, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, (uint32_t)(block_n / cm)))) return rc;
-  if ((rc = make_map_2d(&to, out, out_dtype == GLOWK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                        elo, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, (uint32_t)box_cols, 32))) return rc;
-  ty = to;
-  if (epilogue == GLOWK_EPI_RELU_BWD &&
-      (rc = make_map_2d(&ty, ep.y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldy, 64, 32))) return rc;
+  if (epilogue == GLOWK_EPI_RELU_BWD) {
+    // 16 epilogue warps on [32 rows][32 bf16] boxes (64-byte rows, SWIZZLE_64B) for both the output and y
+    if ((rc = make_map_2d(&to, out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_map_2d(&ty, ep.y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldy, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  } else {
+    if ((rc = make_map_2d(&to, out, out_dtype == GLOWK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                          elo, (uint64_t)N, (uint64_t)M, (uint64_t)ldo, (uint32_t)box_cols, 32))) return rc;
+    ty = to;
+  }
 
 #define GLOWK_TC_CASE(E)                                                                                                  \
   case E:                                                                                                                 \
