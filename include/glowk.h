@@ -295,6 +295,18 @@ int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* 
 int glowk_pack_conv_weights_batched(const void* jobs, int64_t njobs, int64_t total_blocks, int act_dtype, void* stream);
 int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs, int64_t total_blocks, void* stream);
 
+/* Gradient finish of the ActNorm that follows a coupling-net conv (Conv2d, module.py:188-260; ActNorm.forward
+ * module.py:122-149), batched over layers.  glowk_gemm(GLOWK_EPI_RELU_BWD) on the bf16 path may be called with
+ * dlogs == NULL and dbias pointing at per-pass scratch `db`; this call then applies, per output channel n,
+ *     dbias[n] += db[n];   dlogs[n] += f * ( <w[n,:], dw[n,:]> + bias[n]*db[n] )
+ * which equals f * sum_m g*y of the direct epilogue reduction (y = (W a + b) s on the ReLU-active set).
+ * jobs: device array of
+ *   struct { const bf16* w; const float* dw; const float* bias; const float* db; float* dbias; float* dlogs;
+ *            int32 N, K, ldw, lddw; float f; int32 pad; }                                            (64 bytes)
+ * w = the GEMM-layout bf16 weight of the forward pass, dw = THIS pass's weight gradient in the same [N][K] order
+ * (K, ldw, lddw even); max_n = max over jobs of N. */
+int glowk_conv_actnorm_finish_batched(const void* jobs, int64_t njobs, int64_t max_n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ SIGNATURES = {
     "glowk_rows_squeeze": [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_pack_conv_weights_batched": [_p, _i64, _i64, _i32, _p],
     "glowk_unpack_weight_grads_batched": [_p, _i64, _i64, _p],
+    "glowk_conv_actnorm_finish_batched": [_p, _i64, _i64, _p],
 }
 _RESTYPES = {"glowk_last_error": _c.c_char_p, "glowk_coupling_nblk": _i64, "glowk_optim_workspace_floats": _i64,
              "glowk_rows_coupling_nblk": _i64}

@@ -38,6 +38,26 @@ int sm_count() {
   return cached;
 }
 
+// CTAs of `kern` that fit on the device at once (occupancy x SM count): the grid of the looping flow kernels.
+// Cached per thread (no shared mutable state); keyed by kernel, block size and dynamic shared memory.
+int resident_ctas(const void* kern, int threads, size_t smem) {
+  struct Entry { const void* k; int threads; size_t smem; int dev; int ctas; };
+  static thread_local Entry cache[32];
+  static thread_local int used = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < used; ++i)
+    if (cache[i].k == kern && cache[i].threads == threads && cache[i].smem == smem && cache[i].dev == dev) return cache[i].ctas;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    occ = 1;
+  }
+  const int ctas = occ * sm_count();
+  if (used < 32) cache[used++] = Entry{kern, threads, smem, dev, ctas};
+  return ctas;
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -67,7 +87,9 @@ extern "C" int glowk_gemm_ex(const void* A, int64_t lda, const void* B, int64_t 
   if (epilogue != GLOWK_EPI_STORE) GLOWK_CHECK_ARG(logs, "glowk_gemm: epilogue %d needs logs", epilogue);
   if (epilogue == GLOWK_EPI_ACTNORM_RELU || epilogue == GLOWK_EPI_ACTNORM || epilogue == GLOWK_EPI_ZEROS)
     GLOWK_CHECK_ARG(bias, "glowk_gemm: epilogue %d needs bias", epilogue);
-  if (epilogue == GLOWK_EPI_RELU_BWD) GLOWK_CHECK_ARG(y && dlogs && dbias && ldy >= N, "glowk_gemm: RELU_BWD needs y, dlogs, dbias");
+  // dlogs may be NULL on the bf16 path: the caller recovers it with glowk_conv_actnorm_finish_batched
+  if (epilogue == GLOWK_EPI_RELU_BWD)
+    GLOWK_CHECK_ARG(y && dbias && ldy >= N && (dlogs || act_dtype == GLOWK_BF16), "glowk_gemm: RELU_BWD needs y, dbias (and dlogs on the fp32 path)");
   if (M == 0) return GLOWK_OK;
   EpiParams ep;
   ep.bias = bias; ep.logs = logs; ep.f = logscale_factor; ep.y = y; ep.ldy = ldy;

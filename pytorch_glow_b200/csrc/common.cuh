@@ -37,6 +37,8 @@ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // Number of SMs of the current device (cached per device id, read-only after first query).
 int sm_count();
+// CTAs of a kernel resident on the whole device (occupancy x SMs), cached; see api.cu.
+int resident_ctas(const void* kern, int threads, size_t smem);
 
 // Programmatic dependent launch (PDL).  The per-step kernels are short (a K=32, L=3 Glow launches ~1500 of them
 // per training step, many of a few microseconds), so each one is launched with

@@ -736,6 +736,51 @@ __global__ void unpack_grads_batched_kernel(const PackJob* __restrict__ jobs, in
   g[e] += reinterpret_cast<const float*>(jb.packed)[s];
 }
 
+// ------------------------------------------------------------------------------------------
+// ActNorm-after-conv gradient finish (Conv2d = conv -> ActNorm -> ReLU, module.py:188-260), batched over layers.
+// With y = (W a + b) * s on the active set and v = g * s the gradient the dgrad epilogue stores (dW = v^T a,
+// db = sum v), the logs gradient sum_m g*y is EXACTLY  <W[n,:], dW[n,:]> + b[n]*db[n]  per output channel n.
+// The tcgen05 ReLU-backward epilogue is issue-bound; dropping its second transposing column sum (g*y) and
+// recovering dlogs here costs one pass over W and this step's dW.  W is the bf16 copy the forward GEMM multiplied
+// by, dW / db this backward pass's own contributions (scratch, zeroed per pass), so gradient accumulation over
+// several passes stays correct:  dbias[n] += db[n];  dlogs[n] += f * (<W[n,:], dW[n,:]> + b[n]*db[n]).
+// ------------------------------------------------------------------------------------------
+struct FinishJob {           // 64 bytes, mirrored by pytorch_glow_b200/rows_path.py
+  const __nv_bfloat16* w;    // [N][ldw] bf16, k-order of dw
+  const float* dw;           // [N][lddw] fp32, this pass only
+  const float* bias;         // [N] ActNorm bias
+  const float* db;           // [N] this pass's sum of v
+  float* dbias;              // [N] accumulated into
+  float* dlogs;              // [N] accumulated into
+  int32_t N, K, ldw, lddw;
+  float f;
+  int32_t pad_;
+};
+
+__global__ void __launch_bounds__(256)
+conv_actnorm_finish_kernel(const FinishJob* __restrict__ jobs) {
+  pdl_wait();
+  const FinishJob jb = jobs[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y * 8 + warp;
+  if (n >= jb.N) return;
+  const __nv_bfloat16* wr = jb.w + (int64_t)n * jb.ldw;
+  const float* dr = jb.dw + (int64_t)n * jb.lddw;
+  float acc = 0.f;
+  for (int k = lane * 2; k < jb.K; k += 64) {              // K, ldw, lddw are even (GEMM pitches)
+    const float2 wv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(wr + k));
+    const float2 dv = *reinterpret_cast<const float2*>(dr + k);
+    acc = fmaf(wv.x, dv.x, acc);
+    acc = fmaf(wv.y, dv.y, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float db = jb.db[n];
+    jb.dbias[n] += db;
+    jb.dlogs[n] += jb.f * (acc + jb.bias[n] * db);
+  }
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -743,10 +788,21 @@ using namespace glowk;
 // ============================================================================================
 // C ABI
 // ============================================================================================
-static inline int bwd_iters(int64_t NP, int ppb) {
-  int64_t it = NP / ((int64_t)ppb * 2 * sm_count());
+extern "C" int glowk_conv_actnorm_finish_batched(const void* jobs, int64_t njobs, int64_t max_n, void* stream) {
+  if (njobs == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(jobs && njobs > 0 && njobs < 65536 && max_n > 0 && max_n < (1 << 20), "glowk_conv_actnorm_finish_batched: bad arguments");
+  const dim3 grid((unsigned)njobs, (unsigned)ceil_div(max_n, 8));
+  GLOWK_CUDA(launch_pdl(conv_actnorm_finish_kernel, grid, 256, 0, (cudaStream_t)stream, (const FinishJob*)jobs));
+  GLOWK_CHECK_LAUNCH("glowk_conv_actnorm_finish_batched");
+  return GLOWK_OK;
+}
+
+// pixel groups per CTA of the adjoint kernels: one resident wave whose CTAs loop, rounded UP so that no partial
+// second wave is left
+static inline int bwd_iters(int64_t NP, int ppb, int resident) {
+  int64_t it = ceil_div(ceil_div(NP, ppb), resident);
   if (it < 1) it = 1;
-  if (it > 8) it = 8;
+  if (it > 32) it = 32;
   return (int)it;
 }
 
@@ -764,14 +820,19 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   GLOWK_CHECK_ARG(P * C < (1ll << 31), "glowk_rows_actnorm_mix: tensor too large for 32-bit indexing");
   const int G = (int)C / 4, ppb = 256 / G;
   const dim3 block((unsigned)G, (unsigned)ppb);
-  int iters = (int)(ceil_div(P, ppb) / (8 * (int64_t)sm_count()));       // >= 8 CTAs per SM before CTAs start looping
-  if (iters < 1) iters = 1;
-  if (iters > 8) iters = 8;
-  const unsigned grid = (unsigned)ceil_div(P, (int64_t)ppb * iters);
   cudaStream_t st = (cudaStream_t)stream;
+  // one resident wave whose CTAs loop: rounding the loop count DOWN (and assuming 8 CTAs per SM for every
+  // instance) left a second, nearly empty wave that doubled the kernel time (1234 CTAs on 1184 slots at C = 12)
 #define GLOWK_MIX_LAUNCH(PERM_, CT_, SMEM_)                                                                          \
-  GLOWK_CUDA(launch_pdl(rows_mix_kernel<PERM_, CT_>, grid, block, SMEM_, st, x, z, w, idx, bias, logs, logscale_factor, \
-                        (int)P, (int)C, reverse, iters))
+  do {                                                                                                               \
+    auto kern = rows_mix_kernel<PERM_, CT_>;                                                                         \
+    const int64_t passes = ceil_div(P, ppb);                                                                         \
+    int iters = (int)ceil_div(passes, resident_ctas((const void*)kern, G * ppb, SMEM_));                             \
+    iters = iters < 1 ? 1 : (iters > 32 ? 32 : iters);                                                               \
+    const unsigned grid = (unsigned)ceil_div(passes, iters);                                                         \
+    GLOWK_CUDA(launch_pdl(kern, grid, block, SMEM_, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C,   \
+                          reverse, iters));                                                                          \
+  } while (0)
   if (w) {
     const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
     if (C == 12) GLOWK_MIX_LAUNCH(false, 12, smem);
@@ -810,9 +871,23 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
   GLOWK_CHECK_ARG(N <= 65535 && H * W * C < (1ll << 30), "glowk_rows_coupling: shape out of range");
   GLOWK_CHECK_ARG(N * H * W * ldp < (1ll << 31), "glowk_rows_coupling: P3 too large for 32-bit tap offsets");
   const int Ch = (int)C / 2, ppb = 256 / Ch;
-  const dim3 grid((unsigned)glowk_rows_coupling_nblk(H * W, C), (unsigned)N);
+  // CTAs per sample: glowk_rows_coupling_nblk() is the upper bound the caller sized `partials` for.  The kernel is
+  // latency-bound (every pixel group is one round of dependent loads), so its time is ~ waves x (groups per CTA +
+  // a constant for the per-CTA set-up and reduction tail): pick the split that minimises that, which avoids
+  // the nearly empty last wave of a fixed split (3584 CTAs on 888 resident slots at B = 512, level 1).
+  const int64_t groups = ceil_div(H * W, ppb);
+  const int64_t nblk_max = glowk_rows_coupling_nblk(H * W, C);
+  const int64_t resident = resident_ctas((const void*)rows_coupling_kernel, 256, 0);
+  int64_t nblk = 1, best_cost = -1;
+  for (int64_t b = 1; b <= nblk_max; ++b) {
+    const int64_t it = ceil_div(groups, b), eff = ceil_div(groups, it);
+    const int64_t cost = ceil_div(N * eff, resident) * (it + 2);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; nblk = eff; }
+  }
+  const int iters = (int)ceil_div(groups, nblk);
+  const dim3 grid((unsigned)nblk, (unsigned)N);
   GLOWK_CUDA(launch_pdl(rows_coupling_kernel, grid, 256, 0, (cudaStream_t)stream, P3, (int)ldp, bias3, logs3, logscale_factor, z, h_save,
-                        (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch), ppb, coupling_iters(H * W, C), affine, reverse, ld_in, ld_out,
+                        (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch), ppb, iters, affine, reverse, ld_in, ld_out,
                         an_logs, an_logscale_factor, logabsdet, sign, partials, (unsigned int*)tickets));
   GLOWK_CHECK_LAUNCH("glowk_rows_coupling");
   return GLOWK_OK;
@@ -828,7 +903,7 @@ extern "C" int glowk_rows_coupling_bwd(const float* y, const float* hrows, const
   const int64_t NP = N * HW;
   GLOWK_CHECK_ARG(NP * C < (1ll << 31), "glowk_rows_coupling_bwd: tensor too large for 32-bit indexing");
   const int Ch = (int)(C / 2), ppb = 256 / Ch;
-  const int iters = bwd_iters(NP, ppb);
+  const int iters = bwd_iters(NP, ppb, resident_ctas((const void*)rows_coupling_bwd_kernel, Ch * ppb, 0));
   const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
   GLOWK_CUDA(launch_pdl(rows_coupling_bwd_kernel, grid, dim3((unsigned)Ch, (unsigned)ppb), 0, (cudaStream_t)stream, y, hrows, dy, dld,
                         logs3, logscale_factor, dz, du, dlogs3, dbias3, (int)NP, (int)C, make_fastdiv(HW), affine, iters));
@@ -915,7 +990,7 @@ extern "C" int glowk_rows_split2d_bwd(const float* x, const float* hrows, int64_
   GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C && ldh >= C && ldu >= C && ldu % 2 == 0 && ldh % 2 == 0, "glowk_rows_split2d_bwd: bad shape");
   const int64_t NP = N * HW;
   const int ppb = 256 / (int)(C / 2);
-  const int iters = bwd_iters(NP, ppb);
+  const int iters = bwd_iters(NP, ppb, resident_ctas((const void*)rows_split2d_bwd_kernel, 256, 0));
   const unsigned grid = (unsigned)ceil_div(NP, (int64_t)ppb * iters);
   rows_split2d_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, hrows, ldh, dld, logs_p, logscale_factor, dx, du, ldu,
                                                                    dlogs_p, dbias_p, NP, (int)C, (int)HW, iters);

@@ -433,3 +433,8 @@ def pack_conv_weights_batched(jobs_dev, njobs, total_blocks, dtype):
 
 def unpack_weight_grads_batched(jobs_dev, njobs, total_blocks):
     call("glowk_unpack_weight_grads_batched", ptr(jobs_dev), njobs, total_blocks)
+
+
+def conv_actnorm_finish_batched(jobs_dev, njobs, max_n):
+    """dbias += db; dlogs += f*(<W, dW> + bias*db) per output channel of every job (see include/glowk.h)."""
+    call("glowk_conv_actnorm_finish_batched", ptr(jobs_dev), njobs, max_n)

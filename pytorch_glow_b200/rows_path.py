@@ -20,6 +20,10 @@ from .functional import NCHW, ROWS, round_up
 _JOB = np.dtype([("w", "<u8"), ("packed", "<u8"), ("O", "<i4"), ("I", "<i4"), ("ks", "<i4"), ("layout", "<i4"),
                  ("rows", "<i4"), ("ld", "<i4"), ("block0", "<i8")])
 assert _JOB.itemsize == 48
+# struct FinishJob of flow_rows_kernels.cu (glowk_conv_actnorm_finish_batched)
+_FJOB = np.dtype([("w", "<u8"), ("dw", "<u8"), ("bias", "<u8"), ("db", "<u8"), ("dbias", "<u8"), ("dlogs", "<u8"),
+                  ("N", "<i4"), ("K", "<i4"), ("ldw", "<i4"), ("lddw", "<i4"), ("f", "<f4"), ("pad", "<i4")])
+assert _FJOB.itemsize == 72
 
 
 def _gbuf(p):
@@ -137,8 +141,11 @@ def prepare_packs(flow, backward, device):
 
 
 class GradPlan:
-    """fp32 scratch for the packed-layout weight gradients of conv1 / conv3 / the Split2d prior conv of every
-    layer (zeroed once per backward) and ONE kernel scattering them into the [O][I][k][k] .grad tensors."""
+    """fp32 scratch for the packed-layout weight gradients of the coupling-net convs / the Split2d prior conv of
+    every layer (zeroed once per backward) and ONE kernel scattering them into the [O][I][k][k] .grad tensors.
+    The scratch also holds this pass's ActNorm bias gradients of conv1 / conv2 (`db`): on the bf16 path the dgrad
+    epilogue no longer reduces sum g*y, and `finish` recovers dlogs from W, this pass's dW and db in one batched
+    kernel (glowk_conv_actnorm_finish_batched)."""
 
     def __init__(self, flow, device):
         steps, splits = _steps_and_splits(flow)
@@ -149,15 +156,24 @@ class GradPlan:
             k3p = round_up(9 * net.out_channels, 64)
             items.append((st, "w3", net[4].weight, 1, k3p, kh))
             items.append((st, "w1", net[0].weight, 0, kh, net.k1p))
+            items.append((st, "w2", net[2].weight, 0, kh, kh))
         for sp in splits:
             c = sp.num_channels
             items.append((sp, "w0", sp.conv2d_zeros.weight, 0, round_up(c, 64), round_up(9 * (c // 2), 64)))
         self.items = items
         self.sig = tuple(_gbuf(it[2]).data_ptr() for it in items)
         numel = sum(it[4] * it[5] for it in items)
-        self.arena = torch.zeros(numel, device=device, dtype=torch.float32)
+        ndb = sum(2 * round_up(st.f.hidden_channels, 64) for st in steps)
+        self.arena = torch.zeros(numel + ndb, device=device, dtype=torch.float32)
         jobs = np.zeros(len(items), dtype=_JOB)
         self.views = {}
+        off = numel
+        for st in steps:
+            kh = round_up(st.f.hidden_channels, 64)
+            self.views[(id(st), "db1")] = self.arena[off:off + kh]
+            self.views[(id(st), "db2")] = self.arena[off + kh:off + 2 * kh]
+            off += 2 * kh
+        self._fin, self._fin_sig, self._fin_dev = [], None, None
         off = blk = 0
         for i, (owner, tag, prm, layout, rows, ld) in enumerate(items):
             self.views[(id(owner), tag)] = self.arena[off:off + rows * ld].view(rows, ld)
@@ -173,11 +189,25 @@ class GradPlan:
 
     def begin(self):
         self.arena.zero_()
+        self._fin = []
 
     def view(self, owner, tag):
         return self.views[(id(owner), tag)]
 
+    def defer_dlogs(self, w_packed, dw, actnorm, db, n, k):
+        """Register one conv + ActNorm layer for the batched dbias / dlogs finish (bf16 path)."""
+        self._fin.append((w_packed.data_ptr(), dw.data_ptr(), actnorm.bias.data_ptr(), db.data_ptr(),
+                          _gbuf(actnorm.bias).data_ptr(), _gbuf(actnorm.logs).data_ptr(), n, k, w_packed.shape[1],
+                          dw.shape[1], float(actnorm.logscale_factor), 0))
+
     def finish(self):
+        if self._fin:
+            sig = tuple(self._fin)
+            if sig != self._fin_sig:          # pointers are stable across steps: built once, before graph capture
+                jobs = np.array(self._fin, dtype=_FJOB)
+                self._fin_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(self.arena.device)
+                self._fin_sig = sig
+            K.conv_actnorm_finish_batched(self._fin_dev, len(self._fin), max(j[6] for j in self._fin))
         K.unpack_weight_grads_batched(self.jobs_dev, self.njobs, self.blocks)
 
 
@@ -257,15 +287,24 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     k3p = round_up(9 * cout, 64)
     d3col = K.im2col_rows(du, n, h, w, 0, cout, 3, dt, k3p, flip=True)
     K.gemm_wgrad(d3col, h2, k3p, hid, plan.view(step, "w3"))
+    # bf16 (tcgen05) path: the ReLU-backward epilogue only reduces this pass's bias gradient into scratch; dlogs of
+    # the two hidden ActNorms come from W, dW and db in GradPlan.finish (see glowk_conv_actnorm_finish_batched)
+    defer = dt == _C.BF16
+    dl2, db2 = (None, plan.view(step, "db2")) if defer else (_gbuf(an2.logs), _gbuf(an2.bias))
+    dl1, db1 = (None, plan.view(step, "db1")) if defer else (_gbuf(an1.logs), _gbuf(an1.bias))
     d2 = K.gemm(d3col, net.packed("w3t", dt), hid, k3p, _C.EPI_RELU_BWD, None, an2.logs.detach().reshape(-1),
-                an2.logscale_factor, y=h2, dlogs=_gbuf(an2.logs), dbias=_gbuf(an2.bias), out_dtype=dt, ldo=kh)
+                an2.logscale_factor, y=h2, dlogs=dl2, dbias=db2, out_dtype=dt, ldo=kh)
     # (3) conv2 (1x1)
-    K.gemm_wgrad(d2, h1, hid, hid, _gbuf(c2.weight).view(hid, hid))
+    dw2 = plan.view(step, "w2")
+    K.gemm_wgrad(d2, h1, hid, hid, dw2)
     d1 = K.gemm(d2, net.packed("w2t", dt), hid, hid, _C.EPI_RELU_BWD, None, an1.logs.detach().reshape(-1),
-                an1.logscale_factor, y=h1, dlogs=_gbuf(an1.logs), dbias=_gbuf(an1.bias), out_dtype=dt, ldo=kh)
+                an1.logscale_factor, y=h1, dlogs=dl1, dbias=db1, out_dtype=dt, ldo=kh)
     # (4) conv1 (im2col form); its dgrad is gather-summed inside the mix adjoint below
     k1p = net.k1p
     K.gemm_wgrad(d1, a1, hid, k1p, plan.view(step, "w1"))
+    if defer:
+        plan.defer_dlogs(net.packed("w2", dt), dw2, an2, db2, hid, hid)
+        plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p)
     da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32)
     # (5) ActNorm + mix
     dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition

@@ -266,7 +266,8 @@ def test_rows_split2d_pieces(shape):
                                                   ((3, 24, 4, 4), 0, 24, 1, False), ((1, 6, 5, 7), 2, 3, 3, True),
                                                   ((2, 24, 4, 4), 0, 12, 3, False), ((2, 48, 4, 4), 0, 48, 3, True),
                                                   ((3, 4, 3, 5), 0, 2, 3, False), ((2, 8, 6, 6), 4, 4, 3, True),
-                                                  ((2, 8, 6, 6), 2, 4, 3, False), ((40, 12, 32, 32), 0, 6, 3, False)])
+                                                  ((2, 8, 6, 6), 2, 4, 3, False), ((40, 12, 32, 32), 0, 6, 3, False),
+                                                  ((1, 96, 4, 4), 0, 96, 3, True), ((300, 24, 16, 16), 0, 12, 3, False)])
 @pytest.mark.parametrize("dt", [_C.F32, _C.BF16])
 def test_im2col_rows_equals_nchw(shape, c0, cin, ks, flip, dt):
     n, c, h, w = shape
