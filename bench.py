@@ -237,7 +237,9 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
     gemm_flops = 2.0 * M * hidden * hidden
     cases = [
         ("dgrad2", "gemm_tc_kernel<RELU_BWD,bf16>: dgrad of conv2 + ReLU/ActNorm backward epilogue (M=%d N=K=%d)" % (M, hidden),
-         lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_RELU_BWD, None, logs, 3.0, y=hs[(i + 1) % R], dlogs=dlogs,
+         # as launched by the training step: dbias reduced in the epilogue, dlogs deferred to the batched
+         # glowk_conv_actnorm_finish_batched pass (rows_path.GradPlan.finish)
+         lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_RELU_BWD, None, logs, 3.0, y=hs[(i + 1) % R], dlogs=None,
                            dbias=dbias, out_dtype=_C.BF16, out=outs[i]),
          "hbm", 3.0 * M * hidden * 2, gemm_flops),
         ("wgrad2", "wgrad_tc_kernel: dW2 += d2^T h1 (P=%d, 512x512)" % M,

@@ -21,7 +21,7 @@ constexpr int ROWS_MAX_C = 96;   // shared-memory tiles below are sized for C <=
 // CT = compile-time channel count (12 / 24 / 48: the CelebA / CIFAR levels; loops fully unrolled, no predicates),
 // 0 = run-time C.
 template <bool PERM, int CT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float* __restrict__ w,
                 const int64_t* __restrict__ idx, const float* __restrict__ bias, const float* __restrict__ logs,
                 float f, int P, int C_rt, int reverse, int iters) {
@@ -48,55 +48,75 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 #pragma unroll
       for (int u = 0; u < 4; ++u) wt[(og * 4 + u) * C + o] = w[o * C + og * 4 + u];
   __syncthreads();
+  // two pixels per thread and pass (pixA, pixB = pixA + blockDim.y): every W^T float4 read from shared memory
+  // feeds 8 FMAs instead of 4 -- the kernel was bound by the shared-memory pipe (M*C^2/16 LDS.128 per launch, the
+  // same count at every level), not by HBM.  Each pixel's FMA order is unchanged.
   for (int it = 0; it < iters; ++it) {
-  const int pix = (blockIdx.x * iters + it) * blockDim.y + slot;
-  if (pix >= P) return;
-  const float* xr = x + (int64_t)pix * C;
-  float acc[4];
-  if (PERM) {
+    const int pixA = (blockIdx.x * iters + it) * 2 * blockDim.y + slot;
+    if (pixA >= P) return;
+    const int pixB = pixA + blockDim.y;
+    const bool hasB = pixB < P;
+    const float* xrA = x + (int64_t)pixA * C;
+    const float* xrB = x + (int64_t)(hasB ? pixB : pixA) * C;
+    float accA[4], accB[4];
+    if (PERM) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      const int o = og * 4 + a, s = sidx[o];
-      float t = xr[s];
-      if (has_an) t = reverse ? (t * sc[o] - bs[o]) : ((t + bs[s]) * sc[s]);
-      acc[a] = t;
-    }
-  } else {
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+      for (int a = 0; a < 4; ++a) {
+        const int o = og * 4 + a, sx = sidx[o];
+        float tA = xrA[sx], tB = xrB[sx];
+        if (has_an) {
+          tA = reverse ? (tA * sc[o] - bs[o]) : ((tA + bs[sx]) * sc[sx]);
+          tB = reverse ? (tB * sc[o] - bs[o]) : ((tB + bs[sx]) * sc[sx]);
+        }
+        accA[a] = tA; accB[a] = tB;
+      }
+    } else {
 #pragma unroll
-    for (int i0 = 0; i0 < C; i0 += 24) {
-      float4 xb[6];                            // up to 24 channels in flight: one memory latency per batch
+      for (int a = 0; a < 4; ++a) { accA[a] = 0.f; accB[a] = 0.f; }
 #pragma unroll
-      for (int b = 0; b < 6; ++b)
-        xb[b] = (i0 + 4 * b < C) ? *reinterpret_cast<const float4*>(xr + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i0 = 0; i0 < C; i0 += 12) {
+        float4 xa4[3], xb4[3];                   // 12 channels of both pixels in flight: one memory latency per batch
 #pragma unroll
-      for (int b = 0; b < 6; ++b) {
-        const int i = i0 + 4 * b;
-        if (i < C) {
-          float xa[4] = {xb[b].x, xb[b].y, xb[b].z, xb[b].w};
-          if (!reverse && has_an) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bs + i);
-            const float4 s4 = *reinterpret_cast<const float4*>(sc + i);
-            xa[0] = (xa[0] + b4.x) * s4.x; xa[1] = (xa[1] + b4.y) * s4.y;
-            xa[2] = (xa[2] + b4.z) * s4.z; xa[3] = (xa[3] + b4.w) * s4.w;
-          }
+        for (int b = 0; b < 3; ++b) {
+          const bool in = i0 + 4 * b < C;
+          xa4[b] = in ? *reinterpret_cast<const float4*>(xrA + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xb4[b] = in ? *reinterpret_cast<const float4*>(xrB + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
-            acc[0] = fmaf(wv.x, xa[u], acc[0]);
-            acc[1] = fmaf(wv.y, xa[u], acc[1]);
-            acc[2] = fmaf(wv.z, xa[u], acc[2]);
-            acc[3] = fmaf(wv.w, xa[u], acc[3]);
+        for (int b = 0; b < 3; ++b) {
+          const int i = i0 + 4 * b;
+          if (i < C) {
+            float xa[4] = {xa4[b].x, xa4[b].y, xa4[b].z, xa4[b].w};
+            float xb[4] = {xb4[b].x, xb4[b].y, xb4[b].z, xb4[b].w};
+            if (!reverse && has_an) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bs + i);
+              const float4 s4 = *reinterpret_cast<const float4*>(sc + i);
+              xa[0] = (xa[0] + b4.x) * s4.x; xa[1] = (xa[1] + b4.y) * s4.y;
+              xa[2] = (xa[2] + b4.z) * s4.z; xa[3] = (xa[3] + b4.w) * s4.w;
+              xb[0] = (xb[0] + b4.x) * s4.x; xb[1] = (xb[1] + b4.y) * s4.y;
+              xb[2] = (xb[2] + b4.z) * s4.z; xb[3] = (xb[3] + b4.w) * s4.w;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
+              accA[0] = fmaf(wv.x, xa[u], accA[0]); accA[1] = fmaf(wv.y, xa[u], accA[1]);
+              accA[2] = fmaf(wv.z, xa[u], accA[2]); accA[3] = fmaf(wv.w, xa[u], accA[3]);
+              accB[0] = fmaf(wv.x, xb[u], accB[0]); accB[1] = fmaf(wv.y, xb[u], accB[1]);
+              accB[2] = fmaf(wv.z, xb[u], accB[2]); accB[3] = fmaf(wv.w, xb[u], accB[3]);
+            }
           }
         }
       }
-    }
-    if (reverse && has_an) {
+      if (reverse && has_an) {
 #pragma unroll
-      for (int a = 0; a < 4; ++a) acc[a] = acc[a] * sc[og * 4 + a] - bs[og * 4 + a];
+        for (int a = 0; a < 4; ++a) {
+          accA[a] = accA[a] * sc[og * 4 + a] - bs[og * 4 + a];
+          accB[a] = accB[a] * sc[og * 4 + a] - bs[og * 4 + a];
+        }
+      }
     }
-  }
-  *reinterpret_cast<float4*>(z + (int64_t)pix * C + og * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(z + (int64_t)pixA * C + og * 4) = make_float4(accA[0], accA[1], accA[2], accA[3]);
+    if (hasB) *reinterpret_cast<float4*>(z + (int64_t)pixB * C + og * 4) = make_float4(accB[0], accB[1], accB[2], accB[3]);
   }
 }
 
@@ -201,6 +221,130 @@ rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restr
     v += psum;
     ld_out[n] = v;
     tickets[n] = 0u;                                             // ready for the next launch on this stream
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Same operation with the P3 rows of the CTA's pixel run staged in shared memory.  In rows_coupling_kernel
+// every lane gathers its nine 8-byte taps straight from global memory, from nine rows ldp*4 bytes apart: the
+// kernel is bound by load latency and L1 wavefronts (ncu: 48 % of the stall samples on the first tap add, IPC
+// 1.1), 59 % of the HBM roofline at level 1 and 20-30 % at levels 2-3.  Here a CTA owns a contiguous run of
+// T pixels of one sample, copies rows [p0-W-1, p1+W+1) of P3 (a contiguous block of global memory) with 16-byte
+// cp.async in one shot -- fully coalesced, every byte of P3 fetched by ~1.2 CTAs instead of through nine
+// scattered sector reads -- and gathers the taps from shared memory (pitch ldp+4 floats: conflict-light).
+// Arithmetic, summation order and the per-sample logdet reduction are those of rows_coupling_kernel.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(256)
+rows_coupling_win_kernel(const float* __restrict__ P3, int ldp, const float* __restrict__ bias3,
+                         const float* __restrict__ logs3, float f, float* __restrict__ z,
+                         float* __restrict__ h_save, int C, int H, int W, FastDiv divW, FastDiv divCh, FastDiv divVec,
+                         int T, int pitch, int affine, int reverse,
+                         const float* __restrict__ ld_in, float* __restrict__ ld_out,
+                         const float* __restrict__ an_logs, float an_f, const float* __restrict__ logabsdet,
+                         float sign, float* __restrict__ partials, unsigned int* __restrict__ tickets) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float win[];
+  __shared__ float red[32];
+  __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
+  __shared__ int s_last;
+  const int HW = H * W, Ch = C >> 1, Cout = affine ? C : Ch;
+  const int n = blockIdx.y;
+  const int tid = threadIdx.x, nthr = 256;
+  const int p0 = blockIdx.x * T, p1 = min(p0 + T, HW);
+  const int r0 = max(p0 - W - 1, 0), r1 = min(p1 + W + 1, HW);
+  {
+    const int vec = (int)divVec.d;                     // float4 per row that hold the 9*Cout tap columns
+    const float* src = P3 + ((int64_t)n * HW + r0) * ldp;
+    const int total = (r1 - r0) * vec;
+    for (int i = tid; i < total; i += nthr) {
+      const int r = fdiv(i, divVec), v = i - r * vec;
+      cp_async16(win + r * pitch + 4 * v, src + (int64_t)r * ldp + 4 * v);
+    }
+  }
+  for (int c = tid; c < Cout; c += nthr) { s_b[c] = bias3[c]; s_e[c] = expf(logs3[c] * f); }
+  cp_async_wait_all();
+  __syncthreads();
+  float lsum = 0.f;
+  const int items = (p1 - p0) * Ch;
+  for (int i = tid; i < items; i += nthr) {
+    const int pl = fdiv(i, divCh), j = i - pl * Ch;
+    const int pix = p0 + pl;
+    const int yy = fdiv(pix, divW), xx = pix - yy * W;
+    const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
+    const int64_t row = (int64_t)n * HW + pix;
+    float* zp = z + row * C + Ch + j;
+    float v = *zp;
+    const float* wrow = win + (pix - r0) * pitch;
+    if (affine) {
+      const float* Pp = wrow + 2 * j;
+      float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+        if (ok) {
+          const float2 tv = *reinterpret_cast<const float2*>(Pp + (dy * W + dx) * pitch + t * Cout);
+          u0 += tv.x; u1 += tv.y;
+        }
+      }
+      const float shift = (u0 + s_b[2 * j]) * s_e[2 * j];
+      const float hsc = (u1 + s_b[2 * j + 1]) * s_e[2 * j + 1];
+      const float scale = 1.f / (1.f + expf(-(hsc + 2.f)));   // F.sigmoid(scale + 2.)
+      if (!reverse) { v = (v + shift) * scale; lsum += logf(scale); }
+      else { v = v / scale - shift; lsum -= logf(scale); }
+      *zp = v;
+      if (h_save) *reinterpret_cast<float2*>(h_save + row * Cout + 2 * j) = make_float2(shift, hsc);
+    } else {
+      const float* Pp = wrow + j;
+      float u = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dy = t / 3 - 1, dx = t % 3 - 1;
+        const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+        if (ok) u += Pp[(dy * W + dx) * pitch + t * Cout];
+      }
+      const float h = (u + s_b[j]) * s_e[j];
+      v = reverse ? v - h : v + h;
+      *zp = v;
+      if (h_save) h_save[row * Cout + j] = h;
+    }
+  }
+  if (!ld_out) return;
+  const float tot = block_sum(lsum, red);
+  const int nblk = gridDim.x;
+  if (tid == 0) {
+    partials[n * nblk + blockIdx.x] = tot;
+    __threadfence();
+    const unsigned int t = atomicAdd(tickets + n, 1u);
+    s_last = (t == (unsigned int)(nblk - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float a = 0.f;
+  if (an_logs)
+    for (int c = tid; c < C; c += nthr) a += an_logs[c] * an_f;
+  const float term = block_sum(a, red);
+  float ps = 0.f;
+  if (affine)
+    for (int b = tid; b < nblk; b += nthr) ps += __ldcg(partials + n * nblk + b);
+  const float psum = block_sum(ps, red);
+  if (tid == 0) {
+    float v = ld_in ? ld_in[n] : 0.f;
+    v += sign * (term * (float)HW);
+    if (logabsdet) v += sign * (logabsdet[0] * (float)HW);
+    v += psum;
+    ld_out[n] = v;
+    tickets[n] = 0u;
   }
 }
 
@@ -469,6 +613,276 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
     }
     __syncthreads();
     for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, ws[e]);
+  }
+  __syncthreads();
+  if (has_an)
+    for (int c = tid; c < C; c += 256) {
+      atomicAdd(dbias + c, s_red[c] * sc[c]);
+      atomicAdd(dlogs + c, f * s_red[C + c]);
+    }
+  // ---- sample-independent logdet terms (one CTA)
+  if (blockIdx.x == 0 && dld) {
+    float a = 0.f;
+    for (int n = tid; n < Nld; n += 256) a += dld[n];
+    const float tot = block_sum(a, red);
+    if (tid == 0) red[32] = tot * (float)HW;
+    __syncthreads();
+    const float Gs = red[32];
+    if (has_an)
+      for (int c = tid; c < C; c += 256) atomicAdd(dlogs + c, f * Gs);
+    if (!PERM && winv)
+      for (int e = tid; e < C * C; e += 256) {
+        const int o = e / C, i = e - o * C;
+        atomicAdd(dw + e, Gs * winv[i * C + o]);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Same adjoint with the conv1-dgrad operand staged through shared memory.  In rows_mix_bwd_kernel every
+// (pixel, channel quad) thread gathers its 9..18 taps of dA1 straight from global memory, from nine rows ld_a1*4
+// bytes apart (ncu: 38 % of the stall samples wait on those loads, IPC 1.0, 30 % of warp slots occupied;
+// 20-25 % of the HBM roofline).  Here the rows [g0-W-1, g0+TP+W+1) of dA1 -- contiguous in global memory -- are
+// copied with 16-byte cp.async while x and dz are staged, and the taps are gathered from shared memory by
+// (pixel, channel pair) items, which also balances the work (the quad mapping left a third of the threads idle).
+// Further changes: compile-time channel count CT (12/24/48; 0 = run time) and a conflict-free shared-memory
+// combine of the register dW blocks instead of contended shared float atomics (CAS loops).
+// Element arithmetic and summation order of dx are those of rows_mix_bwd_kernel.
+// ------------------------------------------------------------------------------------------
+template <bool PERM, int RMB_MAXIT, int CT>
+__global__ void __launch_bounds__(256, RMB_MAXIT == 1 ? 3 : 1)
+rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
+                        int ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
+                        const float* __restrict__ bias, const float* __restrict__ logs, float f,
+                        float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
+                        float* __restrict__ dbias, int NP, int C_rt, int H, int W, FastDiv divW, FastDiv divHW,
+                        FastDiv divG, FastDiv divVec, FastDiv divPair, int TP, int wpitch, int win_floats,
+                        const float* __restrict__ dld, int Nld, const float* __restrict__ winv) {
+  pdl_trigger();
+  pdl_wait();
+  const int C = CT ? CT : C_rt;
+  const int G = C >> 2;
+  extern __shared__ __align__(16) float smem[];
+  float* win = smem;                          // [TP + 2W + 2][wpitch] dA1 rows; later the dW combine scratch
+  float* ws = win + win_floats;               // [C][C]    W (mix only)
+  float* a_s = ws + (PERM ? 0 : C * C);       // [TP][C]   a = actnorm(x)
+  float* d_s = a_s + TP * C;                  // [TP][C]   dz, later da
+  float* sc = d_s + TP * C;                   // [C]
+  float* bs = sc + C;                         // [C]
+  float* s_red = bs + C;                      // [2][C]
+  int* sinv = reinterpret_cast<int*>(s_red + 2 * C);   // [C] inverse permutation (perm only)
+  float* red = reinterpret_cast<float*>(sinv + C);      // [32] + [1]
+  const int tid = threadIdx.x;
+  const bool has_an = bias != nullptr;
+  const int HW = H * W;
+  auto div_g = [&](int v) { return CT ? v / (CT ? CT / 4 : 1) : fdiv(v, divG); };
+  for (int c = tid; c < C; c += 256) {
+    sc[c] = has_an ? expf(logs[c] * f) : 1.f;
+    bs[c] = has_an ? bias[c] : 0.f;
+    s_red[c] = 0.f; s_red[C + c] = 0.f;
+    if (PERM) sinv[(int)idx[c]] = c;
+  }
+  if (!PERM)
+    for (int e = tid; e < C * C; e += 256) ws[e] = w[e];
+  __syncthreads();
+  const int slot = div_g(tid), quad = tid - slot * G;
+  const int ppb = 256 / G;
+  const int nb4 = G * G;
+  int psplit = 256 / nb4;
+  if (psplit < 1) psplit = 1;
+  const int nitems = nb4 * psplit;
+  float dwacc[RMB_MAXIT][16];
+#pragma unroll
+  for (int k = 0; k < RMB_MAXIT; ++k)
+#pragma unroll
+    for (int u = 0; u < 16; ++u) dwacc[k][u] = 0.f;
+  const int chunks = 256 / C;
+  const int red_ch = tid / C, red_i = tid - red_ch * C;
+  float sg_acc = 0.f, sga_acc = 0.f;
+  const int vec = (int)divVec.d;              // float4 per dA1 row that hold its 9*Cin columns
+  const int npair = Cin >> 1;
+
+  const int ntiles = (NP + TP - 1) / TP;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int g0 = tile * TP;
+    const int wr0 = max(g0 - W - 1, 0), wr1 = min(g0 + TP + W + 1, NP);
+    // ---- (a) async copy of the dA1 window
+    {
+      const float* src = dA1 + (int64_t)wr0 * ld_a1;
+      const int total = (wr1 - wr0) * vec;
+      for (int i = tid; i < total; i += 256) {
+        const int r = fdiv(i, divVec), v = i - r * vec;
+        cp_async16(win + r * wpitch + 4 * v, src + (int64_t)r * ld_a1 + 4 * v);
+      }
+    }
+    // ---- (b) stage a = actnorm(x) and dz, one float4 of one pixel per thread and pass
+    if (slot < ppb) {
+      for (int p = slot; p < TP; p += ppb) {
+        const int pix = g0 + p;
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), dv = xv;
+        if (pix < NP) {
+          xv = *reinterpret_cast<const float4*>(x + (int64_t)pix * C + quad * 4);
+          dv = *reinterpret_cast<const float4*>(dz + (int64_t)pix * C + quad * 4);
+          const float4 b4 = *reinterpret_cast<const float4*>(bs + quad * 4);
+          const float4 s4 = *reinterpret_cast<const float4*>(sc + quad * 4);
+          xv.x = (xv.x + b4.x) * s4.x; xv.y = (xv.y + b4.y) * s4.y;
+          xv.z = (xv.z + b4.z) * s4.z; xv.w = (xv.w + b4.w) * s4.w;
+        }
+        *reinterpret_cast<float4*>(a_s + p * C + quad * 4) = xv;
+        *reinterpret_cast<float4*>(d_s + p * C + quad * 4) = dv;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- (c) conv1 dgrad: dz[p][c] += sum_tap dA1[nbr(p, tap)][tap*Cin + c], c < Cin, taps in the order of
+    // rows_mix_bwd_kernel; one (pixel, channel pair) item per thread and pass
+    {
+      const int total = TP * npair;
+      for (int i = tid; i < total; i += 256) {
+        const int p = fdiv(i, divPair), j = i - p * npair;
+        const int pix = g0 + p;
+        if (pix < NP) {
+          const int n = fdiv(pix, divHW);
+          const int q = pix - n * HW;
+          const int yy = fdiv(q, divW), xx = q - yy * W;
+          const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
+          const float* ap = win + (pix - wr0) * wpitch + 2 * j;
+          float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int tap = 8 - t;
+            const int dy = tap / 3 - 1, dxx = tap % 3 - 1;
+            const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dxx < 0 ? lf : (dxx > 0 ? rt : true));
+            if (ok) {
+              const float2 v0 = *reinterpret_cast<const float2*>(ap + (dy * W + dxx) * wpitch + t * Cin);
+              r0 += v0.x; r1 += v0.y;
+            }
+          }
+          float2* dp = reinterpret_cast<float2*>(d_s + p * C + 2 * j);
+          float2 dv = *dp;
+          dv.x = dv.x + r0; dv.y = dv.y + r1;
+          *dp = dv;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- dW[o][i] += sum_p dz[p][o] a[p][i] on 4x4 register blocks
+    if (!PERM) {
+#pragma unroll
+      for (int k = 0; k < RMB_MAXIT; ++k) {
+        const int it = tid + k * 256;
+        if (it < nitems) {
+          const int ps = it / nb4, blk = it - ps * nb4;
+          const int bo = div_g(blk), bi = blk - bo * G;
+          for (int p = ps; p < TP; p += psplit) {
+            const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + bo * 4);
+            const float4 a4 = *reinterpret_cast<const float4*>(a_s + p * C + bi * 4);
+            const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float aa[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) dwacc[k][u * 4 + v] = fmaf(dd[u], aa[v], dwacc[k][u * 4 + v]);
+          }
+        }
+      }
+    }
+    __syncthreads();                           // dW has read every dz element: da may now overwrite dz in place
+    // ---- da[p][i] = sum_o W[o][i] dz[p][o]; the G threads of a pixel sit in one warp
+    {
+      const int warp = tid >> 5, lane = tid & 31;
+      const int ppw = 32 / G;
+      const int pl = div_g(lane), ig = lane - pl * G;
+      for (int p0 = warp * ppw; p0 < TP; p0 += 8 * ppw) {
+        const int p = p0 + pl;
+        const bool act = pl < ppw && p < TP;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (act) {
+          if (PERM) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = d_s[p * C + sinv[ig * 4 + u]];
+          } else {
+#pragma unroll 4
+            for (int o = 0; o < C; o += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + o);
+              const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 wv = *reinterpret_cast<const float4*>(ws + (o + u) * C + ig * 4);
+                acc[0] = fmaf(wv.x, dd[u], acc[0]); acc[1] = fmaf(wv.y, dd[u], acc[1]);
+                acc[2] = fmaf(wv.z, dd[u], acc[2]); acc[3] = fmaf(wv.w, dd[u], acc[3]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (act) *reinterpret_cast<float4*>(d_s + p * C + ig * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // ---- per-channel reductions over the tile's pixels (registers; flushed once per CTA)
+    if (has_an && red_ch < chunks) {
+      for (int p = red_ch; p < TP; p += chunks) {
+        const float d = d_s[p * C + red_i];
+        sg_acc += d; sga_acc = fmaf(d, a_s[p * C + red_i], sga_acc);
+      }
+    }
+    // ---- dx = da * s, written back as whole pixels
+    if (slot < ppb) {
+      const float4 s4 = *reinterpret_cast<const float4*>(sc + quad * 4);
+      for (int p = slot; p < TP; p += ppb) {
+        const int pix = g0 + p;
+        if (pix < NP) {
+          const float4 d4 = *reinterpret_cast<const float4*>(d_s + p * C + quad * 4);
+          *reinterpret_cast<float4*>(dx + (int64_t)pix * C + quad * 4) =
+              make_float4(d4.x * s4.x, d4.y * s4.y, d4.z * s4.z, d4.w * s4.w);
+        }
+      }
+    }
+    __syncthreads();                           // the tile buffers and the window are free for the next tile
+  }
+  // ---- one round of global atomics per CTA
+  if (has_an && red_ch < chunks) {
+    atomicAdd(&s_red[red_i], sg_acc);
+    atomicAdd(&s_red[C + red_i], sga_acc);
+  }
+  if (!PERM) {
+    if (RMB_MAXIT == 1) {
+      // thread `it` parks its 4x4 block in the (dead) window: scratch[it][16]; then one thread per dW element sums
+      // the psplit copies in a fixed order and issues the CTA's single global atomic for it
+      if (tid < nitems) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(win + tid * 16 + u * 4) =
+              make_float4(dwacc[0][u * 4], dwacc[0][u * 4 + 1], dwacc[0][u * 4 + 2], dwacc[0][u * 4 + 3]);
+      }
+      __syncthreads();
+      for (int e = tid; e < C * C; e += 256) {
+        const int o = CT ? e / (CT ? CT : 1) : e / C, i = e - o * C;
+        const int blk = (o >> 2) * G + (i >> 2), sub = (o & 3) * 4 + (i & 3);
+        float acc = 0.f;
+        for (int ps = 0; ps < psplit; ++ps) acc += win[(ps * nb4 + blk) * 16 + sub];
+        atomicAdd(dw + e, acc);
+      }
+    } else {
+      for (int e = tid; e < C * C; e += 256) ws[e] = 0.f;
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < RMB_MAXIT; ++k) {
+        const int it = tid + k * 256;
+        if (it < nitems) {
+          const int ps = it / nb4, blk = it - ps * nb4;
+          const int bo = div_g(blk), bi = blk - bo * G;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) atomicAdd(&ws[(bo * 4 + u) * C + bi * 4 + v], dwacc[k][u * 4 + v]);
+        }
+      }
+      __syncthreads();
+      for (int e = tid; e < C * C; e += 256) atomicAdd(dw + e, ws[e]);
+    }
   }
   __syncthreads();
   if (has_an)
@@ -826,7 +1240,7 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
 #define GLOWK_MIX_LAUNCH(PERM_, CT_, SMEM_)                                                                          \
   do {                                                                                                               \
     auto kern = rows_mix_kernel<PERM_, CT_>;                                                                         \
-    const int64_t passes = ceil_div(P, ppb);                                                                         \
+    const int64_t passes = ceil_div(P, 2 * ppb);             /* two pixels per thread and pass */                   \
     int iters = (int)ceil_div(passes, resident_ctas((const void*)kern, G * ppb, SMEM_));                             \
     iters = iters < 1 ? 1 : (iters > 32 ? 32 : iters);                                                               \
     const unsigned grid = (unsigned)ceil_div(passes, iters);                                                         \
@@ -871,12 +1285,43 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
   GLOWK_CHECK_ARG(N <= 65535 && H * W * C < (1ll << 30), "glowk_rows_coupling: shape out of range");
   GLOWK_CHECK_ARG(N * H * W * ldp < (1ll << 31), "glowk_rows_coupling: P3 too large for 32-bit tap offsets");
   const int Ch = (int)C / 2, ppb = 256 / Ch;
-  // CTAs per sample: glowk_rows_coupling_nblk() is the upper bound the caller sized `partials` for.  The kernel is
-  // latency-bound (every pixel group is one round of dependent loads), so its time is ~ waves x (groups per CTA +
-  // a constant for the per-CTA set-up and reduction tail): pick the split that minimises that, which avoids
-  // the nearly empty last wave of a fixed split (3584 CTAs on 888 resident slots at B = 512, level 1).
-  const int64_t groups = ceil_div(H * W, ppb);
   const int64_t nblk_max = glowk_rows_coupling_nblk(H * W, C);
+  // (a) shared-memory window kernel: T pixels per CTA, window of min(T + 2W + 2, HW) rows of ldp+4 floats, sized for
+  // two CTAs per SM; taken when the window fits and the caller's `partials` covers the CTAs per sample
+  // Measured on B200 (B = 512, gpurun_out/h3_*): SLOWER than the direct gather (62 vs 42 us per launch averaged
+  // over the three levels): with ~100 KB of window only two CTAs fit per SM and each one waits for its whole window
+  // before computing, so the copy and the arithmetic do not overlap.  Opt-in (GLOWK_COUPLING_WIN=1).
+  static const bool use_win = getenv("GLOWK_COUPLING_WIN") != nullptr;
+  if (use_win && ldp % 4 == 0 && (((uintptr_t)P3) & 15) == 0) {
+    const int64_t HWl = H * W, pitch = ldp + 4;
+    const int64_t rows_max = (100 * 1024) / (pitch * 4);
+    const int64_t t_max = rows_max - 2 * W - 2;
+    if (t_max >= 16 || rows_max >= HWl) {
+      int64_t chunks = rows_max >= HWl ? 1 : ceil_div(HWl, t_max);
+      // whole samples per CTA leave the SMs short of CTAs when the batch is small
+      while (chunks < nblk_max && N * chunks < 2 * (int64_t)sm_count() && ceil_div(HWl, chunks + 1) >= 16) ++chunks;
+      const int64_t T = ceil_div(HWl, chunks);
+      chunks = ceil_div(HWl, T);
+      const int64_t rows = (T + 2 * W + 2) < HWl ? (T + 2 * W + 2) : HWl;
+      const size_t smem = (size_t)rows * pitch * 4;
+      if (chunks <= nblk_max || !ld_out) {
+        const int vec = (int)((9 * Cout + 3) / 4);
+        // always the same value (>= any window this launcher builds): safe when several host threads launch
+        GLOWK_CUDA(cudaFuncSetAttribute(rows_coupling_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        const dim3 gridw((unsigned)chunks, (unsigned)N);
+        GLOWK_CUDA(launch_pdl(rows_coupling_win_kernel, gridw, 256, smem, (cudaStream_t)stream, P3, (int)ldp, bias3, logs3,
+                              logscale_factor, z, h_save, (int)C, (int)H, (int)W, make_fastdiv(W), make_fastdiv(Ch),
+                              make_fastdiv(vec), (int)T, (int)pitch, affine, reverse, ld_in, ld_out, an_logs,
+                              an_logscale_factor, logabsdet, sign, partials, (unsigned int*)tickets));
+        GLOWK_CHECK_LAUNCH("glowk_rows_coupling(window)");
+        return GLOWK_OK;
+      }
+    }
+  }
+  // (b) direct-gather kernel.  CTAs per sample: the kernel is latency-bound (every pixel group is one round of
+  // dependent loads), so its time is ~ waves x (groups per CTA + a constant for the per-CTA set-up and reduction
+  // tail): pick the split that minimises that.
+  const int64_t groups = ceil_div(H * W, ppb);
   const int64_t resident = resident_ctas((const void*)rows_coupling_kernel, 256, 0);
   int64_t nblk = 1, best_cost = -1;
   for (int64_t b = 1; b <= nblk_max; ++b) {
@@ -937,6 +1382,44 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)dz | (uintptr_t)dx) & 15) == 0, "glowk_rows_actnorm_mix_bwd: rows must be 16-byte aligned");
   const FastDiv dW_ = make_fastdiv(W), dHW = make_fastdiv(H * W), dG = make_fastdiv(C / 4);
   const bool big = (C / 4) * (C / 4) > 256;
+  // (a) conv1-dgrad operand staged through a shared-memory window (see rows_mix_bwd_win_kernel)
+  static const bool no_win = getenv("GLOWK_MIXBWD_NOWIN") != nullptr;        // A/B switch for profiling
+  if (dA1 && !no_win && ld_a1 % 4 == 0 && (((uintptr_t)dA1) & 15) == 0) {
+    const int vec = (int)((9 * Cin + 3) / 4), wpitch = 4 * vec + 4;
+    int win_floats = 0;
+    auto smem_for = [&](int tp) {
+      win_floats = (int)((tp + 2 * W + 2) * wpitch);
+      if (win_floats < 4096) win_floats = 4096;                            // also the dW combine scratch (256 x 16)
+      return sizeof(float) * ((size_t)win_floats + 2 * (size_t)tp * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
+    };
+    int TPw = 128;                          // <= 72 KB per CTA (3 per SM); smaller tiles until every SM has two CTAs
+    while (TPw > 32 && (smem_for(TPw) > 72 * 1024 || ceil_div(NP, TPw) < 2 * sm_count())) TPw >>= 1;
+    const size_t smem_w = smem_for(TPw);
+    if (smem_w <= 160 * 1024) {
+      const int64_t tiles_w = ceil_div(NP, TPw);
+      const FastDiv dVec = make_fastdiv(vec), dPair = make_fastdiv(Cin / 2);
+#define GLOWK_RMBW_LAUNCH(PERM_, IT_, CT_)                                                                               \
+  do {                                                                                                                   \
+    auto kern = rows_mix_bwd_win_kernel<PERM_, IT_, CT_>;                                                                \
+    GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));                     \
+    const int64_t cap = resident_ctas((const void*)kern, 256, smem_w);                                                   \
+    const unsigned grid = (unsigned)(tiles_w < cap ? tiles_w : cap);                                                     \
+    GLOWK_CUDA(launch_pdl(kern, grid, 256, smem_w, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs,             \
+                          logscale_factor, dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, dVec,    \
+                          dPair, TPw, wpitch, win_floats, dld, (int)N, winv));                                           \
+  } while (0)
+      if (!w) { if (big) GLOWK_RMBW_LAUNCH(true, 3, 0); else GLOWK_RMBW_LAUNCH(true, 1, 0); }
+      else if (big) GLOWK_RMBW_LAUNCH(false, 3, 0);
+      else if (C == 12) GLOWK_RMBW_LAUNCH(false, 1, 12);
+      else if (C == 24) GLOWK_RMBW_LAUNCH(false, 1, 24);
+      else if (C == 48) GLOWK_RMBW_LAUNCH(false, 1, 48);
+      else GLOWK_RMBW_LAUNCH(false, 1, 0);
+#undef GLOWK_RMBW_LAUNCH
+      GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd(window)");
+      return GLOWK_OK;
+    }
+  }
+  // (b) direct-gather kernel
 #define GLOWK_RMB_LAUNCH(PERM_, IT_)                                                                                     \
   do {                                                                                                                   \
     auto kern = rows_mix_bwd_kernel<PERM_, IT_>;                                                                         \
