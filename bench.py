@@ -30,6 +30,8 @@ WORKLOADS = {
     # name: (image_shape HWC, K, L, hidden, coupling, default per-GPU batch, fwd GFLOP/img)
     "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 512, 32.06),
     "cifar32": ((32, 32, 3), 32, 3, 512, "affine", 256, 8.02),
+    "cifar32_additive": ((32, 32, 3), 32, 3, 512, "additive", 256, 7.22),
+    "celebahq256": ((256, 256, 3), 32, 6, 512, "affine", 8, 537.6),
     "tiny": ((32, 32, 3), 4, 3, 64, "affine", 16, None),
 }
 
@@ -237,10 +239,10 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
     gemm_flops = 2.0 * M * hidden * hidden
     cases = [
         ("dgrad2", "gemm_tc_kernel<RELU_BWD,bf16>: dgrad of conv2 + ReLU/ActNorm backward epilogue (M=%d N=K=%d)" % (M, hidden),
-         # as launched by the training step: dbias reduced in the epilogue, dlogs deferred to the batched
-         # glowk_conv_actnorm_finish_batched pass (rows_path.GradPlan.finish)
+         # as launched by the training step: no column sums in the epilogue (dbias = ones column of conv1's wgrad,
+         # dlogs from W, dW, dbias in the batched glowk_conv_actnorm_finish_batched pass, rows_path.GradPlan.finish)
          lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_RELU_BWD, None, logs, 3.0, y=hs[(i + 1) % R], dlogs=None,
-                           dbias=dbias, out_dtype=_C.BF16, out=outs[i]),
+                           dbias=None, out_dtype=_C.BF16, out=outs[i]),
          "hbm", 3.0 * M * hidden * 2, gemm_flops),
         ("wgrad2", "wgrad_tc_kernel: dW2 += d2^T h1 (P=%d, 512x512)" % M,
          lambda i: KF.gemm_wgrad(hs[i], hs[(i + 1) % R], hidden, hidden, dw),

@@ -108,6 +108,14 @@ int glowk_im2col(const float* src, int64_t N, int64_t sN, int64_t c0, int64_t Ci
 /* Same gather from a pixel-major fp32 source [P][ld_src] (channels c0..c0+Cin). */
 int glowk_im2col_rows(const float* src, int64_t ld_src, int64_t N, int64_t c0, int64_t Cin, int64_t H,
                       int64_t W, int ksize, int flip, void* dst, int act_dtype, int64_t ld, void* stream);
+/* glowk_im2col_rows (3x3, bf16 output, even Cin / c0 / ld_src) that additionally writes 1.0 into the zero-padding
+ * column ones_col (9*Cin <= ones_col < ld; -1 = none).  The conv (zero weight in that column) and its dgrad are
+ * unaffected; the weight-gradient GEMM dW = d^T a1 then carries sum_p d[p][n] -- the bias gradient of the ActNorm
+ * behind the conv (module.py:34-50) -- in column ones_col, so the dgrad epilogue needs no column sum
+ * (see glowk_conv_actnorm_finish_batched). */
+int glowk_im2col_rows_ones(const float* src, int64_t ld_src, int64_t N, int64_t c0, int64_t Cin, int64_t H,
+                           int64_t W, int ksize, int flip, void* dst, int act_dtype, int64_t ld, int64_t ones_col,
+                           void* stream);
 /* dst[n,c,p] = rows[(n*HW+p)*ld + c] for c < C (rows of type act_dtype). */
 int glowk_rows_to_nchw(const void* rows, int act_dtype, int64_t ld, float* dst, int64_t N, int64_t C,
                        int64_t HW, void* stream);
@@ -297,14 +305,15 @@ int glowk_unpack_weight_grads_batched(const void* jobs, int64_t njobs, int64_t t
 
 /* Gradient finish of the ActNorm that follows a coupling-net conv (Conv2d, module.py:188-260; ActNorm.forward
  * module.py:122-149), batched over layers.  glowk_gemm(GLOWK_EPI_RELU_BWD) on the bf16 path may be called with
- * dlogs == NULL and dbias pointing at per-pass scratch `db`; this call then applies, per output channel n,
+ * dlogs == NULL and dbias == NULL or pointing at per-pass scratch `db`; this call then applies, per output channel n,
  *     dbias[n] += db[n];   dlogs[n] += f * ( <w[n,:], dw[n,:]> + bias[n]*db[n] )
  * which equals f * sum_m g*y of the direct epilogue reduction (y = (W a + b) s on the ReLU-active set).
  * jobs: device array of
  *   struct { const bf16* w; const float* dw; const float* bias; const float* db; float* dbias; float* dlogs;
- *            int32 N, K, ldw, lddw; float f; int32 pad; }                                            (64 bytes)
+ *            int32 N, K, ldw, lddw; float f; int32 db_stride; }                                      (72 bytes)
  * w = the GEMM-layout bf16 weight of the forward pass, dw = THIS pass's weight gradient in the same [N][K] order
- * (K, ldw, lddw even); max_n = max over jobs of N. */
+ * (K, ldw, lddw even); db[n * db_stride] = this pass's bias gradient (db_stride = 1 for a vector the dgrad epilogue
+ * reduced into, lddw when it is the ones column of dw, glowk_im2col_rows_ones); max_n = max over jobs of N. */
 int glowk_conv_actnorm_finish_batched(const void* jobs, int64_t njobs, int64_t max_n, void* stream);
 
 #ifdef __cplusplus

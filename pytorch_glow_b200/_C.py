@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglowk.so")
+LIB_PATH = os.environ.get("GLOWK_LIB") or os.path.join(_HERE, "libglowk.so")     # GLOWK_LIB: A/B builds (tools/)
 
 F32, BF16 = 0, 1
 EPI_STORE, EPI_ACTNORM_RELU, EPI_ACTNORM, EPI_ZEROS, EPI_RELU_BWD = 0, 1, 2, 3, 4
@@ -34,6 +34,7 @@ SIGNATURES = {
     "glowk_squeeze2d": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_im2col": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p],
     "glowk_im2col_rows": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p],
+    "glowk_im2col_rows_ones": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _i64, _p],
     "glowk_rows_to_nchw": [_p, _i32, _i64, _p, _i64, _i64, _i64, _p],
     "glowk_tapsum_to_nchw": [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_pack_conv_weight": [_p, _i64, _i64, _i32, _i32, _p, _i32, _i64, _i64, _p],

@@ -87,9 +87,10 @@ extern "C" int glowk_gemm_ex(const void* A, int64_t lda, const void* B, int64_t 
   if (epilogue != GLOWK_EPI_STORE) GLOWK_CHECK_ARG(logs, "glowk_gemm: epilogue %d needs logs", epilogue);
   if (epilogue == GLOWK_EPI_ACTNORM_RELU || epilogue == GLOWK_EPI_ACTNORM || epilogue == GLOWK_EPI_ZEROS)
     GLOWK_CHECK_ARG(bias, "glowk_gemm: epilogue %d needs bias", epilogue);
-  // dlogs may be NULL on the bf16 path: the caller recovers it with glowk_conv_actnorm_finish_batched
+  // dlogs / dbias may be NULL on the bf16 path: the caller recovers them with glowk_conv_actnorm_finish_batched
+  // (dbias from a ones column of its weight-gradient GEMM, dlogs from W, dW and dbias)
   if (epilogue == GLOWK_EPI_RELU_BWD)
-    GLOWK_CHECK_ARG(y && dbias && ldy >= N && (dlogs || act_dtype == GLOWK_BF16), "glowk_gemm: RELU_BWD needs y, dbias (and dlogs on the fp32 path)");
+    GLOWK_CHECK_ARG(y && ldy >= N && ((dlogs && dbias) || act_dtype == GLOWK_BF16), "glowk_gemm: RELU_BWD needs y (and dlogs, dbias on the fp32 path)");
   if (M == 0) return GLOWK_OK;
   EpiParams ep;
   ep.bias = bias; ep.logs = logs; ep.f = logscale_factor; ep.y = y; ep.ldy = ldy;

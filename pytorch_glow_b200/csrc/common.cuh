@@ -50,6 +50,15 @@ int resident_ctas(const void* kern, int threads, size_t smem);
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// The persistent tcgen05 GEMMs (one CTA per SM for the whole kernel) can release their dependents either at entry
+// (default) or -- build with -DGLOWK_PDL_LATE -- once their TMA producer has issued the loads of its last tile.
+#ifdef GLOWK_PDL_LATE
+__device__ __forceinline__ void pdl_trigger_entry() {}
+__device__ __forceinline__ void pdl_trigger_drain() { pdl_trigger(); }
+#else
+__device__ __forceinline__ void pdl_trigger_entry() { pdl_trigger(); }
+__device__ __forceinline__ void pdl_trigger_drain() {}
+#endif
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

@@ -374,7 +374,7 @@ template <int V>
 __global__ void __launch_bounds__(256)
 im2col_rows_piece_kernel(const float* __restrict__ src, int ld_src, int NP, int c0, int Cin, int H, int W,
                          FastDiv divW, FastDiv divHW, FastDiv divChunks, int flip, __nv_bfloat16* __restrict__ dst,
-                         int ld, int ppb, int iters) {
+                         int ld, int ppb, int iters, int ones_col) {
   pdl_trigger();
   pdl_wait();
   constexpr int NG = 8 / V;
@@ -396,6 +396,10 @@ im2col_rows_piece_kernel(const float* __restrict__ src, int ld_src, int NP, int 
       dy[g] = -(1 << 20); dx[g] = 0; off[g] = 0;      // zero padding columns: never in bounds
     }
   }
+  // ones_col >= 9*Cin (a zero-padding column, -1 = none) is written as 1.0: the weight-gradient GEMM dW = d^T a1
+  // then delivers sum_p d[p][n] -- the bias gradient of the ActNorm after the conv -- in that column for free,
+  // while the conv itself (zero weight there) and its dgrad are unaffected
+  const int ones_u = ones_col >= 0 ? ones_col - 8 * j : -1;
   const int pix0 = blockIdx.x * (ppb * iters) + slot;
   for (int it = 0; it < iters; ++it) {
     const int pix = pix0 + it * ppb;
@@ -420,6 +424,10 @@ im2col_rows_piece_kernel(const float* __restrict__ src, int ld_src, int NP, int 
           v[g * V + 4 * q] = t.x; v[g * V + 4 * q + 1] = t.y; v[g * V + 4 * q + 2] = t.z; v[g * V + 4 * q + 3] = t.w;
         }
       }
+    }
+    if (ones_u >= 0 && ones_u < 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (u == ones_u) ? 1.f : v[u];
     }
     __nv_bfloat162 h[4];
 #pragma unroll
@@ -707,7 +715,7 @@ extern "C" int glowk_squeeze2d(const float* x, float* y, int64_t N, int64_t C, i
 
 static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_t N, int64_t Ctot, int64_t c0,
                          int64_t Cin, int64_t H, int64_t W, int ksize, int flip, void* dst, int act_dtype,
-                         int64_t ld, void* stream) {
+                         int64_t ld, void* stream, int64_t ones_col = -1) {
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(src && dst, "glowk_im2col: null pointer");
   GLOWK_CHECK_ARG(ksize == 1 || ksize == 3, "glowk_im2col: kernel size must be 1 or 3");
@@ -724,7 +732,8 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
     __nv_bfloat16* d = (__nv_bfloat16*)dst;
     const int chunks = (int)(ld / 8);
     static const bool warp_variant = getenv("GLOWK_IM2COL_WARP") != nullptr;     // A/B switch for profiling
-    if (chunks <= 256 && !warp_variant) {
+    GLOWK_CHECK_ARG(ones_col < 0 || (ones_col >= 9 * Cin && ones_col < ld && chunks <= 256), "glowk_im2col_rows_ones: ones_col=%lld must be a padding column", (long long)ones_col);
+    if (chunks <= 256 && (!warp_variant || ones_col >= 0)) {
       const int ppb = 256 / chunks;
       int64_t iters = ceil_div(NP, ppb) / (16 * (int64_t)sm_count());             // >= 16 CTAs per SM before CTAs loop
       iters = iters < 1 ? 1 : (iters > 8 ? 8 : iters);
@@ -732,7 +741,7 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
       const FastDiv dCh = make_fastdiv(chunks);
 #define GLOWK_IM2COL_PIECE(V_)                                                                                          \
   GLOWK_CUDA(launch_pdl(im2col_rows_piece_kernel<V_>, gp, 256, 0, st, src, (int)ld_src, (int)NP, (int)c0, (int)Cin,     \
-                        (int)H, (int)W, dW_, dHW, dCh, flip, d, (int)ld, ppb, (int)iters))
+                        (int)H, (int)W, dW_, dHW, dCh, flip, d, (int)ld, ppb, (int)iters, (int)ones_col))
       if (Cin % 8 == 0 && c0 % 4 == 0 && ld_src % 4 == 0) GLOWK_IM2COL_PIECE(8);
       else if (Cin % 4 == 0 && c0 % 4 == 0 && ld_src % 4 == 0) GLOWK_IM2COL_PIECE(4);
       else GLOWK_IM2COL_PIECE(2);
@@ -750,6 +759,7 @@ static int im2col_common(const float* src, int64_t ld_src, bool rows_src, int64_
     GLOWK_CHECK_LAUNCH("glowk_im2col_rows(warp)");
     return GLOWK_OK;
   }
+  GLOWK_CHECK_ARG(ones_col < 0, "glowk_im2col_rows_ones: needs a pixel-major fp32 source, a 3x3 kernel, bf16 output and even Cin / c0 / pitch");
   const unsigned grid = (unsigned)ceil_div(total, 256);
 #define LAUNCH_IM2COL(T, R) im2col_kernel<T, R><<<grid, 256, 0, st>>>(src, ld_src, NP, Ctot, c0, (int)Cin, (int)H, (int)W, ksize, flip, (T*)dst, ld)
   if (act_dtype == GLOWK_BF16) { if (rows_src) LAUNCH_IM2COL(__nv_bfloat16, true); else LAUNCH_IM2COL(__nv_bfloat16, false); }
@@ -768,6 +778,12 @@ extern "C" int glowk_im2col(const float* src, int64_t N, int64_t sN, int64_t c0,
 extern "C" int glowk_im2col_rows(const float* src, int64_t ld_src, int64_t N, int64_t c0, int64_t Cin, int64_t H,
                                  int64_t W, int ksize, int flip, void* dst, int act_dtype, int64_t ld, void* stream) {
   return im2col_common(src, ld_src, true, N, 0, c0, Cin, H, W, ksize, flip, dst, act_dtype, ld, stream);
+}
+
+extern "C" int glowk_im2col_rows_ones(const float* src, int64_t ld_src, int64_t N, int64_t c0, int64_t Cin, int64_t H,
+                                      int64_t W, int ksize, int flip, void* dst, int act_dtype, int64_t ld,
+                                      int64_t ones_col, void* stream) {
+  return im2col_common(src, ld_src, true, N, 0, c0, Cin, H, W, ksize, flip, dst, act_dtype, ld, stream, ones_col);
 }
 
 extern "C" int glowk_rows_to_nchw(const void* rows, int act_dtype, int64_t ld, float* dst, int64_t N, int64_t C,

@@ -1159,7 +1159,7 @@ __global__ void unpack_grads_batched_kernel(const PackJob* __restrict__ jobs, in
 // by, dW / db this backward pass's own contributions (scratch, zeroed per pass), so gradient accumulation over
 // several passes stays correct:  dbias[n] += db[n];  dlogs[n] += f * (<W[n,:], dW[n,:]> + b[n]*db[n]).
 // ------------------------------------------------------------------------------------------
-struct FinishJob {           // 64 bytes, mirrored by pytorch_glow_b200/rows_path.py
+struct FinishJob {           // 72 bytes, mirrored by pytorch_glow_b200/rows_path.py
   const __nv_bfloat16* w;    // [N][ldw] bf16, k-order of dw
   const float* dw;           // [N][lddw] fp32, this pass only
   const float* bias;         // [N] ActNorm bias
@@ -1168,7 +1168,7 @@ struct FinishJob {           // 64 bytes, mirrored by pytorch_glow_b200/rows_pat
   float* dlogs;              // [N] accumulated into
   int32_t N, K, ldw, lddw;
   float f;
-  int32_t pad_;
+  int32_t db_stride;         // db[n * db_stride]: 1 for a vector, lddw when db is a (ones-)column of dw
 };
 
 __global__ void __launch_bounds__(256)
@@ -1189,7 +1189,7 @@ conv_actnorm_finish_kernel(const FinishJob* __restrict__ jobs) {
   }
   acc = warp_sum(acc);
   if (lane == 0) {
-    const float db = jb.db[n];
+    const float db = jb.db[(int64_t)n * jb.db_stride];
     jb.dbias[n] += db;
     jb.dlogs[n] += jb.f * (acc + jb.bias[n] * db);
   }

@@ -305,7 +305,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const uint16_t mask_all = mask_a | mask_b;
   const bool small_n = N <= EPI_NMAX;
 
-  pdl_trigger();                             // the next kernel may be scheduled as SMs free up (it waits for us)
+  pdl_trigger_entry();                       // the next kernel may be scheduled as SMs free up (it waits for us)
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_o);
@@ -376,6 +376,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
+      pdl_trigger_drain();
       if (tr) { g_gemm_trace[0] = w_empty; g_gemm_trace[1] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
@@ -440,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const uint8_t* yrow = my_y + lane * 64;
     const int sw = (lane >> 1) & 3;
     const bool want_gy = ep.dlogs != nullptr;
+    const bool want_gb = ep.dbias != nullptr;      // null: the caller takes the bias gradient from a ones column of its wgrad
     int acc = 0; uint32_t acc_phase = 0;
     int cached_nblk = -1;
     const bool tr = (dbg & 64) && blockIdx.x == 0 && ew == 0;
@@ -501,7 +503,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const int j = j4 * 8 + u * 2;
             const float g0 = yv.x > 0.f ? __uint_as_float(raw[j]) : 0.f;
             const float g1 = yv.y > 0.f ? __uint_as_float(raw[j + 1]) : 0.f;
-            ga[j] = g0 * yv.x; ga[j + 1] = g1 * yv.y;
+            if (want_gy) { ga[j] = g0 * yv.x; ga[j + 1] = g1 * yv.y; }
             v[j] = g0 * scl[j]; v[j + 1] = g1 * scl[j + 1];
           }
         }
@@ -529,12 +531,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           tma_store_commit();
         }
         // column sums over this warp's 32 rows: dbias += sum of the scaled gradient, dlogs += f * sum g*y
-        const float sb = warp_colsum32(v, lane);
-        float sa = 0.f;
+        float sb = 0.f, sa = 0.f;
+        if (want_gb) sb = warp_colsum32(v, lane);
         if (want_gy) sa = warp_colsum32(ga, lane);
-        if (ncol0 + lane < N) {
-          if (small_n) { atomicAdd(&s_g[ncol0 + lane], sb); if (want_gy) atomicAdd(&s_gy[ncol0 + lane], sa); }
-          else { atomicAdd(ep.dbias + ncol0 + lane, sb); if (want_gy) atomicAdd(ep.dlogs + ncol0 + lane, ep.f * sa); }
+        if ((want_gb || want_gy) && ncol0 + lane < N) {
+          if (small_n) { if (want_gb) atomicAdd(&s_g[ncol0 + lane], sb); if (want_gy) atomicAdd(&s_gy[ncol0 + lane], sa); }
+          else { if (want_gb) atomicAdd(ep.dbias + ncol0 + lane, sb); if (want_gy) atomicAdd(ep.dlogs + ncol0 + lane, ep.f * sa); }
         }
       }
       tcgen05_fence_before();
@@ -549,7 +551,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       epi_bar_sync<32 * EW>();
       for (int n = et; n < N; n += 32 * EW) {
         const float a = s_gy[n], b = s_g[n];
-        if (b != 0.f) atomicAdd(ep.dbias + n, b);
+        if (want_gb && b != 0.f) atomicAdd(ep.dbias + n, b);
         if (want_gy && a != 0.f) atomicAdd(ep.dlogs + n, ep.f * a);
       }
     }
@@ -763,7 +765,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   // pixel chunk, so its A and B rows are fetched from HBM once and re-read from L2 by the other tiles (with the
   // chunk fastest, every wave of CTAs re-streamed both operands: 815 MB of DRAM reads for 537 MB of operands)
 
-  pdl_trigger();
+  pdl_trigger_entry();
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_b); prefetch_tensormap(&tm_d);
@@ -800,6 +802,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
       }
+      pdl_trigger_drain();
     }
   } else if (warp == 1) {
     if (lane == 0) {

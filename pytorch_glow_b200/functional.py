@@ -141,12 +141,17 @@ def im2col(src, c0, cin, ksize, dtype, ld, flip=False):
     return rows
 
 
-def im2col_rows(src_rows, n, h, w, c0, cin, ksize, dtype, ld, flip=False):
+def im2col_rows(src_rows, n, h, w, c0, cin, ksize, dtype, ld, flip=False, ones_col=-1):
+    """ones_col >= 0: also write 1.0 into that zero-padding column (glowk_im2col_rows_ones)."""
     check_cuda(src_rows)
     assert src_rows.dtype == torch.float32 and src_rows.dim() == 2 and src_rows.is_contiguous()
     rows = torch.empty(n * h * w, ld, device=src_rows.device, dtype=TORCH_DTYPE[dtype])
-    call("glowk_im2col_rows", ptr(src_rows), src_rows.shape[1], n, c0, cin, h, w, int(ksize), int(bool(flip)),
-         ptr(rows), dtype, ld)
+    if ones_col >= 0:
+        call("glowk_im2col_rows_ones", ptr(src_rows), src_rows.shape[1], n, c0, cin, h, w, int(ksize),
+             int(bool(flip)), ptr(rows), dtype, ld, int(ones_col))
+    else:
+        call("glowk_im2col_rows", ptr(src_rows), src_rows.shape[1], n, c0, cin, h, w, int(ksize), int(bool(flip)),
+             ptr(rows), dtype, ld)
     return rows
 
 

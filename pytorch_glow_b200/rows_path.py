@@ -22,7 +22,7 @@ _JOB = np.dtype([("w", "<u8"), ("packed", "<u8"), ("O", "<i4"), ("I", "<i4"), ("
 assert _JOB.itemsize == 48
 # struct FinishJob of flow_rows_kernels.cu (glowk_conv_actnorm_finish_batched)
 _FJOB = np.dtype([("w", "<u8"), ("dw", "<u8"), ("bias", "<u8"), ("db", "<u8"), ("dbias", "<u8"), ("dlogs", "<u8"),
-                  ("N", "<i4"), ("K", "<i4"), ("ldw", "<i4"), ("lddw", "<i4"), ("f", "<f4"), ("pad", "<i4")])
+                  ("N", "<i4"), ("K", "<i4"), ("ldw", "<i4"), ("lddw", "<i4"), ("f", "<f4"), ("db_stride", "<i4")])
 assert _FJOB.itemsize == 72
 
 
@@ -194,11 +194,16 @@ class GradPlan:
     def view(self, owner, tag):
         return self.views[(id(owner), tag)]
 
-    def defer_dlogs(self, w_packed, dw, actnorm, db, n, k):
-        """Register one conv + ActNorm layer for the batched dbias / dlogs finish (bf16 path)."""
-        self._fin.append((w_packed.data_ptr(), dw.data_ptr(), actnorm.bias.data_ptr(), db.data_ptr(),
+    def defer_dlogs(self, w_packed, dw, actnorm, db, n, k, ones_col=-1):
+        """Register one conv + ActNorm layer for the batched dbias / dlogs finish (bf16 path).  ones_col >= 0:
+        this pass's bias gradient is column `ones_col` of dw (the im2col operand carried a ones column)."""
+        if ones_col >= 0:
+            db_ptr, stride = dw.data_ptr() + 4 * ones_col, dw.shape[1]
+        else:
+            db_ptr, stride = db.data_ptr(), 1
+        self._fin.append((w_packed.data_ptr(), dw.data_ptr(), actnorm.bias.data_ptr(), db_ptr,
                           _gbuf(actnorm.bias).data_ptr(), _gbuf(actnorm.logs).data_ptr(), n, k, w_packed.shape[1],
-                          dw.shape[1], float(actnorm.logscale_factor), 0))
+                          dw.shape[1], float(actnorm.logscale_factor), stride))
 
     def finish(self):
         if self._fin:
@@ -228,6 +233,13 @@ def _mix_params(step, device, reverse, need_inverse):
     return None, step.perm_module.device_indices(device, reverse), None, None, None
 
 
+def _ones_col(net, dt):
+    """First zero-padding column of the conv1 im2col operand (or -1): written as 1.0 on the bf16 training path so
+    that conv1's weight-gradient GEMM also yields the bias gradient of its ActNorm (glowk_im2col_rows_ones)."""
+    k = 9 * net.in_channels
+    return k if (dt == _C.BF16 and k < net.k1p and net.in_channels % 2 == 0) else -1
+
+
 def _step_forward(step, x, n, c, h, w, ld, ws, save):
     """FlowStep.normal_flow (network/model.py:82-117) on rows x [P][C]."""
     an = step.actnorm
@@ -238,7 +250,7 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save):
     z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
     net = step.f
     dt = net.dtype(step.conv_dtype)
-    a1 = K.im2col_rows(z, n, h, w, 0, net.in_channels, 3, dt, net.k1p)
+    a1 = K.im2col_rows(z, n, h, w, 0, net.in_channels, 3, dt, net.k1p, ones_col=_ones_col(net, dt) if save else -1)
     sv = {} if save else None
     p3 = net.tap_rows_from_a1(a1, dt, sv)
     c3 = net[4]
@@ -292,6 +304,9 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     defer = dt == _C.BF16
     dl2, db2 = (None, plan.view(step, "db2")) if defer else (_gbuf(an2.logs), _gbuf(an2.bias))
     dl1, db1 = (None, plan.view(step, "db1")) if defer else (_gbuf(an1.logs), _gbuf(an1.bias))
+    ones = _ones_col(net, dt) if defer else -1        # a1 carries a ones column: dbias of an1 = that column of dW1
+    if ones >= 0:
+        db1 = None
     d2 = K.gemm(d3col, net.packed("w3t", dt), hid, k3p, _C.EPI_RELU_BWD, None, an2.logs.detach().reshape(-1),
                 an2.logscale_factor, y=h2, dlogs=dl2, dbias=db2, out_dtype=dt, ldo=kh)
     # (3) conv2 (1x1)
@@ -304,7 +319,7 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     K.gemm_wgrad(d1, a1, hid, k1p, plan.view(step, "w1"))
     if defer:
         plan.defer_dlogs(net.packed("w2", dt), dw2, an2, db2, hid, hid)
-        plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p)
+        plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
     da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32)
     # (5) ActNorm + mix
     dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition

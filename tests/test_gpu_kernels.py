@@ -281,6 +281,58 @@ def test_gemm_relu_bwd(dtype):
     assert_close(dbias, ref_dbias.float(), 1e-3, 1e-2, "dbias")
 
 
+def test_conv_actnorm_deferred_grads():
+    """Conv2d backward on the bf16 path without epilogue column sums: the ActNorm bias gradient comes out of the
+    weight-gradient GEMM through a ones column of the im2col operand (glowk_im2col_rows_ones), the logs gradient
+    from <W, dW> + b*db (glowk_conv_actnorm_finish_batched).  Checked against the direct fp64 sums of the oracle
+    formulas (module.py:34-84, 188-260)."""
+    import numpy as np
+    from pytorch_glow_b200 import rows_path
+    n, h, w, cin, hid = 3, 6, 5, 6, 128
+    kp = (9 * cin + 63) // 64 * 64
+    ones_col = 9 * cin
+    z = torch.randn(n * h * w, 2 * cin, generator=g(90))
+    wgt = (torch.randn(hid, kp, generator=g(91)) * 0.2)
+    wgt[:, 9 * cin:] = 0                                              # GEMM-layout weight: zero padding columns
+    bias = torch.randn(hid, generator=g(92)) * 0.3
+    logs = torch.randn(hid, generator=g(93)) * 0.1
+    up = torch.randn(n * h * w, hid, generator=g(94)) * 0.5           # gradient wrt the ReLU output
+    a_plain = K.im2col_rows(cu(z), n, h, w, 0, cin, 3, _C.BF16, kp)
+    a1 = K.im2col_rows(cu(z), n, h, w, 0, cin, 3, _C.BF16, kp, ones_col=ones_col)
+    assert torch.equal(a1[:, :ones_col], a_plain[:, :ones_col]) and torch.equal(a1[:, ones_col + 1:], a_plain[:, ones_col + 1:])
+    assert float(a_plain[:, ones_col].float().abs().max()) == 0.0 and bool((a1[:, ones_col].float() == 1.0).all())
+    wb = cu(wgt).bfloat16()
+    s = torch.exp(3.0 * logs.double())
+    # forward: the ones column meets a zero weight
+    y = K.gemm(a1, wb, hid, kp, _C.EPI_ACTNORM_RELU, cu(bias), cu(logs), 3.0, out_dtype=_C.BF16)
+    y_plain = K.gemm(a_plain, wb, hid, kp, _C.EPI_ACTNORM_RELU, cu(bias), cu(logs), 3.0, out_dtype=_C.BF16)
+    assert torch.equal(y, y_plain)
+    # backward through ReLU + ActNorm: "dgrad of the next layer" stands in as an identity GEMM on `up`
+    eye = torch.eye(hid).bfloat16()
+    upb = up.bfloat16()
+    dl_direct = torch.zeros(hid, device=DEV); db_direct = torch.zeros(hid, device=DEV)
+    v_direct = K.gemm(cu(upb), cu(eye), hid, hid, _C.EPI_RELU_BWD, None, cu(logs), 3.0, y=y, dlogs=dl_direct,
+                      dbias=db_direct, out_dtype=_C.BF16)
+    v = K.gemm(cu(upb), cu(eye), hid, hid, _C.EPI_RELU_BWD, None, cu(logs), 3.0, y=y, dlogs=None, dbias=None,
+               out_dtype=_C.BF16)
+    assert torch.equal(v, v_direct)
+    dw = torch.zeros(hid, kp, device=DEV)
+    K.gemm_wgrad(v, a1, hid, kp, dw)
+    dbias = torch.full((hid,), 0.25, device=DEV); dlogs = torch.full((hid,), -0.5, device=DEV)   # accumulate into
+    bias_d = cu(bias)
+    job = np.array([(wb.data_ptr(), dw.data_ptr(), bias_d.data_ptr(), dw.data_ptr() + 4 * ones_col, dbias.data_ptr(),
+                     dlogs.data_ptr(), hid, kp, kp, kp, 3.0, kp)], dtype=rows_path._FJOB)
+    K.conv_actnorm_finish_batched(torch.from_numpy(job.view(np.uint8).copy()).to(DEV), 1, hid)
+    gm = torch.where(y.double().cpu() > 0, upb.double(), torch.zeros(1, dtype=torch.float64))
+    ref_db = (gm * s).sum(0)
+    ref_dl = 3.0 * (gm * y.double().cpu()).sum(0)
+    # the deferred sums run over the bf16-ROUNDED gradient v (and bf16 W, a1): bf16 tolerances
+    assert_close(dbias - 0.25, ref_db.float(), 1e-2, 5e-2, "deferred dbias")
+    assert_close(dlogs + 0.5, ref_dl.float(), 3e-2, 1e-1, "deferred dlogs")
+    assert_close(dbias - 0.25, db_direct, 1e-2, 5e-2, "deferred vs epilogue dbias")
+    assert_close(dlogs + 0.5, dl_direct, 3e-2, 1e-1, "deferred vs epilogue dlogs")
+
+
 @pytest.mark.parametrize("dtype,p,mo,no", [(_C.F32, 1000, 70, 50), (_C.BF16, 1000, 70, 50), (_C.BF16, 5000, 512, 512),
                                            (_C.BF16, 300, 128, 64), (_C.BF16, 20000, 448, 512),
                                            (_C.BF16, 64 * 1024, 512, 256)])
