@@ -129,7 +129,7 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 // per-CTA partials with a fixed-shape tree:
 //   ld_out[n] = ld_in[n] + sign*HW*(sum_c f*an_logs[c] + logabsdet[0]) + sum_b partial[n][b]
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restrict__ bias3,
                      const float* __restrict__ logs3, float f, float* __restrict__ z,
                      float* __restrict__ h_save, int C, int H, int W, FastDiv divW, FastDiv divCh, int ppb, int iters,
@@ -240,6 +240,30 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+// mbarrier + bulk (TMA engine, no tensor map) global -> shared copies: one instruction per contiguous run
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
 
 __global__ void __launch_bounds__(256)
@@ -645,6 +669,9 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
 // 20-25 % of the HBM roofline).  Here the rows [g0-W-1, g0+TP+W+1) of dA1 -- contiguous in global memory -- are
 // copied with 16-byte cp.async while x and dz are staged, and the taps are gathered from shared memory by
 // (pixel, channel pair) items, which also balances the work (the quad mapping left a third of the threads idle).
+// The window is filled by the TMA engine: one bulk copy per row (16 x ceil(9*Cin/4) bytes into a padded pitch),
+// completion counted on an mbarrier every thread arrives on (a per-16-byte cp.async loop cost ~25 % of the
+// kernel's instructions).
 // Further changes: compile-time channel count CT (12/24/48; 0 = run time) and a conflict-free shared-memory
 // combine of the register dW blocks instead of contended shared float atomics (CAS loops).
 // Element arithmetic and summation order of dx are those of rows_mix_bwd_kernel.
@@ -672,9 +699,15 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
   float* s_red = bs + C;                      // [2][C]
   int* sinv = reinterpret_cast<int*>(s_red + 2 * C);   // [C] inverse permutation (perm only)
   float* red = reinterpret_cast<float*>(sinv + C);      // [32] + [1]
+  __shared__ uint64_t s_bar;                  // window-copy barrier: 256 arrivals + the rows' bytes per tile
   const int tid = threadIdx.x;
   const bool has_an = bias != nullptr;
   const int HW = H * W;
+  if (tid == 0) {
+    mbar_init(&s_bar, 256);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t win_parity = 0;
   auto div_g = [&](int v) { return CT ? v / (CT ? CT / 4 : 1) : fdiv(v, divG); };
   for (int c = tid; c < C; c += 256) {
     sc[c] = has_an ? expf(logs[c] * f) : 1.f;
@@ -706,14 +739,14 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int g0 = tile * TP;
     const int wr0 = max(g0 - W - 1, 0), wr1 = min(g0 + TP + W + 1, NP);
-    // ---- (a) async copy of the dA1 window
+    // ---- (a) async copy of the dA1 window: thread r copies row wr0 + r (and r + 256, ...), everyone arrives once
     {
-      const float* src = dA1 + (int64_t)wr0 * ld_a1;
-      const int total = (wr1 - wr0) * vec;
-      for (int i = tid; i < total; i += 256) {
-        const int r = fdiv(i, divVec), v = i - r * vec;
-        cp_async16(win + r * wpitch + 4 * v, src + (int64_t)r * ld_a1 + 4 * v);
-      }
+      const int nrows = wr1 - wr0;
+      uint32_t my_bytes = 0;
+      for (int r = tid; r < nrows; r += 256) my_bytes += (uint32_t)vec * 16u;
+      if (my_bytes) mbar_arrive_expect_tx(&s_bar, my_bytes); else mbar_arrive(&s_bar);
+      for (int r = tid; r < nrows; r += 256)
+        bulk_g2s(win + r * wpitch, dA1 + (int64_t)(wr0 + r) * ld_a1, (uint32_t)vec * 16u, &s_bar);
     }
     // ---- (b) stage a = actnorm(x) and dz, one float4 of one pixel per thread and pass
     if (slot < ppb) {
@@ -732,7 +765,8 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
         *reinterpret_cast<float4*>(d_s + p * C + quad * 4) = dv;
       }
     }
-    cp_async_wait_all();
+    mbar_wait(&s_bar, win_parity);
+    win_parity ^= 1u;
     __syncthreads();
     // ---- (c) conv1 dgrad: dz[p][c] += sum_tap dA1[nbr(p, tap)][tap*Cin + c], c < Cin, taps in the order of
     // rows_mix_bwd_kernel; one (pixel, channel pair) item per thread and pass
@@ -1392,8 +1426,9 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
       if (win_floats < 4096) win_floats = 4096;                            // also the dW combine scratch (256 x 16)
       return sizeof(float) * ((size_t)win_floats + 2 * (size_t)tp * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
     };
+    static const size_t smem_cap = []() { const char* e = getenv("GLOWK_MIXBWD_SMEM_KB"); return (size_t)(e ? atoi(e) : 72) * 1024; }();
     int TPw = 128;                          // <= 72 KB per CTA (3 per SM); smaller tiles until every SM has two CTAs
-    while (TPw > 32 && (smem_for(TPw) > 72 * 1024 || ceil_div(NP, TPw) < 2 * sm_count())) TPw >>= 1;
+    while (TPw > 32 && (smem_for(TPw) > smem_cap || ceil_div(NP, TPw) < 2 * sm_count())) TPw >>= 1;
     const size_t smem_w = smem_for(TPw);
     if (smem_w <= 160 * 1024) {
       const int64_t tiles_w = ceil_div(NP, TPw);
