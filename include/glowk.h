@@ -269,6 +269,14 @@ int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const float* dA1
                                float logscale_factor, float* dx, float* dw, float* dlogs, float* dbias, int64_t N,
                                int64_t C, int64_t H, int64_t W, const float* dld, const float* winv, void* stream);
 
+/* Same with the element type of dA1 given (GLOWK_F32 or GLOWK_BF16): the bf16 training path lets the conv1 dgrad
+ * GEMM store dA1 in bf16 (half the bytes of that GEMM's output and of this kernel's gather; the nine taps are
+ * still summed in fp32).  A bf16 dA1 needs 16-byte aligned rows. */
+int glowk_rows_actnorm_mix_bwd_ex(const float* x, const float* dz, const void* dA1, int da1_dtype, int64_t ld_a1,
+                                  int64_t Cin, const float* w, const int64_t* idx, const float* bias, const float* logs,
+                                  float logscale_factor, float* dx, float* dw, float* dlogs, float* dbias, int64_t N,
+                                  int64_t C, int64_t H, int64_t W, const float* dld, const float* winv, void* stream);
+
 /* glowk_gaussian_logp on rows: x: [P][ldx], channels c0..c0+Cz; h: [P][ldh] or null (N(0,I)). */
 int glowk_rows_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t ldx, int64_t N, int64_t HW,
                              int64_t c0, int64_t Cz, const float* logdet_in, float* logdet_out, void* stream);

@@ -676,9 +676,9 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
 // combine of the register dW blocks instead of contended shared float atomics (CAS loops).
 // Element arithmetic and summation order of dx are those of rows_mix_bwd_kernel.
 // ------------------------------------------------------------------------------------------
-template <bool PERM, int RMB_MAXIT, int CT>
+template <bool PERM, int RMB_MAXIT, int CT, typename TA>
 __global__ void __launch_bounds__(256, RMB_MAXIT == 1 ? 3 : 1)
-rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ dz, const float* __restrict__ dA1,
+rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ dz, const TA* __restrict__ dA1,
                         int ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
                         const float* __restrict__ bias, const float* __restrict__ logs, float f,
                         float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ dlogs,
@@ -690,7 +690,8 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
   const int C = CT ? CT : C_rt;
   const int G = C >> 2;
   extern __shared__ __align__(16) float smem[];
-  float* win = smem;                          // [TP + 2W + 2][wpitch] dA1 rows; later the dW combine scratch
+  float* win = smem;                          // [TP + 2W + 2][wpitch] dA1 rows (TA); later the dW combine scratch
+  TA* wina = reinterpret_cast<TA*>(smem);     // wpitch is in TA elements (a multiple of 16 bytes)
   float* ws = win + win_floats;               // [C][C]    W (mix only)
   float* a_s = ws + (PERM ? 0 : C * C);       // [TP][C]   a = actnorm(x)
   float* d_s = a_s + TP * C;                  // [TP][C]   dz, later da
@@ -732,7 +733,7 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
   const int chunks = 256 / C;
   const int red_ch = tid / C, red_i = tid - red_ch * C;
   float sg_acc = 0.f, sga_acc = 0.f;
-  const int vec = (int)divVec.d;              // float4 per dA1 row that hold its 9*Cin columns
+  const int vec = (int)divVec.d;              // 16-byte pieces per dA1 row that hold its 9*Cin columns
   const int npair = Cin >> 1;
 
   const int ntiles = (NP + TP - 1) / TP;
@@ -746,7 +747,7 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
       for (int r = tid; r < nrows; r += 256) my_bytes += (uint32_t)vec * 16u;
       if (my_bytes) mbar_arrive_expect_tx(&s_bar, my_bytes); else mbar_arrive(&s_bar);
       for (int r = tid; r < nrows; r += 256)
-        bulk_g2s(win + r * wpitch, dA1 + (int64_t)(wr0 + r) * ld_a1, (uint32_t)vec * 16u, &s_bar);
+        bulk_g2s(wina + r * wpitch, dA1 + (int64_t)(wr0 + r) * ld_a1, (uint32_t)vec * 16u, &s_bar);
     }
     // ---- (b) stage a = actnorm(x) and dz, one float4 of one pixel per thread and pass
     if (slot < ppb) {
@@ -780,7 +781,7 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
           const int q = pix - n * HW;
           const int yy = fdiv(q, divW), xx = q - yy * W;
           const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
-          const float* ap = win + (pix - wr0) * wpitch + 2 * j;
+          const TA* ap = wina + (pix - wr0) * wpitch + 2 * j;
           float r0 = 0.f, r1 = 0.f;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
@@ -788,7 +789,9 @@ rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ d
             const int dy = tap / 3 - 1, dxx = tap % 3 - 1;
             const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dxx < 0 ? lf : (dxx > 0 ? rt : true));
             if (ok) {
-              const float2 v0 = *reinterpret_cast<const float2*>(ap + (dy * W + dxx) * wpitch + t * Cin);
+              float2 v0;
+              if (sizeof(TA) == 4) v0 = *reinterpret_cast<const float2*>(ap + (dy * W + dxx) * wpitch + t * Cin);
+              else v0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ap + (dy * W + dxx) * wpitch + t * Cin));
               r0 += v0.x; r1 += v0.y;
             }
           }
@@ -1395,6 +1398,18 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
                                           const float* logs, float logscale_factor, float* dx, float* dw,
                                           float* dlogs, float* dbias, int64_t N, int64_t C, int64_t H, int64_t W,
                                           const float* dld, const float* winv, void* stream) {
+  return glowk_rows_actnorm_mix_bwd_ex(x, dz, dA1, GLOWK_F32, ld_a1, Cin, w, idx, bias, logs, logscale_factor, dx, dw,
+                                       dlogs, dbias, N, C, H, W, dld, winv, stream);
+}
+
+extern "C" int glowk_rows_actnorm_mix_bwd_ex(const float* x, const float* dz, const void* dA1v, int da1_dtype,
+                                             int64_t ld_a1, int64_t Cin, const float* w, const int64_t* idx,
+                                             const float* bias, const float* logs, float logscale_factor, float* dx,
+                                             float* dw, float* dlogs, float* dbias, int64_t N, int64_t C, int64_t H,
+                                             int64_t W, const float* dld, const float* winv, void* stream) {
+  const float* dA1 = (const float*)dA1v;
+  GLOWK_CHECK_ARG(da1_dtype == GLOWK_F32 || da1_dtype == GLOWK_BF16, "glowk_rows_actnorm_mix_bwd: bad da1_dtype");
+  const bool a_bf16 = dA1v && da1_dtype == GLOWK_BF16;
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(x && dz && dx, "glowk_rows_actnorm_mix_bwd: null pointer");
   GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_rows_actnorm_mix_bwd: exactly one of w / idx");
@@ -1418,11 +1433,16 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
   const bool big = (C / 4) * (C / 4) > 256;
   // (a) conv1-dgrad operand staged through a shared-memory window (see rows_mix_bwd_win_kernel)
   static const bool no_win = getenv("GLOWK_MIXBWD_NOWIN") != nullptr;        // A/B switch for profiling
-  if (dA1 && !no_win && ld_a1 % 4 == 0 && (((uintptr_t)dA1) & 15) == 0) {
-    const int vec = (int)((9 * Cin + 3) / 4), wpitch = 4 * vec + 4;
+  const int esz = a_bf16 ? 2 : 4;
+  if (dA1 && (!no_win || a_bf16) && (ld_a1 * esz) % 16 == 0 && (((uintptr_t)dA1) & 15) == 0) {
+    // window rows: `vec` 16-byte pieces of data, pitch an ODD number of 16-byte units (rows of neighbouring pixels
+    // then start 4 banks apart instead of 0 / 16)
+    const int vec = (int)((9 * Cin * esz + 15) / 16);
+    const int pitch16 = (vec + 1) | 1;
+    const int wpitch = pitch16 * 16 / esz;                                     // in dA1 elements
     int win_floats = 0;
     auto smem_for = [&](int tp) {
-      win_floats = (int)((tp + 2 * W + 2) * wpitch);
+      win_floats = (int)((tp + 2 * W + 2) * pitch16 * 4);
       if (win_floats < 4096) win_floats = 4096;                            // also the dW combine scratch (256 x 16)
       return sizeof(float) * ((size_t)win_floats + 2 * (size_t)tp * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
     };
@@ -1433,15 +1453,19 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
     if (smem_w <= 160 * 1024) {
       const int64_t tiles_w = ceil_div(NP, TPw);
       const FastDiv dVec = make_fastdiv(vec), dPair = make_fastdiv(Cin / 2);
-#define GLOWK_RMBW_LAUNCH(PERM_, IT_, CT_)                                                                               \
+#define GLOWK_RMBW_LAUNCH_T(PERM_, IT_, CT_, TA_)                                                                        \
   do {                                                                                                                   \
-    auto kern = rows_mix_bwd_win_kernel<PERM_, IT_, CT_>;                                                                \
+    auto kern = rows_mix_bwd_win_kernel<PERM_, IT_, CT_, TA_>;                                                           \
     GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));                     \
     const int64_t cap = resident_ctas((const void*)kern, 256, smem_w);                                                   \
     const unsigned grid = (unsigned)(tiles_w < cap ? tiles_w : cap);                                                     \
-    GLOWK_CUDA(launch_pdl(kern, grid, 256, smem_w, st, x, dz, dA1, (int)ld_a1, (int)Cin, w, idx, bias, logs,             \
-                          logscale_factor, dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG, dVec,    \
-                          dPair, TPw, wpitch, win_floats, dld, (int)N, winv));                                           \
+    GLOWK_CUDA(launch_pdl(kern, grid, 256, smem_w, st, x, dz, (const TA_*)dA1v, (int)ld_a1, (int)Cin, w, idx, bias,      \
+                          logs, logscale_factor, dx, dw, dlogs, dbias, (int)NP, (int)C, (int)H, (int)W, dW_, dHW, dG,    \
+                          dVec, dPair, TPw, wpitch, win_floats, dld, (int)N, winv));                                     \
+  } while (0)
+#define GLOWK_RMBW_LAUNCH(PERM_, IT_, CT_)                                                                               \
+  do {                                                                                                                   \
+    if (a_bf16) GLOWK_RMBW_LAUNCH_T(PERM_, IT_, CT_, __nv_bfloat16); else GLOWK_RMBW_LAUNCH_T(PERM_, IT_, CT_, float);   \
   } while (0)
       if (!w) { if (big) GLOWK_RMBW_LAUNCH(true, 3, 0); else GLOWK_RMBW_LAUNCH(true, 1, 0); }
       else if (big) GLOWK_RMBW_LAUNCH(false, 3, 0);
@@ -1450,11 +1474,13 @@ extern "C" int glowk_rows_actnorm_mix_bwd(const float* x, const float* dz, const
       else if (C == 48) GLOWK_RMBW_LAUNCH(false, 1, 48);
       else GLOWK_RMBW_LAUNCH(false, 1, 0);
 #undef GLOWK_RMBW_LAUNCH
+#undef GLOWK_RMBW_LAUNCH_T
       GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix_bwd(window)");
       return GLOWK_OK;
     }
   }
-  // (b) direct-gather kernel
+  // (b) direct-gather kernel (fp32 operand only)
+  if (a_bf16) return fail(GLOWK_EUNSUP, "glowk_rows_actnorm_mix_bwd: a bf16 conv1-dgrad operand needs the shared-memory window path (16-byte aligned rows, window <= 160 KB)");
 #define GLOWK_RMB_LAUNCH(PERM_, IT_)                                                                                     \
   do {                                                                                                                   \
     auto kern = rows_mix_bwd_kernel<PERM_, IT_>;                                                                         \

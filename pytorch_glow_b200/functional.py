@@ -393,7 +393,8 @@ def rows_actnorm_mix_bwd(x, dz, n, h, w, da1=None, cin=0, weight=None, indices=N
     check_cuda(x, dz, da1, weight, indices, bias, logs, dw, dlogs, dbias, dld, winv)
     c = x.shape[1]
     dx = torch.empty_like(x)
-    call("glowk_rows_actnorm_mix_bwd", ptr(x), ptr(dz), ptr(da1), 0 if da1 is None else da1.shape[1], int(cin),
+    adt = BF16 if (da1 is not None and da1.dtype == torch.bfloat16) else F32
+    call("glowk_rows_actnorm_mix_bwd_ex", ptr(x), ptr(dz), ptr(da1), adt, 0 if da1 is None else da1.shape[1], int(cin),
          ptr(weight), ptr(indices), ptr(bias), ptr(logs), float(logscale_factor), ptr(dx), ptr(dw), ptr(dlogs),
          ptr(dbias), n, c, h, w, ptr(dld), ptr(winv))
     return dx

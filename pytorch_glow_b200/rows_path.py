@@ -320,7 +320,9 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     if defer:
         plan.defer_dlogs(net.packed("w2", dt), dw2, an2, db2, hid, hid)
         plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
-    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32)
+    # bf16 path: the nine-tap partial gradients are stored in bf16 (they are products of bf16 operands already) and
+    # summed in fp32 by the mix adjoint
+    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=dt)
     # (5) ActNorm + mix
     dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition
     gw = _gbuf(step.invconv.weight) if dense else None

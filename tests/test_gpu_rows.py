@@ -215,6 +215,22 @@ def test_rows_mix_bwd_matches_nchw(shape, mode, with_da1):
     assert_close(dl2, dl_ref, 1e-4, 2e-4, "dlogs + logdet term")
     if mode == "mix":
         assert_close(dw2, dw_ref, 1e-4, 2e-4, "dW + logdet term")
+    # bf16 conv1-dgrad operand (the tcgen05 training path): taps widen exactly to fp32 and are summed in the same
+    # order, so the result is bit-identical to feeding the same values as fp32
+    if with_da1:
+        da1_b = da1.bfloat16()
+        outs = []
+        for operand in (da1_b, da1_b.float()):
+            dwb = torch.zeros(c * c, device=DEV) if mode == "mix" else None
+            dlb, dbb = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+            dxb = K.rows_actnorm_mix_bwd(to_rows(x), to_rows(dz), n, h, w, da1=operand, cin=cin, weight=wgt, indices=idx,
+                                         bias=bias, logs=logs, dw=dwb, dlogs=dlb, dbias=dbb)
+            outs.append((dxb, dlb, dbb, dwb))
+        assert torch.equal(outs[0][0], outs[1][0])
+        assert_close(outs[0][1], outs[1][1], 1e-5, 1e-5, "dlogs bf16 operand")
+        assert_close(outs[0][2], outs[1][2], 1e-5, 1e-5, "dbias bf16 operand")
+        if mode == "mix":
+            assert_close(outs[0][3], outs[1][3], 1e-5, 1e-5, "dW bf16 operand")
 
 
 # ---------------------------------------------------------------- Split2d pieces
