@@ -227,10 +227,11 @@ def test_rows_mix_bwd_matches_nchw(shape, mode, with_da1):
                                          bias=bias, logs=logs, dw=dwb, dlogs=dlb, dbias=dbb)
             outs.append((dxb, dlb, dbb, dwb))
         assert torch.equal(outs[0][0], outs[1][0])
-        assert_close(outs[0][1], outs[1][1], 1e-5, 1e-5, "dlogs bf16 operand")
-        assert_close(outs[0][2], outs[1][2], 1e-5, 1e-5, "dbias bf16 operand")
+        # (the channel / weight reductions are atomic: their summation order differs from launch to launch)
+        assert_close(outs[0][1], outs[1][1], 1e-4, 5e-4, "dlogs bf16 operand")
+        assert_close(outs[0][2], outs[1][2], 1e-4, 5e-4, "dbias bf16 operand")
         if mode == "mix":
-            assert_close(outs[0][3], outs[1][3], 1e-5, 1e-5, "dW bf16 operand")
+            assert_close(outs[0][3], outs[1][3], 1e-4, 5e-4, "dW bf16 operand")
 
 
 # ---------------------------------------------------------------- Split2d pieces
