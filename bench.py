@@ -31,7 +31,7 @@ WORKLOADS = {
     "celeba64": ((64, 64, 3), 32, 3, 512, "affine", 512, 32.06),
     "cifar32": ((32, 32, 3), 32, 3, 512, "affine", 256, 8.02),
     "cifar32_additive": ((32, 32, 3), 32, 3, 512, "additive", 256, 7.22),
-    "celebahq256": ((256, 256, 3), 32, 6, 512, "affine", 8, 537.6),
+    "celebahq256": ((256, 256, 3), 32, 6, 512, "affine", 32, 537.6),
     "tiny": ((32, 32, 3), 4, 3, 64, "affine", 16, None),
 }
 

@@ -160,7 +160,17 @@ class FlowEncodeFunction(torch.autograd.Function):
             ctx.tape = tape
             ctx.has_ld = ld is not None
             return z if ld is None else (z, ld)
-        for layer in flow.layers:
+        # hybrid: the leading levels on the pixel-major kernels, the wide tail (C > 96) on the per-layer NCHW kernels
+        ctx.head = None
+        tail = flow.layers
+        hd = rows_path.head(flow, z) if config.use_rows_path else None
+        if hd is not None:
+            view, k = hd
+            head_tape = []
+            z, ld = rows_path.encode(view, z, ld, head_tape)
+            ctx.head = (view, head_tape)
+            tail = list(flow.layers)[k:]
+        for layer in tail:
             if isinstance(layer, Squeeze2d):
                 z = K.squeeze2d(z, layer.factor, reverse=False)
                 tape.append((layer, None))
@@ -200,6 +210,10 @@ class FlowEncodeFunction(torch.autograd.Function):
             elif isinstance(layer, Split2d):
                 dz = split2d_backward(layer, c, dz, dld)
         ctx.tape = None
+        if ctx.head is not None:
+            view, head_tape = ctx.head
+            dz = rows_path.backward(view, head_tape, dz.contiguous(), dld)
+            ctx.head = None
         return (None, dz, dld) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 

@@ -276,8 +276,10 @@ __global__ void logdet_param_grad_kernel(const float* __restrict__ dld, int64_t 
   if (threadIdx.x == 0) s_g = tot;
   __syncthreads();
   const float G = s_g * hw;
-  if (dlogs) for (int c = threadIdx.x; c < C; c += blockDim.x) dlogs[c] += f * G;
-  if (dw) for (int e = threadIdx.x; e < C * C; e += blockDim.x) {
+  // every CTA re-derives G (N floats) and owns a slice of dW; CTA 0 also updates dlogs.  (One CTA for the whole
+  // C x C transpose-add took 180 us per call at C = 384.)
+  if (dlogs && blockIdx.x == 0) for (int c = threadIdx.x; c < C; c += blockDim.x) dlogs[c] += f * G;
+  if (dw) for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C * C; e += gridDim.x * blockDim.x) {
     const int o = e / C, i = e - o * C;
     dw[e] += G * winv[i * C + o];
   }
@@ -443,7 +445,8 @@ extern "C" int glowk_actnorm_mix_bwd(const float* x, const float* dz, const floa
 extern "C" int glowk_logdet_param_grad(const float* dld, int64_t N, int64_t HW, float logscale_factor, float* dlogs,
                                        int64_t C, const float* winv, float* dw, void* stream) {
   GLOWK_CHECK_ARG(dld && (dlogs || dw) && (!dw || winv), "glowk_logdet_param_grad: null pointer");
-  logdet_param_grad_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dld, N, (float)HW, logscale_factor, dlogs, (int)C, winv, dw);
+  const unsigned ctas = dw ? (unsigned)ceil_div(C * C, 1024) : 1u;
+  logdet_param_grad_kernel<<<ctas < 1 ? 1 : (ctas > 296 ? 296 : ctas), 256, 0, (cudaStream_t)stream>>>(dld, N, (float)HW, logscale_factor, dlogs, (int)C, winv, dw);
   GLOWK_CHECK_LAUNCH("glowk_logdet_param_grad");
   return GLOWK_OK;
 }

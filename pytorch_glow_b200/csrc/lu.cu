@@ -94,6 +94,61 @@ __global__ void invconv_prepare_kernel(const float* __restrict__ w, int C, float
   }
 }
 
+// ---- large matrices (fp64 workspace in global memory: C > 96 with the inverse, the CelebA-HQ levels 5 / 6) ----
+// ncu launch list of the 256^2 L=6 model: the one-CTA kernel above took 7.5 ms per launch (45 ms of a 215 ms step):
+// 256 threads per matrix, and one thread per inverse column walking 2 x C^2/2 dependent fp64 FMAs.  Here the
+// factorisation runs with 1024 threads per matrix and the inverse is a second kernel with ONE WARP PER COLUMN
+// (lanes split each row's dot product; the 8 warps of a CTA walk the same rows of LU, which they share through L1).
+__global__ void __launch_bounds__(1024)
+invconv_lu_big_kernel(const float* __restrict__ w, int C, float* __restrict__ logabsdet_out, double* gwork, int* gperm) {
+  const size_t mat = blockIdx.x;
+  double* A = gwork + mat * (size_t)C * C;
+  int* perm = gperm + mat * (size_t)C;
+  w += mat * (size_t)C * C;
+  for (int e = threadIdx.x; e < C * C; e += blockDim.x) A[e] = (double)w[e];
+  __syncthreads();
+  double logabs;
+  lu_factor_inplace(A, perm, C, &logabs);
+  if (threadIdx.x == 0) logabsdet_out[mat] = (float)logabs;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+invconv_inverse_big_kernel(const double* __restrict__ gwork, const int* __restrict__ gperm, int C,
+                           float* __restrict__ winv_out) {
+  extern __shared__ __align__(16) unsigned char lu_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;                       // column of W^-1: solve L U x = P e_j
+  if (j >= C) return;
+  const size_t mat = blockIdx.y;
+  const double* A = gwork + mat * (size_t)C * C;
+  const int* perm = gperm + mat * (size_t)C;
+  double* x = reinterpret_cast<double*>(lu_smem) + (size_t)warp * C;
+  for (int i = 0; i < C; ++i) {                              // L y = P e_j (unit lower triangle)
+    const double* row = A + (size_t)i * C;
+    double s = 0.0;
+    for (int k = lane; k < i; k += 32) s += row[k] * x[k];
+    s = warp_sum_f64(s);
+    if (lane == 0) x[i] = ((perm[i] == j) ? 1.0 : 0.0) - s;
+    __syncwarp();
+  }
+  for (int i = C - 1; i >= 0; --i) {                         // U x = y
+    const double* row = A + (size_t)i * C;
+    double s = 0.0;
+    for (int k = i + 1 + lane; k < C; k += 32) s += row[k] * x[k];
+    s = warp_sum_f64(s);
+    if (lane == 0) x[i] = (x[i] - s) / row[i];
+    __syncwarp();
+  }
+  float* out = winv_out + mat * (size_t)C * C;
+  for (int i = lane; i < C; i += 32) out[(size_t)i * C + j] = (float)x[i];
+}
+
 __global__ void lu_assemble_kernel(const float* __restrict__ p, const float* __restrict__ l,
                                    const float* __restrict__ u, const float* __restrict__ sign_s,
                                    const float* __restrict__ log_s, int C, float* __restrict__ w_out,
@@ -159,8 +214,24 @@ extern "C" int glowk_invconv_prepare_batched(const float* w, int64_t batch, int6
   size_t smem = mats * (size_t)C * C * sizeof(double) + (size_t)C * sizeof(int);
   double* gwork = nullptr;
   if (smem > 200 * 1024) {
-    GLOWK_CUDA(cudaMallocAsync((void**)&gwork, (size_t)batch * 2 * (size_t)C * C * sizeof(double), st));
-    smem = (size_t)C * sizeof(int);
+    // two kernels over a global fp64 workspace: [batch][C][C] LU factors followed by [batch][C] pivots
+    const size_t work = (size_t)batch * C * C * sizeof(double), all = work + (size_t)batch * C * sizeof(int);
+    GLOWK_CUDA(cudaMallocAsync((void**)&gwork, all, st));
+    int* gperm = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(gwork) + work);
+    invconv_lu_big_kernel<<<(unsigned)batch, 1024, 0, st>>>(w, (int)C, logabsdet_out, gwork, gperm);
+    cudaError_t e1 = cudaGetLastError();
+    if (e1 == cudaSuccess && winv_out) {
+      const size_t xs = 8 * (size_t)C * sizeof(double);
+      if (xs > 48 * 1024)
+        e1 = cudaFuncSetAttribute(invconv_inverse_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs);
+      if (e1 == cudaSuccess) {
+        invconv_inverse_big_kernel<<<dim3((unsigned)ceil_div(C, 8), (unsigned)batch), 256, xs, st>>>(gwork, gperm, (int)C, winv_out);
+        e1 = cudaGetLastError();
+      }
+    }
+    cudaFreeAsync(gwork, st);
+    if (e1 != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_invconv_prepare: %s", cudaGetErrorString(e1));
+    return GLOWK_OK;
   }
   if (smem > 48 * 1024)
     GLOWK_CUDA(cudaFuncSetAttribute(invconv_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

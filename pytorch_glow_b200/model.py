@@ -184,7 +184,13 @@ class FlowModel(nn.Module):
         if config.use_rows_path and vector_ld and rows_path.supported(self, z):
             ld = None if logdet is None else logdet.to(torch.float32).contiguous()
             return rows_path.encode(self, z, ld)              # pixel-major flow state (rows_path.py)
-        for layer in self.layers:
+        tail = self.layers
+        hd = rows_path.head(self, z) if (config.use_rows_path and vector_ld) else None
+        if hd is not None:                                    # wide tail levels (C > 96): per-layer NCHW kernels
+            ld = None if logdet is None else logdet.to(torch.float32).contiguous()
+            z, logdet = rows_path.encode(hd[0], z, ld)
+            tail = list(self.layers)[hd[1]:]
+        for layer in tail:
             z, logdet = layer(z, logdet, reverse=False)
         return z, logdet
 
@@ -196,13 +202,31 @@ class FlowModel(nn.Module):
         if config.use_rows_path and rows_path.supported(self, z):
             with torch.no_grad():
                 return rows_path.decode(self, z, eps_std, eps_list)
-        for layer in reversed(self.layers):
+        tail = list(self.layers)
+        hd = None
+        if config.use_rows_path and z.is_cuda:
+            kh = rows_path._prefix_len(self)
+            if 0 < kh < len(tail) and isinstance(tail[kh - 1], module.Split2d):
+                hd, tail = kh, tail[kh:]
+        for layer in reversed(tail):
             if isinstance(layer, module.Split2d):
                 e = None if eps_list is None else eps_list[k]
                 k += 1
                 z, logdet = layer(z, logdet=0., reverse=True, eps_std=eps_std, eps=e)
             else:
                 z, logdet = layer(z, logdet=0., reverse=True)
+        if hd is not None:                                    # the leading levels on the pixel-major kernels
+            view = rows_path.head(self, z)
+            if view is not None:
+                with torch.no_grad():
+                    return rows_path.decode(view[0], z, eps_std, None if eps_list is None else eps_list[k:])
+            for layer in reversed(list(self.layers)[:hd]):    # (tensor not eligible: finish on the NCHW kernels)
+                if isinstance(layer, module.Split2d):
+                    e = None if eps_list is None else eps_list[k]
+                    k += 1
+                    z, logdet = layer(z, logdet=0., reverse=True, eps_std=eps_std, eps=e)
+                else:
+                    z, logdet = layer(z, logdet=0., reverse=True)
         return z
 
     def forward(self, z, logdet=0., eps_std=None, reverse=False):

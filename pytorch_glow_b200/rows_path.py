@@ -62,6 +62,54 @@ def supported(flow, z):
     return True
 
 
+class _FlowView:
+    """The leading levels of a FlowModel as a flow of their own (same layer objects; own plan / workspace caches)."""
+
+    def __init__(self, layers):
+        self.layers = layers
+
+
+def _prefix_len(flow):
+    """Number of leading layers that form whole levels (Squeeze2d, FlowStep x K [, Split2d]) the rows kernels run:
+    channel counts a multiple of 4 and <= glowk_rows_max_channels()."""
+    from .model import FlowStep
+    cmax = K.rows_max_channels()
+    layers = list(flow.layers)
+    i = good = 0
+    while i < len(layers) and isinstance(layers[i], module.Squeeze2d):
+        j = i + 1
+        while j < len(layers) and isinstance(layers[j], FlowStep) and layers[j].in_channels % 4 == 0 \
+                and layers[j].in_channels <= cmax:
+            j += 1
+        if j == i + 1 or (j < len(layers) and isinstance(layers[j], FlowStep)):
+            break                                   # no step, or a step the kernels cannot run
+        if j < len(layers) and isinstance(layers[j], module.Split2d):
+            if layers[j].num_channels % 4 or layers[j].num_channels > cmax:
+                break
+            j += 1
+        elif j < len(layers):
+            break
+        good = i = j
+    return good
+
+
+def head(flow, z):
+    """(view, k) if only the first k layers (whole levels, ending in a Split2d) can run on the rows kernels --
+    the CelebA-HQ shape family, whose levels 5 and 6 have 192 / 384 channels -- else None.  FlowModel.encode /
+    decode and the autograd node then run the head on the pixel-major path and the tail on the per-layer NCHW
+    kernels; the hand-over tensor is the NCHW z1 of the head's last Split2d."""
+    if not (torch.is_tensor(z) and z.is_cuda and z.dtype == torch.float32 and z.dim() == 4 and 0 < z.shape[0] <= 65535):
+        return None
+    k = _prefix_len(flow)
+    if k <= 0 or k >= len(flow.layers) or not isinstance(flow.layers[k - 1], module.Split2d):
+        return None
+    cache = flow.__dict__.setdefault("_rows_head", {})
+    view = cache.get(k)
+    if view is None:
+        view = cache[k] = _FlowView(list(flow.layers)[:k])
+    return view, k
+
+
 # ------------------------------------------------------------------ per-model device workspaces
 class _Workspace:
     """Deterministic-reduction scratch of glowk_rows_coupling (tickets stay zero between launches)."""
@@ -441,8 +489,11 @@ def backward(flow, tape, dz, dld):
     dev = dz.device
     plan = grad_plan(flow, dev)
     plan.begin()
-    cur = torch.empty(n * h * w, c, device=dev, dtype=torch.float32)
-    K.rows_squeeze(dz, NCHW, c * h * w, cur, ROWS, c, n, c, h, w, 1, False)
+    # a flow that ends in a Split2d (the head of a hybrid model) returned z1 only: dz fills the first half of the
+    # [P][2c] gradient rows, the Split2d adjoint writes the second half
+    pitch = 2 * c if (tape and tape[-1][0] == "split") else c
+    cur = torch.empty(n * h * w, pitch, device=dev, dtype=torch.float32)
+    K.rows_squeeze(dz, NCHW, c * h * w, cur, ROWS, pitch, n, c, h, w, 1, False)
     for kind, layer, ctx in reversed(tape):
         if kind == "step":
             cur = _step_backward(layer, ctx, cur, dld, n, c, h, w, plan)

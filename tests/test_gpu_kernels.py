@@ -54,7 +54,7 @@ def test_actnorm_init(shape, scale):
 
 
 # ---------------------------------------------------------------- 1x1 conv weight prep
-@pytest.mark.parametrize("c", [2, 6, 12, 24, 48, 96, 130])
+@pytest.mark.parametrize("c", [2, 6, 12, 24, 48, 96, 130, 192, 384])
 def test_invconv_prepare(c):
     np.random.seed(c)
     w = O.invconv_init_weight(c) + 0.1 * torch.randn(c, c, generator=g(c))

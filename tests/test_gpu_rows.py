@@ -407,6 +407,52 @@ def test_flowmodel_rows_gradients_equal_nchw_path(perm, coup):
     print("rows vs NCHW parameter gradients: worst rel err %.2e over %d tensors" % (worst, len(g_n)))
 
 
+def test_hybrid_rows_head_and_nchw_tail_match_the_pure_nchw_path():
+    """L=5 (12 ... 192 channels): levels 1-4 run on the pixel-major kernels, level 5 on the per-layer NCHW kernels;
+    encode and every gradient (randomised weights) and decode with supplied noise (fresh weights: zero-initialised
+    couplings keep the inverse of mismatched latents bounded) equal the all-NCHW path."""
+    flow = _flow("invconv", "affine", K_=2, L=5, hidden=32, shape=(32, 32, 3), seed=3).train()
+    flow.set_conv_dtype("fp32")
+    x = cu(torch.rand(3, 3, 32, 32, generator=g(80)))
+    hd = rows_path.head(flow, x)
+    assert hd is not None and not rows_path.supported(flow, x)
+    k = hd[1]
+    assert isinstance(flow.layers[k - 1], G.Split2d) and flow.layers[k + 1].in_channels == 192
+    np.random.seed(4); torch.manual_seed(4)
+    fresh = G.FlowModel((32, 32, 3), 32, K=2, L=5, permutation="invconv", coupling="affine")
+    for m in fresh.modules():
+        if isinstance(m, G.ActNorm):
+            m.bias_inited = m.logs_inited = True
+    fresh = fresh.to(DEV).eval()
+    fresh.set_conv_dtype("fp32")
+    eps, c, hh = [], 3, 32
+    for lvl in range(4):
+        c, hh = c * 4, hh // 2
+        eps.append(cu(torch.randn(3, c // 2, hh, hh, generator=g(90 + lvl))))
+        c //= 2
+    eps = eps[::-1]                                                          # deepest split first
+    res = {}
+    for use_rows in (True, False):
+        config.use_rows_path = use_rows
+        try:
+            flow.zero_grad(set_to_none=True)
+            z, ld = flow(x, torch.zeros(3, device=DEV))
+            (z.square().sum() + 0.01 * ld.sum()).backward()
+            grads = {n_: p_.grad.clone() for n_, p_ in flow.named_parameters()}
+            with torch.no_grad():
+                z0, ld0 = flow(x, torch.zeros(3, device=DEV))
+                zf, _ = fresh(x, torch.zeros(3, device=DEV))
+                xr = fresh.decode(zf.clone(), eps_std=1.0, eps_list=eps)
+            res[use_rows] = (z.detach(), ld.detach(), grads, z0, xr)
+        finally:
+            config.use_rows_path = True
+    a, b = res[True], res[False]
+    assert rel_err(a[0], b[0]) < 1e-5 and rel_err(a[1], b[1]) < 1e-5 and rel_err(a[3], b[3]) < 1e-5
+    assert bool(torch.isfinite(b[4]).all()) and rel_err(a[4], b[4]) < 1e-5
+    for n_ in a[2]:
+        assert rel_err(a[2][n_], b[2][n_]) < 2e-4, n_
+
+
 def test_rows_path_falls_back_for_wide_levels():
     flow = G.FlowModel((16, 16, 3), 32, K=1, L=4)          # last level has 3*4*8 = 96 ... 192 channels
     assert max(l.in_channels for l in flow.layers if isinstance(l, G.FlowStep)) == 96
