@@ -277,6 +277,16 @@ int glowk_rows_actnorm_mix_bwd_ex(const float* x, const float* dz, const void* d
                                   float logscale_factor, float* dx, float* dw, float* dlogs, float* dbias, int64_t N,
                                   int64_t C, int64_t H, int64_t W, const float* dld, const float* winv, void* stream);
 
+/* Largest channel count of the rows coupling / Split2d kernels (384: levels 5-6 of the 256x256 L=6 model).  Above
+ * glowk_rows_max_channels() (96) the ActNorm + 1x1 conv pair of a FlowStep runs as glowk_actnorm on the rows
+ * (HW = 1) + glowk_gemm (fp32), and its adjoint as glowk_rows_tapsum + glowk_gemm / glowk_gemm_wgrad +
+ * glowk_rows_actnorm_bwd + glowk_logdet_param_grad. */
+int glowk_rows_max_channels_wide(void);
+/* ActNorm adjoint on rows (module.py:34-84): dx = da*s, dbias += sum_p da*s, dlogs += f*sum_p da*(x+bias)*s with
+ * s = exp(f*logs); da, x, dx: [P][C] (dx may alias da). */
+int glowk_rows_actnorm_bwd(const float* da, const float* x, const float* bias, const float* logs, float logscale_factor,
+                           float* dx, float* dlogs, float* dbias, int64_t P, int64_t C, void* stream);
+
 /* glowk_gaussian_logp on rows: x: [P][ldx], channels c0..c0+Cz; h: [P][ldh] or null (N(0,I)). */
 int glowk_rows_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t ldx, int64_t N, int64_t HW,
                              int64_t c0, int64_t Cz, const float* logdet_in, float* logdet_out, void* stream);

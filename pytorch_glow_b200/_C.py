@@ -66,6 +66,8 @@ SIGNATURES = {
                                    _i64, _p, _p, _p],
     "glowk_rows_actnorm_mix_bwd_ex": [_p, _p, _p, _i32, _i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _i64, _i64,
                                       _i64, _i64, _p, _p, _p],
+    "glowk_rows_max_channels_wide": [],
+    "glowk_rows_actnorm_bwd": [_p, _p, _p, _p, _f32, _p, _p, _p, _i64, _i64, _p],
     "glowk_rows_gaussian_logp": [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p],
     "glowk_rows_split2d_sample": [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _p],
     "glowk_rows_split2d_bwd": [_p, _p, _i64, _p, _p, _f32, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _p],

@@ -11,7 +11,11 @@
 
 namespace glowk {
 
-constexpr int ROWS_MAX_C = 96;   // shared-memory tiles below are sized for C <= 96 (levels 1..4 of every config)
+constexpr int ROWS_MAX_C = 96;   // shared-memory tiles of the mix kernels are sized for C <= 96 (levels 1..4 of every config)
+// The coupling / Split2d kernels (no C x C weight in shared memory) run up to 384 channels -- levels 5 and 6 of the
+// 256x256 L=6 configuration -- where ActNorm + the 1x1 conv and their adjoint are done by the fp32 GEMMs instead
+// (rows_path.py: _mix_wide_*; glowk_rows_actnorm_bwd below).
+constexpr int ROWS_MAX_C_WIDE = 384;
 
 // ------------------------------------------------------------------------------------------
 // ActNorm + channel mix / permutation (model.py:94-103 fwd, 142-152 rev).
@@ -140,7 +144,7 @@ rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restr
   pdl_trigger();
   pdl_wait();
   __shared__ float red[32];
-  __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
+  __shared__ float s_b[ROWS_MAX_C_WIDE], s_e[ROWS_MAX_C_WIDE];
   __shared__ int s_last;
   const int HW = H * W, Ch = C >> 1, Cout = affine ? C : Ch;
   const int n = blockIdx.y;
@@ -278,7 +282,7 @@ rows_coupling_win_kernel(const float* __restrict__ P3, int ldp, const float* __r
   pdl_wait();
   extern __shared__ __align__(16) float win[];
   __shared__ float red[32];
-  __shared__ float s_b[2 * ROWS_MAX_C], s_e[2 * ROWS_MAX_C];
+  __shared__ float s_b[ROWS_MAX_C_WIDE], s_e[ROWS_MAX_C_WIDE];
   __shared__ int s_last;
   const int HW = H * W, Ch = C >> 1, Cout = affine ? C : Ch;
   const int n = blockIdx.y;
@@ -386,7 +390,7 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
   pdl_trigger();
   pdl_wait();
   __shared__ float s_part[4][256];
-  __shared__ float s_e[2 * ROWS_MAX_C];
+  __shared__ float s_e[ROWS_MAX_C_WIDE];
   const int Ch = C >> 1, Cout = affine ? C : Ch;
   const int j = threadIdx.x, slot = threadIdx.y, ppb = blockDim.y;
   const int tid = slot * Ch + j;
@@ -421,8 +425,8 @@ rows_coupling_bwd_kernel(const float* __restrict__ y, const float* __restrict__ 
   __syncthreads();
   // thread (q, j): sum of quantity q over the pixel slots, then one global atomic per channel and CTA
   const int nq = affine ? 4 : 2;
-  if (tid < nq * Ch) {
-    const int q = tid / Ch, jj = tid - q * Ch;
+  for (int t = tid; t < nq * Ch; t += Ch * ppb) {          // (more than one pass only for C > 128)
+    const int q = t / Ch, jj = t - q * Ch;
     float s = 0.f;
     for (int k = 0; k < ppb; ++k) s += s_part[q][k * Ch + jj];
     const int c = affine ? (2 * jj + (q >> 1)) : jj;
@@ -1006,7 +1010,7 @@ rows_split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h
                         int iters) {
   pdl_wait();
   __shared__ float s_part[4][256];
-  __shared__ float s_e[2 * ROWS_MAX_C];
+  __shared__ float s_e[ROWS_MAX_C_WIDE];
   const int Ch = C >> 1;
   const int tid = threadIdx.x;
   const int ppb = 256 / Ch;
@@ -1032,8 +1036,8 @@ rows_split2d_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h
   }
   s_part[0][tid] = a0; s_part[1][tid] = b0; s_part[2][tid] = a1; s_part[3][tid] = b1;
   __syncthreads();
-  if (tid < 4 * Ch) {
-    const int q = tid / Ch, jj = tid - q * Ch;
+  for (int t = tid; t < 4 * Ch; t += 256) {
+    const int q = t / Ch, jj = t - q * Ch;
     float s = 0.f;
     for (int k = 0; k < ppb; ++k) s += s_part[q][k * Ch + jj];
     const int c = 2 * jj + (q >> 1);
@@ -1232,6 +1236,32 @@ conv_actnorm_finish_kernel(const FinishJob* __restrict__ jobs) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ActNorm adjoint on rows for the wide levels (C > ROWS_MAX_C), where the 1x1 conv and its adjoint run as fp32
+// GEMMs:  dx = da*s ; dbias += sum_p da*s ; dlogs += f * sum_p da*(x+b)*s   (module.py:34-84).  dx may alias da.
+// grid = (channel blocks of 256, row chunks); one atomic per channel, quantity and CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_actnorm_bwd_kernel(const float* __restrict__ da, const float* __restrict__ x, const float* __restrict__ bias,
+                        const float* __restrict__ logs, float f, float* dx, float* __restrict__ dlogs,
+                        float* __restrict__ dbias, int P, int C, int rows_per_cta) {
+  pdl_wait();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const float s = expf(logs[c] * f), b = bias[c];
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, P);
+  float sg = 0.f, sga = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int64_t e = (int64_t)r * C + c;
+    const float v = da[e];
+    const float a = (x[e] + b) * s;
+    dx[e] = v * s;
+    sg += v; sga = fmaf(v, a, sga);
+  }
+  atomicAdd(dbias + c, sg * s);
+  atomicAdd(dlogs + c, f * sga);
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -1239,6 +1269,21 @@ using namespace glowk;
 // ============================================================================================
 // C ABI
 // ============================================================================================
+extern "C" int glowk_rows_actnorm_bwd(const float* da, const float* x, const float* bias, const float* logs,
+                                      float logscale_factor, float* dx, float* dlogs, float* dbias, int64_t P,
+                                      int64_t C, void* stream) {
+  if (P == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(da && x && bias && logs && dx && dlogs && dbias, "glowk_rows_actnorm_bwd: null pointer");
+  GLOWK_CHECK_ARG(C > 0 && P > 0 && P * C < (1ll << 31), "glowk_rows_actnorm_bwd: bad shape");
+  int rows_per_cta = 32;
+  while (ceil_div(P, rows_per_cta) > 65535) rows_per_cta *= 2;
+  const dim3 grid((unsigned)ceil_div(C, 256), (unsigned)ceil_div(P, rows_per_cta));
+  rows_actnorm_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(da, x, bias, logs, logscale_factor, dx, dlogs, dbias,
+                                                                  (int)P, (int)C, rows_per_cta);
+  GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_bwd");
+  return GLOWK_OK;
+}
+
 extern "C" int glowk_conv_actnorm_finish_batched(const void* jobs, int64_t njobs, int64_t max_n, void* stream) {
   if (njobs == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(jobs && njobs > 0 && njobs < 65536 && max_n > 0 && max_n < (1 << 20), "glowk_conv_actnorm_finish_batched: bad arguments");
@@ -1258,6 +1303,7 @@ static inline int bwd_iters(int64_t NP, int ppb, int resident) {
 }
 
 extern "C" int glowk_rows_max_channels(void) { return ROWS_MAX_C; }
+extern "C" int glowk_rows_max_channels_wide(void) { return ROWS_MAX_C_WIDE; }
 
 extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, const int64_t* idx,
                                       const float* bias, const float* logs, float logscale_factor, int64_t P,
@@ -1315,7 +1361,7 @@ extern "C" int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bi
                                    float sign, float* partials, void* tickets, void* stream) {
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(P3 && bias3 && logs3 && z, "glowk_rows_coupling: null pointer");
-  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling: bad channel count %lld", (long long)C);
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C_WIDE, "glowk_rows_coupling: bad channel count %lld", (long long)C);
   const int64_t Cout = affine ? C : C / 2;
   GLOWK_CHECK_ARG(ldp >= 9 * Cout && ldp % 2 == 0, "glowk_rows_coupling: ldp=%lld too small for 9*Cout=%lld", (long long)ldp, (long long)(9 * Cout));
   GLOWK_CHECK_ARG(!ld_out || (partials && tickets), "glowk_rows_coupling: logdet output needs partials and tickets");
@@ -1381,7 +1427,7 @@ extern "C" int glowk_rows_coupling_bwd(const float* y, const float* hrows, const
                                        void* stream) {
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(y && hrows && dy && logs3 && dz && du && dlogs3 && dbias3, "glowk_rows_coupling_bwd: null pointer");
-  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling_bwd: bad channel count");
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C_WIDE, "glowk_rows_coupling_bwd: bad channel count");
   const int64_t NP = N * HW;
   GLOWK_CHECK_ARG(NP * C < (1ll << 31), "glowk_rows_coupling_bwd: tensor too large for 32-bit indexing");
   const int Ch = (int)(C / 2), ppb = 256 / Ch;
@@ -1531,7 +1577,7 @@ extern "C" int glowk_rows_split2d_bwd(const float* x, const float* hrows, int64_
                                       float* dlogs_p, float* dbias_p, int64_t N, int64_t C, int64_t HW, void* stream) {
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(x && hrows && dld && logs_p && dx && du && dlogs_p && dbias_p, "glowk_rows_split2d_bwd: null pointer");
-  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C && ldh >= C && ldu >= C && ldu % 2 == 0 && ldh % 2 == 0, "glowk_rows_split2d_bwd: bad shape");
+  GLOWK_CHECK_ARG(C > 0 && C % 2 == 0 && C <= ROWS_MAX_C_WIDE && ldh >= C && ldu >= C && ldu % 2 == 0 && ldh % 2 == 0, "glowk_rows_split2d_bwd: bad shape");
   const int64_t NP = N * HW;
   const int ppb = 256 / (int)(C / 2);
   const int iters = bwd_iters(NP, ppb, resident_ctas((const void*)rows_split2d_bwd_kernel, 256, 0));

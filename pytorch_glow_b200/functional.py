@@ -341,6 +341,19 @@ def rows_max_channels():
     return int(_C.lib().glowk_rows_max_channels())
 
 
+def rows_max_channels_wide():
+    return int(_C.lib().glowk_rows_max_channels_wide())
+
+
+def rows_actnorm_bwd(da, x, bias, logs, dlogs, dbias, logscale_factor=3.0, out=None):
+    """dx = da*s (in place by default), dbias += sum da*s, dlogs += f*sum da*(x+bias)*s on rows [P][C]."""
+    check_cuda(da, x, bias, logs, dlogs, dbias)
+    out = da if out is None else out
+    call("glowk_rows_actnorm_bwd", ptr(da), ptr(x), ptr(bias), ptr(logs), float(logscale_factor), ptr(out), ptr(dlogs),
+         ptr(dbias), da.shape[0], da.shape[1])
+    return out
+
+
 def rows_squeeze(src, src_layout, src_ld, dst, dst_layout, dst_ld, n, c, h, w, factor, reverse):
     """Squeeze2d / unsqueeze between layouts (module.py:551-591); see glowk_rows_squeeze."""
     check_cuda(src, dst)

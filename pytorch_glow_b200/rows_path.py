@@ -39,6 +39,19 @@ def _steps_and_splits(flow):
     return steps, splits
 
 
+def _step_ok(step):
+    """Channel counts the rows kernels take: <= 96 for every permutation type (ActNorm + mix kernels with the
+    weight in shared memory); up to 384 for the 1x1 conv, whose ActNorm + mix then run as fp32 GEMMs (_mix_wide_*)."""
+    c = step.in_channels
+    if c % 4:
+        return False
+    return c <= K.rows_max_channels() or (c <= K.rows_max_channels_wide() and step.permutation == 'invconv')
+
+
+def _split_ok(sp):
+    return sp.num_channels % 4 == 0 and sp.num_channels <= K.rows_max_channels_wide()
+
+
 def supported(flow, z):
     """True iff FlowModel `flow` can run on the rows kernels for input z (else: per-layer NCHW path)."""
     from .model import FlowStep
@@ -46,16 +59,15 @@ def supported(flow, z):
         return False
     if not (0 < z.shape[0] <= 65535) or len(flow.layers) == 0:
         return False
-    cmax = K.rows_max_channels()
     layers = list(flow.layers)
     if not isinstance(layers[0], module.Squeeze2d) or isinstance(layers[-1], module.Split2d):
         return False
     for i, layer in enumerate(layers):
         if isinstance(layer, FlowStep):
-            if layer.in_channels % 4 or layer.in_channels > cmax:
+            if not _step_ok(layer):
                 return False
         elif isinstance(layer, module.Split2d):
-            if layer.num_channels % 4 or layer.num_channels > cmax or not isinstance(layers[i + 1], module.Squeeze2d):
+            if not _split_ok(layer) or not isinstance(layers[i + 1], module.Squeeze2d):
                 return False
         elif not isinstance(layer, module.Squeeze2d):
             return False
@@ -73,18 +85,16 @@ def _prefix_len(flow):
     """Number of leading layers that form whole levels (Squeeze2d, FlowStep x K [, Split2d]) the rows kernels run:
     channel counts a multiple of 4 and <= glowk_rows_max_channels()."""
     from .model import FlowStep
-    cmax = K.rows_max_channels()
     layers = list(flow.layers)
     i = good = 0
     while i < len(layers) and isinstance(layers[i], module.Squeeze2d):
         j = i + 1
-        while j < len(layers) and isinstance(layers[j], FlowStep) and layers[j].in_channels % 4 == 0 \
-                and layers[j].in_channels <= cmax:
+        while j < len(layers) and isinstance(layers[j], FlowStep) and _step_ok(layers[j]):
             j += 1
         if j == i + 1 or (j < len(layers) and isinstance(layers[j], FlowStep)):
             break                                   # no step, or a step the kernels cannot run
         if j < len(layers) and isinstance(layers[j], module.Split2d):
-            if layers[j].num_channels % 4 or layers[j].num_channels > cmax:
+            if not _split_ok(layers[j]):
                 break
             j += 1
         elif j < len(layers):
@@ -281,6 +291,35 @@ def _mix_params(step, device, reverse, need_inverse):
     return None, step.perm_module.device_indices(device, reverse), None, None, None
 
 
+def _is_wide(c):
+    return c > K.rows_max_channels()
+
+
+def _mix_wide_forward(x, wm, bias, logs, f, reverse):
+    """ActNorm + 1x1 conv on rows for C > 96 (model.py:94-99 / 148-152): the C x C weight does not fit the shared
+    memory of rows_mix_kernel, and at these levels (8x8 / 4x4 pixels) the mix is a small fp32 GEMM anyway."""
+    p, c = x.shape
+    if not reverse:
+        a = K.actnorm(x.view(p, c, 1, 1), bias, logs, f, reverse=False).view(p, c)
+        return K.gemm(a, wm, c, c, _C.EPI_STORE, out_dtype=_C.F32)
+    t = K.gemm(x, wm, c, c, _C.EPI_STORE, out_dtype=_C.F32)                  # wm = W^-1
+    return K.actnorm(t.view(p, c, 1, 1), bias, logs, f, reverse=True).view(p, c)
+
+
+def _mix_wide_backward(x, dz, n, h, w, da1, cin, wmat, winv, an, gw, dld):
+    """Adjoint of _mix_wide_forward (+ conv1 dgrad tap gather, + logdet parameter gradients)."""
+    p, c = x.shape
+    K.rows_tapsum(da1, dz, 0, cin, n, h, w, flip=True, accumulate=True)       # dz[:, :cin] += conv1 dgrad
+    bias, logs = an.bias.detach().reshape(-1), an.logs.detach().reshape(-1)
+    a = K.actnorm(x.view(p, c, 1, 1), bias, logs, an.logscale_factor, reverse=False).view(p, c)
+    K.gemm_wgrad(dz, a, c, c, gw.view(c, c))                                  # dW += dz^T a
+    da = K.gemm(dz, wmat.t().contiguous(), c, c, _C.EPI_STORE, out_dtype=_C.F32)   # da = dz W
+    dx = K.rows_actnorm_bwd(da, x, bias, logs, _gbuf(an.logs), _gbuf(an.bias), an.logscale_factor)
+    if dld is not None:
+        K.logdet_param_grad(dld, h * w, _gbuf(an.logs), winv, gw, an.logscale_factor)
+    return dx
+
+
 def _ones_col(net, dt):
     """First zero-padding column of the conv1 im2col operand (or -1): written as 1.0 on the bf16 training path so
     that conv1's weight-gradient GEMM also yields the bias gradient of its ActNorm (glowk_im2col_rows_ones)."""
@@ -295,7 +334,10 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save):
         an.initialize_from_rows(x)
     wm, idx, logabsdet, wmat, winv = _mix_params(step, x.device, False, save)
     b, l = an.bias.detach().reshape(-1), an.logs.detach().reshape(-1)
-    z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
+    if _is_wide(c):
+        z = _mix_wide_forward(x, wm, b, l, an.logscale_factor, False)
+    else:
+        z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
     net = step.f
     dt = net.dtype(step.conv_dtype)
     a1 = K.im2col_rows(z, n, h, w, 0, net.in_channels, 3, dt, net.k1p, ones_col=_ones_col(net, dt) if save else -1)
@@ -324,6 +366,9 @@ def _step_reverse(step, x, n, c, h, w, ws):
     K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
                     c3.logscale_factor)
     wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
+    if _is_wide(c):
+        return _mix_wide_forward(x, wm, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
+                                 an.logscale_factor, True)
     return K.rows_actnorm_mix(x, wm, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
                               an.logscale_factor, reverse=True)
 
@@ -370,16 +415,21 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
         plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
     # bf16 path: the nine-tap partial gradients are stored in bf16 (they are products of bf16 operands already) and
     # summed in fp32 by the mix adjoint
-    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=dt)
+    wide = _is_wide(c)
+    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32 if wide else dt)
     # (5) ActNorm + mix
     dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition
     gw = _gbuf(step.invconv.weight) if dense else None
     if step.permutation == 'invconv' and gw is None:
         gw = torch.zeros(c * c, device=dev, dtype=torch.float32)
-    dx = K.rows_actnorm_mix_bwd(ctx["x"], dz, n, h, w, da1=da1, cin=net.in_channels, weight=ctx["wmat"],
-                                indices=ctx["idx"], bias=an.bias.detach().reshape(-1),
-                                logs=an.logs.detach().reshape(-1), dw=gw, dlogs=_gbuf(an.logs), dbias=_gbuf(an.bias),
-                                logscale_factor=an.logscale_factor, dld=dld, winv=ctx["winv"])
+    if wide:
+        dx = _mix_wide_backward(ctx["x"], dz, n, h, w, da1, net.in_channels, ctx["wmat"], ctx["winv"], an, gw, dld)
+    else:
+        dx = K.rows_actnorm_mix_bwd(ctx["x"], dz, n, h, w, da1=da1, cin=net.in_channels, weight=ctx["wmat"],
+                                    indices=ctx["idx"], bias=an.bias.detach().reshape(-1),
+                                    logs=an.logs.detach().reshape(-1), dw=gw, dlogs=_gbuf(an.logs),
+                                    dbias=_gbuf(an.bias), logscale_factor=an.logscale_factor, dld=dld,
+                                    winv=ctx["winv"])
     if step.permutation == 'invconv' and step.invconv.lu_decomposition:
         step.invconv.accumulate_lu_grads(gw.view(c, c))
     return dx

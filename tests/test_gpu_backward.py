@@ -140,7 +140,8 @@ def test_split2d_and_flowmodel_gradients_vs_oracle():
 
 def test_six_level_flowmodel_trains_through_the_wide_channel_fallback():
     """BASELINE config 5 shape family (L=6: 12 ... 384 channels) at a small image: the levels wider than the
-    pixel-major kernels' 96 channels run on the per-layer NCHW kernels; z, logdet and every gradient vs the oracle."""
+    mix kernels' 96 channels run ActNorm + the 1x1 conv as fp32 GEMMs on the pixel-major path; z, logdet and every
+    gradient vs the oracle."""
     from pytorch_glow_b200 import rows_path
     np.random.seed(5)
     torch.manual_seed(5)
@@ -151,7 +152,7 @@ def test_six_level_flowmodel_trains_through_the_wide_channel_fallback():
     fm = fm.to(DEV).train()
     g = torch.Generator().manual_seed(12)
     x = torch.rand(2, 3, 64, 64, generator=g)
-    assert not rows_path.supported(fm, cu(x))
+    assert rows_path.supported(fm, cu(x))
     z_w = torch.randn(2, 384, 1, 1, generator=g) * 0.1
     p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
     z_ref, ld_ref = O.flow_encode(x, torch.zeros(2), p, (64, 64, 3), 1, 6, "invconv", "affine", prefix="")

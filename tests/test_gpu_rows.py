@@ -407,19 +407,24 @@ def test_flowmodel_rows_gradients_equal_nchw_path(perm, coup):
     print("rows vs NCHW parameter gradients: worst rel err %.2e over %d tensors" % (worst, len(g_n)))
 
 
-def test_hybrid_rows_head_and_nchw_tail_match_the_pure_nchw_path():
-    """L=5 (12 ... 192 channels): levels 1-4 run on the pixel-major kernels, level 5 on the per-layer NCHW kernels;
-    encode and every gradient (randomised weights) and decode with supplied noise (fresh weights: zero-initialised
-    couplings keep the inverse of mismatched latents bounded) equal the all-NCHW path."""
-    flow = _flow("invconv", "affine", K_=2, L=5, hidden=32, shape=(32, 32, 3), seed=3).train()
+@pytest.mark.parametrize("perm", ["invconv", "shuffle"])
+def test_wide_levels_match_the_pure_nchw_path(perm):
+    """L=5 (12 ... 192 channels).  invconv: the 192-channel level runs on the pixel-major path with ActNorm + 1x1
+    conv as fp32 GEMMs.  shuffle: levels 1-4 run on the pixel-major kernels, level 5 on the per-layer NCHW kernels
+    (hybrid, one autograd node).  Encode and every gradient (randomised weights) and decode with supplied noise
+    (fresh weights: zero-initialised couplings keep the inverse of mismatched latents bounded) equal the all-NCHW path."""
+    flow = _flow(perm, "affine", K_=2, L=5, hidden=32, shape=(32, 32, 3), seed=3).train()
     flow.set_conv_dtype("fp32")
     x = cu(torch.rand(3, 3, 32, 32, generator=g(80)))
     hd = rows_path.head(flow, x)
-    assert hd is not None and not rows_path.supported(flow, x)
-    k = hd[1]
-    assert isinstance(flow.layers[k - 1], G.Split2d) and flow.layers[k + 1].in_channels == 192
+    if perm == "invconv":
+        assert rows_path.supported(flow, x) and hd is None
+    else:
+        assert hd is not None and not rows_path.supported(flow, x)
+        k = hd[1]
+        assert isinstance(flow.layers[k - 1], G.Split2d) and flow.layers[k + 1].in_channels == 192
     np.random.seed(4); torch.manual_seed(4)
-    fresh = G.FlowModel((32, 32, 3), 32, K=2, L=5, permutation="invconv", coupling="affine")
+    fresh = G.FlowModel((32, 32, 3), 32, K=2, L=5, permutation=perm, coupling="affine")
     for m in fresh.modules():
         if isinstance(m, G.ActNorm):
             m.bias_inited = m.logs_inited = True
@@ -457,8 +462,9 @@ def test_rows_path_falls_back_for_wide_levels():
     flow = G.FlowModel((16, 16, 3), 32, K=1, L=4)          # last level has 3*4*8 = 96 ... 192 channels
     assert max(l.in_channels for l in flow.layers if isinstance(l, G.FlowStep)) == 96
     assert rows_path.supported(flow.to(DEV), torch.zeros(1, 3, 16, 16, device=DEV))
-    flow5 = G.FlowModel((32, 32, 3), 32, K=1, L=5).to(DEV)
+    flow5 = G.FlowModel((32, 32, 3), 32, K=1, L=5, permutation="reverse").to(DEV)     # 192-channel permutation
     assert not rows_path.supported(flow5, torch.zeros(1, 3, 32, 32, device=DEV))
+    assert rows_path.supported(G.FlowModel((32, 32, 3), 32, K=1, L=5).to(DEV), torch.zeros(1, 3, 32, 32, device=DEV))
     with torch.no_grad():
         z, ld = flow5.eval()(torch.rand(2, 3, 32, 32, device=DEV), logdet=torch.zeros(2, device=DEV))
     assert z.shape == (2, 192, 1, 1) and ld.shape == (2,)
