@@ -99,17 +99,128 @@ __global__ void invconv_prepare_kernel(const float* __restrict__ w, int C, float
 // 256 threads per matrix, and one thread per inverse column walking 2 x C^2/2 dependent fp64 FMAs.  Here the
 // factorisation runs with 1024 threads per matrix and the inverse is a second kernel with ONE WARP PER COLUMN
 // (lanes split each row's dot product; the 8 warps of a CTA walk the same rows of LU, which they share through L1).
+// Blocked right-looking LU with partial pivoting (panel width LU_NB): the panel [C-kb][NB] and the row block
+// U12 [NB][C-kb-NB] live in shared memory, so every trailing element is loaded / stored once per NB columns (the
+// unblocked rank-1 loop touched each one C times through L2: 4.3 ms per launch at C = 384).  Same pivot choice
+// (largest |a|, lowest index on ties) as lu_factor_inplace.
+constexpr int LU_NB = 16;
 __global__ void __launch_bounds__(1024)
 invconv_lu_big_kernel(const float* __restrict__ w, int C, float* __restrict__ logabsdet_out, double* gwork, int* gperm) {
+  extern __shared__ __align__(16) unsigned char lu_smem[];
+  double* Pn = reinterpret_cast<double*>(lu_smem);          // [C][NB]   panel (rows kb.. of columns kb..kb+NB)
+  double* U12 = Pn + (size_t)C * LU_NB;                     // [NB][C]   row block right of the panel
+  __shared__ int s_piv[LU_NB];
+  __shared__ double s_best[32];
+  __shared__ int s_bi[32];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
   const size_t mat = blockIdx.x;
   double* A = gwork + mat * (size_t)C * C;
   int* perm = gperm + mat * (size_t)C;
   w += mat * (size_t)C * C;
-  for (int e = threadIdx.x; e < C * C; e += blockDim.x) A[e] = (double)w[e];
+  for (int e = tid; e < C * C; e += nthr) A[e] = (double)w[e];
+  for (int i = tid; i < C; i += nthr) perm[i] = i;
   __syncthreads();
-  double logabs;
-  lu_factor_inplace(A, perm, C, &logabs);
-  if (threadIdx.x == 0) logabsdet_out[mat] = (float)logabs;
+  double logabs = 0.0;
+  for (int kb = 0; kb < C; kb += LU_NB) {
+    const int nb = min(LU_NB, C - kb), rows = C - kb;
+    // ---- panel -> shared memory
+    for (int e = tid; e < rows * nb; e += nthr) {
+      const int r = e / nb, c = e - r * nb;
+      Pn[r * LU_NB + c] = A[(size_t)(kb + r) * C + kb + c];
+    }
+    __syncthreads();
+    // ---- unblocked LU of the panel (pivots recorded relative to kb)
+    for (int k = 0; k < nb; ++k) {
+      double best = -1.0; int bi = k;
+      for (int r = k + tid; r < rows; r += nthr) {
+        const double v = fabs(Pn[r * LU_NB + k]);
+        if (v > best) { best = v; bi = r; }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { s_best[warp] = best; s_bi[warp] = bi; }
+      __syncthreads();
+      if (warp == 0) {
+        best = lane < nwarp ? s_best[lane] : -1.0; bi = lane < nwarp ? s_bi[lane] : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) s_piv[k] = bi;
+      }
+      __syncthreads();
+      const int piv = s_piv[k];
+      if (piv != k && tid < nb) {
+        const double t = Pn[k * LU_NB + tid]; Pn[k * LU_NB + tid] = Pn[piv * LU_NB + tid]; Pn[piv * LU_NB + tid] = t;
+      }
+      __syncthreads();
+      const double d = Pn[k * LU_NB + k];
+      if (tid == 0) logabs += log(fabs(d));
+      for (int r = k + 1 + tid; r < rows; r += nthr) Pn[r * LU_NB + k] /= d;
+      __syncthreads();
+      const int rc = nb - k - 1;
+      for (int e = tid; e < (rows - k - 1) * rc; e += nthr) {
+        const int r = k + 1 + e / rc, c = k + 1 + e % rc;
+        Pn[r * LU_NB + c] -= Pn[r * LU_NB + k] * Pn[k * LU_NB + c];
+      }
+      __syncthreads();
+    }
+    // ---- apply the panel's row swaps to the columns outside the panel (in order) and to perm; write the panel back
+    for (int c = tid; c < C; c += nthr) {
+      if (c >= kb && c < kb + nb) continue;
+      for (int k = 0; k < nb; ++k) {
+        const int piv = s_piv[k];
+        if (piv != k) {
+          const double t = A[(size_t)(kb + k) * C + c];
+          A[(size_t)(kb + k) * C + c] = A[(size_t)(kb + piv) * C + c];
+          A[(size_t)(kb + piv) * C + c] = t;
+        }
+      }
+    }
+    if (tid == 0)
+      for (int k = 0; k < nb; ++k) {
+        const int piv = s_piv[k];
+        if (piv != k) { const int t = perm[kb + k]; perm[kb + k] = perm[kb + piv]; perm[kb + piv] = t; }
+      }
+    for (int e = tid; e < rows * nb; e += nthr) {
+      const int r = e / nb, c = e - r * nb;
+      A[(size_t)(kb + r) * C + kb + c] = Pn[r * LU_NB + c];
+    }
+    __syncthreads();
+    const int rest = C - kb - nb;                           // columns (and rows) right of / below the panel
+    if (rest <= 0) break;
+    // ---- U12 = L11^-1 A12: one thread per column, forward substitution over the nb panel rows
+    for (int c = tid; c < rest; c += nthr) {
+      double u[LU_NB];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k) u[k] = k < nb ? A[(size_t)(kb + k) * C + kb + nb + c] : 0.0;
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+#pragma unroll
+        for (int m = 0; m < LU_NB; ++m)
+          if (m < k) u[k] -= Pn[k * LU_NB + m] * u[m];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+        if (k < nb) { U12[k * C + c] = u[k]; A[(size_t)(kb + k) * C + kb + nb + c] = u[k]; }
+    }
+    __syncthreads();
+    // ---- trailing update A22 -= L21 U12
+    for (int e = tid; e < rest * rest; e += nthr) {
+      const int r = e / rest, c = e - r * rest;
+      const double* l = Pn + (size_t)(nb + r) * LU_NB;
+      double acc = A[(size_t)(kb + nb + r) * C + kb + nb + c];
+#pragma unroll
+      for (int k = 0; k < LU_NB; ++k)
+        if (k < nb) acc -= l[k] * U12[k * C + c];
+      A[(size_t)(kb + nb + r) * C + kb + nb + c] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) logabsdet_out[mat] = (float)logabs;
 }
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
@@ -218,11 +329,17 @@ extern "C" int glowk_invconv_prepare_batched(const float* w, int64_t batch, int6
     const size_t work = (size_t)batch * C * C * sizeof(double), all = work + (size_t)batch * C * sizeof(int);
     GLOWK_CUDA(cudaMallocAsync((void**)&gwork, all, st));
     int* gperm = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(gwork) + work);
-    invconv_lu_big_kernel<<<(unsigned)batch, 1024, 0, st>>>(w, (int)C, logabsdet_out, gwork, gperm);
-    cudaError_t e1 = cudaGetLastError();
+    const size_t lu_smem_bytes = 2 * (size_t)C * LU_NB * sizeof(double);            // panel + U12 (96 KB at C = 384)
+    cudaError_t e1 = cudaSuccess;
+    if (lu_smem_bytes > 40 * 1024)            // (static shared memory counts against the 48 KB default too)
+      e1 = cudaFuncSetAttribute(invconv_lu_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_smem_bytes);
+    if (e1 == cudaSuccess) {
+      invconv_lu_big_kernel<<<(unsigned)batch, 1024, lu_smem_bytes, st>>>(w, (int)C, logabsdet_out, gwork, gperm);
+      e1 = cudaGetLastError();
+    }
     if (e1 == cudaSuccess && winv_out) {
       const size_t xs = 8 * (size_t)C * sizeof(double);
-      if (xs > 48 * 1024)
+      if (xs > 40 * 1024)
         e1 = cudaFuncSetAttribute(invconv_inverse_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xs);
       if (e1 == cudaSuccess) {
         invconv_inverse_big_kernel<<<dim3((unsigned)ceil_div(C, 8), (unsigned)batch), 256, xs, st>>>(gwork, gperm, (int)C, winv_out);
