@@ -468,3 +468,20 @@ def test_rows_path_falls_back_for_wide_levels():
     with torch.no_grad():
         z, ld = flow5.eval()(torch.rand(2, 3, 32, 32, device=DEV), logdet=torch.zeros(2, device=DEV))
     assert z.shape == (2, 192, 1, 1) and ld.shape == (2,)
+
+
+# ---------------------------------------------------------------- kernels kept behind A/B switches
+def test_alternate_kernels_behind_ab_switches():
+    """The direct-gather mix adjoint, the warp-per-pixel im2col and the shared-memory-window coupling kernel stay
+    selectable through environment switches read at first use (DESIGN.md section 5 and the negative results): run their
+    parity tests in a fresh process with the switches set so that they do not rot."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GLOWK_MIXBWD_NOWIN="1", GLOWK_IM2COL_WARP="1", GLOWK_COUPLING_WIN="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_rows.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "rows_coupling_matches_nchw or rows_mix_bwd_matches_nchw or im2col_rows_equals_nchw or "
+                              "flowmodel_rows_equals_nchw_path or flowmodel_rows_gradients_equal_nchw_path"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
