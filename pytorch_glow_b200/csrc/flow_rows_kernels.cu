@@ -55,24 +55,6 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
   // two pixels per thread and pass (pixA, pixB = pixA + blockDim.y): every W^T float4 read from shared memory
   // feeds 8 FMAs instead of 4 -- the kernel was bound by the shared-memory pipe (M*C^2/16 LDS.128 per launch, the
   // same count at every level), not by HBM.  Each pixel's FMA order is unchanged.
-  // The first 12 channels of the NEXT pass are fetched before this pass's arithmetic (register double buffer): a
-  // CTA's passes are otherwise one exposed memory latency each (6 passes at level 1: 16 us for 50 MB).
-  constexpr bool PF = !PERM && (CT == 12 || CT == 24);
-  float4 pa4[3], pb4[3];
-  auto load_first = [&](int it_, float4* a4, float4* b4) {
-    const int pA = (blockIdx.x * iters + it_) * 2 * blockDim.y + slot;
-    if (pA < P) {
-      const int pB = pA + blockDim.y;
-      const float* rA = x + (int64_t)pA * C;
-      const float* rB = x + (int64_t)(pB < P ? pB : pA) * C;
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        a4[b] = *reinterpret_cast<const float4*>(rA + 4 * b);
-        b4[b] = *reinterpret_cast<const float4*>(rB + 4 * b);
-      }
-    }
-  };
-  if (PF) load_first(0, pa4, pb4);
   for (int it = 0; it < iters; ++it) {
     const int pixA = (blockIdx.x * iters + it) * 2 * blockDim.y + slot;
     if (pixA >= P) return;
@@ -80,8 +62,6 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
     const bool hasB = pixB < P;
     const float* xrA = x + (int64_t)pixA * C;
     const float* xrB = x + (int64_t)(hasB ? pixB : pixA) * C;
-    float4 na4[3], nb4[3];
-    if (PF && it + 1 < iters) load_first(it + 1, na4, nb4);
     float accA[4], accB[4];
     if (PERM) {
 #pragma unroll
@@ -103,7 +83,6 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 #pragma unroll
         for (int b = 0; b < 3; ++b) {
           const bool in = i0 + 4 * b < C;
-          if (PF && i0 == 0) { xa4[b] = pa4[b]; xb4[b] = pb4[b]; continue; }
           xa4[b] = in ? *reinterpret_cast<const float4*>(xrA + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
           xb4[b] = in ? *reinterpret_cast<const float4*>(xrB + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -142,10 +121,6 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
     }
     *reinterpret_cast<float4*>(z + (int64_t)pixA * C + og * 4) = make_float4(accA[0], accA[1], accA[2], accA[3]);
     if (hasB) *reinterpret_cast<float4*>(z + (int64_t)pixB * C + og * 4) = make_float4(accB[0], accB[1], accB[2], accB[3]);
-    if (PF) {
-#pragma unroll
-      for (int b = 0; b < 3; ++b) { pa4[b] = na4[b]; pb4[b] = nb4[b]; }
-    }
   }
 }
 
