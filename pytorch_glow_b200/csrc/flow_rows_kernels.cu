@@ -17,6 +17,17 @@ constexpr int ROWS_MAX_C = 96;   // shared-memory tiles of the mix kernels are s
 // (rows_path.py: _mix_wide_*; glowk_rows_actnorm_bwd below).
 constexpr int ROWS_MAX_C_WIDE = 384;
 
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // ActNorm + channel mix / permutation (model.py:94-103 fwd, 142-152 rev).
 // block = (G = C/4 output-channel groups, PPB pixels): thread (og, slot) produces 4 output channels of one
@@ -40,6 +51,21 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
   const int og = threadIdx.x, slot = threadIdx.y;
   const int nthr = blockDim.x * blockDim.y;
   const int tid = slot * blockDim.x + og;
+  // the pixel rows of a pass (2*blockDim.y contiguous pixels = one contiguous block of x) are staged through a
+  // double buffer with cp.async: the copy of pass it+1 runs under the FMAs of pass it.  (Straight global loads made
+  // every pass of a CTA one exposed memory round trip: ~16 us per launch at EVERY level, whatever its size.)
+  const int ppp = 2 * blockDim.y;                 // pixels per pass
+  float* xbuf = reinterpret_cast<float*>(sidx + C);   // [2][ppp][C]   (16-byte aligned: C is a multiple of 4)
+  const int64_t total4 = (int64_t)P * C / 4;
+  auto stage_pass = [&](int it_) {
+    const int64_t base4 = (int64_t)(blockIdx.x * iters + it_) * ppp * C / 4;
+    float* dst = xbuf + (it_ & 1) * ppp * C;
+    const int n4 = ppp * C / 4;
+    for (int i = tid; i < n4; i += nthr)
+      if (base4 + i < total4) cp_async16(dst + 4 * i, x + 4 * (base4 + i));
+    cp_async_commit();
+  };
+  stage_pass(0);
   const bool has_an = bias != nullptr;
   for (int c = tid; c < C; c += nthr) {
     const float l = has_an ? logs[c] * f : 0.f;
@@ -56,12 +82,15 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
   // feeds 8 FMAs instead of 4 -- the kernel was bound by the shared-memory pipe (M*C^2/16 LDS.128 per launch, the
   // same count at every level), not by HBM.  Each pixel's FMA order is unchanged.
   for (int it = 0; it < iters; ++it) {
-    const int pixA = (blockIdx.x * iters + it) * 2 * blockDim.y + slot;
-    if (pixA >= P) return;
+    if ((int64_t)(blockIdx.x * iters + it) * ppp >= P) break;       // (CTA-uniform)
+    if (it + 1 < iters) { stage_pass(it + 1); cp_async_wait_group<1>(); } else cp_async_wait_group<0>();
+    __syncthreads();
+    const int pixA = (blockIdx.x * iters + it) * ppp + slot;
     const int pixB = pixA + blockDim.y;
-    const bool hasB = pixB < P;
-    const float* xrA = x + (int64_t)pixA * C;
-    const float* xrB = x + (int64_t)(hasB ? pixB : pixA) * C;
+    const bool hasA = pixA < P, hasB = pixB < P;
+    const float* xb_ = xbuf + (it & 1) * ppp * C;
+    const float* xrA = xb_ + (hasA ? slot : 0) * C;
+    const float* xrB = xb_ + (hasB ? slot + (int)blockDim.y : (hasA ? slot : 0)) * C;
     float accA[4], accB[4];
     if (PERM) {
 #pragma unroll
@@ -119,8 +148,9 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
         }
       }
     }
-    *reinterpret_cast<float4*>(z + (int64_t)pixA * C + og * 4) = make_float4(accA[0], accA[1], accA[2], accA[3]);
+    if (hasA) *reinterpret_cast<float4*>(z + (int64_t)pixA * C + og * 4) = make_float4(accA[0], accA[1], accA[2], accA[3]);
     if (hasB) *reinterpret_cast<float4*>(z + (int64_t)pixB * C + og * 4) = make_float4(accB[0], accB[1], accB[2], accB[3]);
+    __syncthreads();                                // this pass's buffer is refilled by the pass after next
   }
 }
 
@@ -238,13 +268,6 @@ rows_coupling_kernel(const float* __restrict__ P3, int ldp, const float* __restr
 // scattered sector reads -- and gathers the taps from shared memory (pitch ldp+4 floats: conflict-light).
 // Arithmetic, summation order and the per-sample logdet reduction are those of rows_coupling_kernel.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
 // mbarrier + bulk (TMA engine, no tensor map) global -> shared copies: one instruction per contiguous run
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -1323,6 +1346,7 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
 #define GLOWK_MIX_LAUNCH(PERM_, CT_, SMEM_)                                                                          \
   do {                                                                                                               \
     auto kern = rows_mix_kernel<PERM_, CT_>;                                                                         \
+    if (SMEM_ > 40 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
     const int64_t passes = ceil_div(P, 2 * ppb);             /* two pixels per thread and pass */                   \
     int iters = (int)ceil_div(passes, resident_ctas((const void*)kern, G * ppb, SMEM_));                             \
     iters = iters < 1 ? 1 : (iters > 32 ? 32 : iters);                                                               \
@@ -1330,14 +1354,15 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
     GLOWK_CUDA(launch_pdl(kern, grid, block, SMEM_, st, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C,   \
                           reverse, iters));                                                                          \
   } while (0)
+  const size_t xbuf_bytes = sizeof(float) * 2 * (size_t)(2 * ppb) * C;      // double-buffered pixel rows of a pass
   if (w) {
-    const size_t smem = sizeof(float) * ((size_t)C * C + 2 * C);
+    const size_t smem = sizeof(float) * ((size_t)C * C + 3 * C) + xbuf_bytes;
     if (C == 12) GLOWK_MIX_LAUNCH(false, 12, smem);
     else if (C == 24) GLOWK_MIX_LAUNCH(false, 24, smem);
     else if (C == 48) GLOWK_MIX_LAUNCH(false, 48, smem);
     else GLOWK_MIX_LAUNCH(false, 0, smem);
   } else {
-    const size_t smem = sizeof(float) * (3 * (size_t)C);
+    const size_t smem = sizeof(float) * (3 * (size_t)C) + xbuf_bytes;
     GLOWK_MIX_LAUNCH(true, 0, smem);
   }
 #undef GLOWK_MIX_LAUNCH
