@@ -112,3 +112,23 @@ def test_hps_container():
     h.a.b = 4
     import json
     assert json.loads(json.dumps(h))["a"]["b"] == 4
+
+
+def test_rows_path_level_dispatch():
+    """Which layers the pixel-major path takes (rows_path._prefix_len): every level up to 96 channels, 1x1-conv
+    levels up to 384 channels (fp32 GEMM mix), and only whole levels ending in a Split2d before a wide permutation level."""
+    from pytorch_glow_b200 import rows_path
+    with torch.device("meta"):
+        celeba = G.FlowModel((64, 64, 3), 512, K=4, L=3)
+        hq = G.FlowModel((256, 256, 3), 512, K=2, L=6)                          # 12 ... 384 channels, invconv
+        hq_perm = G.FlowModel((64, 64, 3), 32, K=2, L=6, permutation="reverse")  # wide permutation levels
+        too_wide = G.FlowModel((128, 128, 3), 32, K=1, L=7)                      # level 7: 768 channels
+    assert _C.lib().glowk_rows_max_channels() == 96 and _C.lib().glowk_rows_max_channels_wide() == 384
+    assert rows_path._prefix_len(celeba) == len(celeba.layers)
+    assert rows_path._prefix_len(hq) == len(hq.layers)
+    k = rows_path._prefix_len(hq_perm)
+    assert 0 < k < len(hq_perm.layers)
+    assert isinstance(hq_perm.layers[k - 1], G.Split2d) and isinstance(hq_perm.layers[k], G.Squeeze2d)
+    assert hq_perm.layers[k - 2].in_channels == 96 and hq_perm.layers[k + 1].in_channels == 192
+    k7 = rows_path._prefix_len(too_wide)
+    assert isinstance(too_wide.layers[k7 - 1], G.Split2d) and too_wide.layers[k7 + 1].in_channels == 768
