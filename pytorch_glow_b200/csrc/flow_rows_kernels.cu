@@ -704,7 +704,7 @@ rows_mix_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dz, c
 // Element arithmetic and summation order of dx are those of rows_mix_bwd_kernel.
 // ------------------------------------------------------------------------------------------
 template <bool PERM, int RMB_MAXIT, int CT, typename TA>
-__global__ void __launch_bounds__(256, RMB_MAXIT == 1 ? 3 : 1)
+__global__ void __launch_bounds__(256, RMB_MAXIT == 1 ? 4 : 1)
 rows_mix_bwd_win_kernel(const float* __restrict__ x, const float* __restrict__ dz, const TA* __restrict__ dA1,
                         int ld_a1, int Cin, const float* __restrict__ w, const int64_t* __restrict__ idx,
                         const float* __restrict__ bias, const float* __restrict__ logs, float f,
@@ -1517,8 +1517,10 @@ extern "C" int glowk_rows_actnorm_mix_bwd_ex(const float* x, const float* dz, co
       if (win_floats < 4096) win_floats = 4096;                            // also the dW combine scratch (256 x 16)
       return sizeof(float) * ((size_t)win_floats + 2 * (size_t)tp * C + (w ? (size_t)C * C : 0) + 5 * (size_t)C + 33);
     };
-    static const size_t smem_cap = []() { const char* e = getenv("GLOWK_MIXBWD_SMEM_KB"); return (size_t)(e ? atoi(e) : 72) * 1024; }();
-    int TPw = 128;                          // <= 72 KB per CTA (3 per SM); smaller tiles until every SM has two CTAs
+    // <= 56 KB per CTA and 64 registers: four CTAs per SM.  A/B at B = 512 (profiles/r1j_mixbwd_occupancy_ab.txt):
+    // 61.4 / 42.2 / 43.1 us at levels 1 / 2 / 3 with three CTAs of <= 72 KB, 60.4 / 40.1 / 37.6 us with four.
+    static const size_t smem_cap = []() { const char* e = getenv("GLOWK_MIXBWD_SMEM_KB"); return (size_t)(e ? atoi(e) : 56) * 1024; }();
+    int TPw = 128;                          // smaller tiles until the cap holds and every SM has two CTAs
     while (TPw > 32 && (smem_for(TPw) > smem_cap || ceil_div(NP, TPw) < 2 * sm_count())) TPw >>= 1;
     const size_t smem_w = smem_for(TPw);
     if (smem_w <= 160 * 1024) {
