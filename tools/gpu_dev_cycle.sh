@@ -1,8 +1,8 @@
 #!/bin/bash
-# cycle h: full GPU tests, eager launch list at B=512, graph bench, ncu --set full of mix_bwd / coupling at levels 3 and 2
+# development cycle: full GPU tests, eager launch list at B=512, graph bench, ncu --set full of mix_bwd / coupling at levels 3 and 2
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-TAG=${TAG:-h1}
+TAG=${TAG:-dev}
 B=${B:-512}
 timeout 900 python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/${TAG}_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log
