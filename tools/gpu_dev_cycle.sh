@@ -13,7 +13,7 @@ python tools/summarize_launches.py gpurun_out/${TAG}_launches.csv 30
 timeout 400 python bench.py --batch $B --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | grep -v Warn > gpurun_out/${TAG}_bench.log
 python - <<'PY'
 import json,os
-for l in open("gpurun_out/%s_bench.log" % os.environ.get("TAG","h1")):
+for l in open("gpurun_out/%s_bench.log" % os.environ.get("TAG","dev")):
     if l.startswith("{"):
         d=json.loads(l); print(d["config"]["per_gpu_batch"], "train", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms", round(d["ms_per_step"],2), "sample", d["sample"] and round(d["sample"]["value"]), "roof", round(d["roofline"]["frac"],3), "loss", d["loss_bits_per_dim"])
         for r in d["roofline_all"]: print("   ", r["id"], round(r["us_per_launch"],1), "us frac", round(r["frac"],3))
