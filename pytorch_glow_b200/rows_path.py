@@ -113,10 +113,14 @@ def head(flow, z):
     k = _prefix_len(flow)
     if k <= 0 or k >= len(flow.layers) or not isinstance(flow.layers[k - 1], module.Split2d):
         return None
+    # nn.DataParallel replicas share this dict (shallow __dict__ copies) but own their layers: key on the layer object
     cache = flow.__dict__.setdefault("_rows_head", {})
-    view = cache.get(k)
-    if view is None:
-        view = cache[k] = _FlowView(list(flow.layers)[:k])
+    key = (k, id(flow.layers[0]))
+    view = cache.get(key)
+    if view is None or view.layers[0] is not flow.layers[0]:
+        if len(cache) >= 16:
+            cache.clear()
+        view = cache[key] = _FlowView(list(flow.layers)[:k])
     return view, k
 
 
