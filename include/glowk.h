@@ -155,6 +155,36 @@ int glowk_gemm_ex(const void* A, int64_t lda, const void* B, int64_t ldb, int ac
 int glowk_gemm_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int act_dtype,
                      int64_t P, int64_t Mo, int64_t No, float* dW, int64_t lddw, void* stream);
 
+/* ---- Fused coupling network f() (module.py:300-319): conv1 3x3 -> ActNorm -> ReLU -> conv2 1x1 -> ActNorm ->
+ * ReLU -> conv3 3x3 as ONE tcgen05 kernel per 128-pixel tile (hidden = 512, bf16 operands, fp32 accumulate).
+ * The 512-wide hidden activations never leave the SM: h1 is written back to tensor memory (tcgen05.st) and is
+ * the TMEM A operand of conv2, h2 goes through a 16 KB shared-memory chunk straight into conv3's MMAs.
+ *   a1 : [M][lda]   bf16  im2col rows of z1 (glowk_im2col_rows), K1 = padded 9*Cin (multiple of 64, <= 256)
+ *   w1 : [512][ldw1], w2: [512][ldw2], w3: [N3][ldw3]   bf16 GEMM-layout weights (glowk_pack_conv_weight
+ *        layouts 0, 0, 1); N3 = padded 9*Cout (multiple of 16, <= 128; or a multiple of 32 <= 256)
+ *   bias*, logs*, f* : the two hidden ActNorms (module.py:238-239, 34-84)
+ *   p3 : [M][ldp3]  fp32  conv3 in tap form (input of glowk_rows_coupling)
+ *   h1_save / h2_save : NULL when sampling; [M][ldh] bf16 to keep the activations for glowk_cnet_backward
+ * Results are bit-identical to three glowk_gemm calls (EPI_ACTNORM_RELU, EPI_ACTNORM_RELU, EPI_STORE).
+ * glowk_cnet_fused_supported(backward, K1, hidden, N3) tells whether a shape is served (else: glowk_gemm). */
+int glowk_cnet_fused_supported(int backward, int64_t K1, int64_t hidden, int64_t N3);
+int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2, int64_t ldw2,
+                       const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden, int64_t N3,
+                       const float* bias1, const float* logs1, float f1, const float* bias2, const float* logs2,
+                       float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* stream);
+/* Adjoint chain of the same network (autograd of module.py:300-319) in one kernel:
+ *   d2 = [h2 > 0] * (d3col . w3t^T) * exp(f2*logs2)   -> TMEM A operand + stored [M][ldh] bf16 (wgrad operand)
+ *   d1 = [h1 > 0] * (d2 . w2t^T) * exp(f1*logs1)      -> shared-memory chunk + stored [M][ldh] bf16
+ *   da1 = d1 . w1t^T                                  -> [M][ldda1] bf16 (conv1 dgrad in im2col form)
+ * d3col: [M][ldd3] bf16 flipped im2col of du, K3 = padded 9*Cout (multiple of 64, <= 256); w3t: [512][ldw3t],
+ * w2t: [512][ldw2t], w1t: [K1p][ldw1t] (glowk_pack_conv_weight layouts 3, 2, 2); K1p multiple of 16, <= 128.
+ * dbias2 / dbias1 (nullable, fp32 [512]): += column sums of the stored d2 / d1 (ActNorm bias gradients). */
+int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
+                        int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t M, int64_t K3, int64_t hidden,
+                        int64_t K1p, const float* logs2, float f2, const float* logs1, float f1, const void* h2,
+                        const void* h1, void* d2, void* d1, int64_t ldh, void* da1, int64_t ldda1, float* dbias2,
+                        float* dbias1, void* stream);
+
 /* ---- Coupling: model.py:105-115 (fwd) / 131-140 (rev) --------------------------------------
  * h[n,co,y,x] = (u + bias3[co]) * exp(f*logs3[co]),  u = 3x3 tap gather-sum of P (ldp floats/row,
  * column tap*Cout+co), i.e. Conv2dZeros (module.py:295-296).

@@ -1,0 +1,618 @@
+// The coupling network f() (reference network/module.py:300-319) as ONE tcgen05 kernel per direction, sm_100a.
+//
+// Forward, per 128-pixel tile (hidden = 512):
+//   GEMM1  acc[128][512] = a1[128][K1] . W1[512][K1]^T        conv1 3x3 in im2col form, SS-mode MMA, eight 64-column chunks
+//   EPI1   h1 = relu(acc*s1 + t1) -> bf16 -> TMEM (tcgen05.st)  (+ optional TMA store of h1 for the backward pass)
+//   GEMM2  acc[128][512] = h1 . W2[512][512]^T                 conv2 1x1, **A operand read from TMEM** (TS-mode MMA)
+//   EPI2   h2 = relu(acc*s2 + t2) -> bf16 -> 16 KB shared-memory chunk (K-major, SWIZZLE_128B) (+ optional TMA store)
+//   GEMM3  P3[128][N3] += h2 chunk . W3[N3][chunk]^T           conv3 as nine pointwise GEMMs folded into N (tap form)
+//   EPI3   P3 fp32 -> staging -> TMA store
+// so h1 / h2 never touch HBM when sampling and are written exactly once (never re-read) when training.
+//
+// Backward (dgrad chain), same skeleton with other operands and epilogues:
+//   GEMM1  d_h2 = dP3[128][K3] . W3t[512][K3]^T ; EPI1: d2 = [h2 > 0] * d_h2 * s2 -> TMEM + TMA store (wgrad operand)
+//   GEMM2  d_h1 = d2 . W2t^T                    ; EPI2: d1 = [h1 > 0] * d_h1 * s1 -> smem chunk + TMA store
+//   GEMM3  dA1[128][K1p] += d1 chunk . W1t[K1p][chunk]^T ; EPI3: bf16 store
+//
+// Roles (320 threads, one CTA per SM, persistent over tiles):
+//   warp 0      TMA producer: the tile's A operand (resident for the whole tile) + every weight box, in issue order,
+//               through a ring of 16 KB stages
+//   warp 1      MMA issuer (one lane)
+//   warps 2..9  epilogue: two groups of four warps (one warp per TMEM lane quarter); group g owns the chunks c = g mod 2,
+//               accumulator buffer g and shared-memory chunk buffers b = g mod 2
+// TMEM (512 columns): [0,256) h1 / d2 as bf16 pairs, [256,320) + [320,384) chunk accumulators (ping-pong),
+//   [384,512) GEMM3 accumulator.  When N3 > 128 (level 2 forward: 9*24 = 216) GEMM3's accumulator aliases the
+//   h1 columns instead: all eight h2 chunks stay in shared memory and GEMM3 runs after GEMM2 ("deferred").
+#include "tc_common.cuh"
+#include "gemm_epilogue.cuh"
+
+namespace glowk {
+namespace cnet {
+
+using namespace tc;
+
+constexpr int HID = 512;
+constexpr int NC = 64;                    // chunk width (columns of GEMM1 / GEMM2 per accumulator buffer)
+constexpr int NCHUNK = HID / NC;          // 8
+constexpr int STAGE_BYTES = 16384;
+constexpr int BOX_BYTES = 8192;           // one [64 n][64 k] bf16 weight box
+constexpr int HB_BYTES = 16384;           // one [128][64] bf16 chunk
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int COL_H = 0, COL_ACC0 = 256, COL_ACC1 = 320, COL_C3 = 384;
+constexpr int MAX_STAGES = 8, MAX_HB = 8;
+
+enum { MODE_FWD = 0, MODE_BWD = 1 };
+
+struct Shared {
+  uint64_t ring_full[MAX_STAGES], ring_empty[MAX_STAGES];
+  uint64_t a_full, a_empty;
+  uint64_t acc_full[2], acc_empty[2];
+  uint64_t h1_full;
+  uint64_t h2_full[MAX_HB], h2_empty[MAX_HB];
+  uint64_t c3_full, c3_empty;
+  uint64_t y_bar[EPI_WARPS];
+  uint32_t tmem_base;
+};
+
+struct Params {
+  int M, K1B, N3, NH, nhb, c3_col, deferred, nstages;
+  int save1, save2;
+  const float *bias1, *logs1, *bias2, *logs2;
+  float f1, f2;
+  float *dbias1, *dbias2;     // backward: column sums of the stored d2 (EPI1) / d1 (EPI2), nullable
+};
+
+__device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// 128-byte row `lane` of a [32 rows][128 B] SWIZZLE_128B box: 16-byte piece j lives at (j ^ (lane & 7)) * 16
+__device__ __forceinline__ void store_row_sw128(uint8_t* box, int lane, const uint32_t (&w)[32]) {
+  uint8_t* row = box + lane * 128;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) * 16)) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+
+// Column sums of a [32 rows][64 bf16] SWIZZLE_128B box: lane l sums columns 2l, 2l+1 (bank-conflict free: for a
+// fixed row the 32 lanes read the 32 distinct words of that row) and adds them to acc[2l], acc[2l+1] in shared memory.
+__device__ __forceinline__ void box_colsum_bf16(const uint8_t* box, int lane, float* acc) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(box + r * 128 + (((lane >> 2) ^ (r & 7)) * 16) + (lane & 3) * 4);
+    const float2 v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+    s0 += v.x; s1 += v.y;
+  }
+  atomicAdd(acc + 2 * lane, s0);
+  atomicAdd(acc + 2 * lane + 1, s1);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
+                  const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
+                  const __grid_constant__ CUtensorMap tm_o1, const __grid_constant__ CUtensorMap tm_o2,
+                  const __grid_constant__ CUtensorMap tm_o3, const __grid_constant__ CUtensorMap tm_y1,
+                  const __grid_constant__ CUtensorMap tm_y2, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr bool BWD = MODE == MODE_BWD;
+  uint8_t* a_smem = smem;                                          // K1B boxes [128][64] bf16
+  uint8_t* ring = a_smem + (size_t)p.K1B * 16384;
+  uint8_t* hb = ring + (size_t)p.nstages * STAGE_BYTES;            // nhb chunk buffers [128][64] bf16
+  uint8_t* ysm = hb + (size_t)p.nhb * HB_BYTES;                    // BWD: one [32][64] bf16 mask box per epilogue warp
+  float* s_vec = reinterpret_cast<float*>(ysm + (BWD ? EPI_WARPS * 4096 : 0));
+  float* s_sc1 = s_vec;                 // [512] exp(f*logs)
+  float* s_sc2 = s_vec + HID;
+  float* s_x1 = s_vec + 2 * HID;        // FWD: shift = bias*scale ; BWD: column sums (dbias)
+  float* s_x2 = s_vec + 3 * HID;
+  Shared* sh = reinterpret_cast<Shared*>(s_vec + 4 * HID);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
+  const int num_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int upt = NCHUNK / p.nhb;                                  // uses of one chunk buffer per tile
+
+  if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_a); prefetch_tensormap(&tm_w1); prefetch_tensormap(&tm_w2); prefetch_tensormap(&tm_w3);
+    prefetch_tensormap(&tm_o3);
+    if (BWD || p.save1) prefetch_tensormap(&tm_o1);
+    if (BWD || p.save2) prefetch_tensormap(&tm_o2);
+    if (BWD) { prefetch_tensormap(&tm_y1); prefetch_tensormap(&tm_y2); }
+    for (int s = 0; s < p.nstages; ++s) { mbar_init(&sh->ring_full[s], 1); mbar_init(&sh->ring_empty[s], 1); }
+    mbar_init(&sh->a_full, 1); mbar_init(&sh->a_empty, 1);
+    for (int g = 0; g < 2; ++g) { mbar_init(&sh->acc_full[g], 1); mbar_init(&sh->acc_empty[g], 4); }
+    mbar_init(&sh->h1_full, 4 * NCHUNK);
+    for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], 4); mbar_init(&sh->h2_empty[b], 1); }
+    mbar_init(&sh->c3_full, 1); mbar_init(&sh->c3_empty, EPI_WARPS);
+    for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < HID; i += THREADS) {
+    const float sc1 = expf(p.logs1[i] * p.f1), sc2 = expf(p.logs2[i] * p.f2);
+    s_sc1[i] = sc1; s_sc2[i] = sc2;
+    s_x1[i] = BWD ? 0.f : p.bias1[i] * sc1;
+    s_x2[i] = BWD ? 0.f : p.bias2[i] * sc2;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      auto next_stage = [&]() { if (++stage == p.nstages) { stage = 0; phase ^= 1; } };
+      auto fill_w3 = [&](int cc) {
+        for (int h = 0; h < p.NH; ++h) {
+          mbar_wait(&sh->ring_empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)p.N3 * 128u);
+          tma_load_2d(&tm_w3, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES, cc * NC, h * p.N3);
+          next_stage();
+        }
+      };
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        mbar_wait(&sh->a_empty, (tcount & 1) ^ 1);
+        mbar_arrive_expect_tx(&sh->a_full, (uint32_t)p.K1B * 16384u);
+        for (int kb = 0; kb < p.K1B; ++kb)
+          tma_load_2d(&tm_a, &sh->a_full, a_smem + (size_t)kb * 16384, kb * BLOCK_K, tile * BLOCK_M);
+        for (int c = 0; c < NCHUNK; ++c)
+          for (int kb = 0; kb < p.K1B; kb += 2) {
+            const int nb = p.K1B - kb < 2 ? 1 : 2;
+            mbar_wait(&sh->ring_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)nb * BOX_BYTES);
+            for (int b = 0; b < nb; ++b)
+              tma_load_2d(&tm_w1, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES + b * BOX_BYTES,
+                          (kb + b) * BLOCK_K, c * NC);
+            next_stage();
+          }
+        for (int c = 0; c < NCHUNK; ++c) {
+          for (int kp = 0; kp < HID / 128; ++kp) {
+            mbar_wait(&sh->ring_empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&sh->ring_full[stage], 2u * BOX_BYTES);
+            tma_load_2d(&tm_w2, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES, kp * 128, c * NC);
+            tma_load_2d(&tm_w2, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES + BOX_BYTES, kp * 128 + 64, c * NC);
+            next_stage();
+          }
+          if (!p.deferred && c >= 1) fill_w3(c - 1);
+        }
+        if (!p.deferred) fill_w3(NCHUNK - 1);
+        else for (int c = 0; c < NCHUNK; ++c) fill_w3(c);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs this loop (warp-uniform control flow: descriptors and addresses stay in uniform registers);
+    // one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
+    {
+      const uint32_t idesc_c = make_idesc(NC, 0, 0);
+      const uint32_t idesc_3 = make_idesc(p.N3, 0, 0);
+      const uint32_t a_base = smem_u32(a_smem), ring_base = smem_u32(ring), hb_base = smem_u32(hb);
+      int stage = 0; uint32_t phase = 0;
+      auto next_stage = [&]() { if (++stage == p.nstages) { stage = 0; phase ^= 1; } };
+      uint32_t tcount = 0;
+      auto gemm3_partial = [&](int cc) {
+        const int b = cc % p.nhb;
+        const uint32_t idx = tcount * (uint32_t)upt + (uint32_t)(cc / p.nhb);
+        mbar_wait(&sh->h2_full[b], idx & 1);
+        if (cc == 0 && !p.deferred) mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint64_t adesc = make_smem_desc(hb_base + (uint32_t)b * HB_BYTES, 16, 1024);
+        for (int h = 0; h < p.NH; ++h) {
+          mbar_wait(&sh->ring_full[stage], phase);
+          tcgen05_fence_after();
+          const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
+          const uint32_t d = tmem_base + (uint32_t)(p.c3_col + h * p.N3);
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              tcgen05_mma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_3, (cc | k) != 0);
+            tcgen05_commit(&sh->ring_empty[stage]);
+          }
+          __syncwarp();
+          next_stage();
+        }
+        if (elect_one_sync()) tcgen05_commit(&sh->h2_empty[b]);
+        __syncwarp();
+      };
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        // ---- GEMM1: A from shared memory
+        mbar_wait(&sh->a_full, tcount & 1);
+        tcgen05_fence_after();
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int g = c & 1;
+          const uint32_t idx = tcount * 8u + (uint32_t)(c >> 1);
+          mbar_wait(&sh->acc_empty[g], (idx & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(g ? COL_ACC1 : COL_ACC0);
+          for (int kb = 0; kb < p.K1B; kb += 2) {
+            const int nb = p.K1B - kb < 2 ? 1 : 2;
+            mbar_wait(&sh->ring_full[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)kb * 16384u, 16, 1024);
+            const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                tcgen05_mma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_c, (kb | k) != 0);
+              if (nb == 2) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // second box: A +16 KB, B +8 KB (descriptor units of 16 B)
+                  tcgen05_mma_bf16(d, adesc + (uint64_t)(1024 + k * 2), bdesc + (uint64_t)(512 + k * 2), idesc_c, 1u);
+              }
+              tcgen05_commit(&sh->ring_empty[stage]);
+            }
+            __syncwarp();
+            next_stage();
+          }
+          if (elect_one_sync()) tcgen05_commit(&sh->acc_full[g]);
+          __syncwarp();
+        }
+        if (elect_one_sync()) tcgen05_commit(&sh->a_empty);
+        __syncwarp();
+        // ---- GEMM2: A = h1 / d2 in TMEM (bf16 pairs: 16 k = 8 columns); GEMM3 partial sums interleaved
+        mbar_wait(&sh->h1_full, tcount & 1);
+        tcgen05_fence_after();
+        for (int c = 0; c < NCHUNK; ++c) {
+          const int g = c & 1;
+          const uint32_t idx = tcount * 8u + 4u + (uint32_t)(c >> 1);
+          mbar_wait(&sh->acc_empty[g], (idx & 1) ^ 1);
+          tcgen05_fence_after();
+          const uint32_t d = tmem_base + (uint32_t)(g ? COL_ACC1 : COL_ACC0);
+#pragma unroll
+          for (int kp = 0; kp < HID / 128; ++kp) {
+            mbar_wait(&sh->ring_full[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
+            const uint32_t ta = tmem_base + (uint32_t)(COL_H + kp * 64);
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k)      // 8 k-steps of 16: box k/4 (+8 KB = +512 descriptor units), 32 B steps inside
+                tcgen05_mma_bf16_ts(d, ta + (uint32_t)(k * 8), bdesc + (uint64_t)((k >> 2) * 512 + (k & 3) * 2), idesc_c,
+                                    (kp | k) != 0);
+              tcgen05_commit(&sh->ring_empty[stage]);
+            }
+            __syncwarp();
+            next_stage();
+          }
+          if (elect_one_sync()) tcgen05_commit(&sh->acc_full[g]);
+          __syncwarp();
+          if (!p.deferred && c >= 1) gemm3_partial(c - 1);
+        }
+        if (!p.deferred) gemm3_partial(NCHUNK - 1);
+        else for (int c = 0; c < NCHUNK; ++c) gemm3_partial(c);
+        if (elect_one_sync()) tcgen05_commit(&sh->c3_full);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int ew = warp - 2, g = ew >> 2, quarter = warp & 3;      // TMEM lane quarter = warp % 4 (hardware rule)
+    const int row0 = quarter * 32;
+    const uint32_t lane_taddr = tmem_base + ((uint32_t)row0 << 16);
+    const uint32_t acc_col = g ? COL_ACC1 : COL_ACC0;
+    uint8_t* stg = hb + (size_t)g * HB_BYTES + (size_t)quarter * 4096;   // this warp's 32 rows of chunk buffer g
+    uint8_t* ybox = ysm + (size_t)ew * 4096;
+    uint32_t ycount = 0;
+    // mask boxes (BWD): this warp's sequence is tile-major, then EPI1 chunks g, g+2, .. (y1), then EPI2 chunks (y2)
+    auto issue_y = [&](int tile, int ph, int c) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&sh->y_bar[ew], 4096);
+        tma_load_2d(ph ? &tm_y2 : &tm_y1, &sh->y_bar[ew], ybox, c * NC, tile * BLOCK_M + row0);
+      }
+    };
+    auto issue_next_y = [&](int tile, int ph, int c) {
+      c += 2;
+      if (c >= NCHUNK) { c = g; ph ^= 1; if (ph == 0) tile += gridDim.x; }
+      if (tile < num_tiles) issue_y(tile, ph, c);
+    };
+    if (BWD && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, g);
+
+    // accumulator chunk -> bf16 pairs (64 columns of this lane's row)
+    auto epilogue_chunk = [&](int c, int ph, uint32_t (&pk)[32]) {
+      uint32_t r0[32], r1[32];
+      tmem_ld32_async(lane_taddr + acc_col, r0);
+      tmem_ld32_async(lane_taddr + acc_col + 32, r1);
+      if (BWD) mbar_wait(&sh->y_bar[ew], ycount & 1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->acc_empty[g]);              // accumulator buffer is in registers now
+      const float* sc = (ph ? s_sc2 : s_sc1) + c * NC;
+      if (!BWD) {
+        const float* sf = (ph ? s_x2 : s_x1) + c * NC;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(fmaf(__uint_as_float(r0[2 * j]), sc[2 * j], sf[2 * j]), 0.f);
+          const float b = fmaxf(fmaf(__uint_as_float(r0[2 * j + 1]), sc[2 * j + 1], sf[2 * j + 1]), 0.f);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = fmaxf(fmaf(__uint_as_float(r1[2 * j]), sc[32 + 2 * j], sf[32 + 2 * j]), 0.f);
+          const float b = fmaxf(fmaf(__uint_as_float(r1[2 * j + 1]), sc[32 + 2 * j + 1], sf[32 + 2 * j + 1]), 0.f);
+          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+          pk[16 + j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+      } else {
+        const uint8_t* yrow = ybox + lane * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 yraw = *reinterpret_cast<const uint4*>(yrow + ((j4 ^ (lane & 7)) * 16));
+          const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&yraw);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 yv = __bfloat1622float2(yp[u]);
+            const int j = j4 * 8 + u * 2;                          // column within the chunk
+            const float ra = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+            const float rb = __uint_as_float(j < 32 ? r0[j + 1] : r1[j - 31]);
+            const float a = (yv.x > 0.f ? ra : 0.f) * sc[j];
+            const float b = (yv.y > 0.f ? rb : 0.f) * sc[j + 1];
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+        }
+        ++ycount;
+        __syncwarp();                                              // every lane has read the mask box
+      }
+    };
+
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int grow = tile * BLOCK_M + row0;
+      // ---- EPI1: chunk accumulators -> bf16 -> TMEM (A operand of GEMM2)
+      for (int c = g; c < NCHUNK; c += 2) {
+        const uint32_t idx = tcount * 8u + (uint32_t)(c >> 1);
+        mbar_wait(&sh->acc_full[g], idx & 1);
+        tcgen05_fence_after();
+        uint32_t pk[32];
+        epilogue_chunk(c, 0, pk);
+        if (BWD) issue_next_y(tile, 0, c);                         // next mask box of this warp's sequence
+        if (p.deferred && c == g) {                                // GEMM3's accumulator of the previous tile aliases h1
+          mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
+          tcgen05_fence_after();
+        }
+        tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2)), pk);
+        if (BWD || p.save1) {
+          if (lane == 0) tma_store_wait_read<0>();                 // my previous store out of this staging box
+          __syncwarp();
+          store_row_sw128(stg, lane, pk);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tm_o1, stg, c * NC, grow); tma_store_commit(); }
+          if (BWD && p.dbias2) box_colsum_bf16(stg, lane, s_x2 + c * NC);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->h1_full);
+      }
+      // ---- EPI2: chunk accumulators -> bf16 -> shared-memory chunk (A operand of GEMM3)
+      for (int c = g; c < NCHUNK; c += 2) {
+        const uint32_t idx = tcount * 8u + 4u + (uint32_t)(c >> 1);
+        mbar_wait(&sh->acc_full[g], idx & 1);
+        tcgen05_fence_after();
+        uint32_t pk[32];
+        epilogue_chunk(c, 1, pk);
+        if (BWD) issue_next_y(tile, 1, c);
+        const int b = c % p.nhb;
+        const uint32_t hidx = tcount * (uint32_t)upt + (uint32_t)(c / p.nhb);
+        mbar_wait(&sh->h2_empty[b], (hidx & 1) ^ 1);               // GEMM3 partial that last read this buffer retired
+        if (lane == 0) tma_store_wait_read<0>();                   // ... and so has my TMA store out of it
+        __syncwarp();
+        uint8_t* slice = hb + (size_t)b * HB_BYTES + (size_t)quarter * 4096;
+        store_row_sw128(slice, lane, pk);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (BWD || p.save2) { tma_store_2d(&tm_o2, slice, c * NC, grow); tma_store_commit(); }
+          mbar_arrive(&sh->h2_full[b]);
+        }
+        if (BWD && p.dbias1) box_colsum_bf16(slice, lane, s_x1 + c * NC);
+      }
+      // ---- EPI3: GEMM3 accumulator -> global
+      mbar_wait(&sh->c3_full, tcount & 1);
+      tcgen05_fence_after();
+      const int n3tot = p.NH * p.N3;
+      if (!BWD) {
+        for (int j = g; j * 32 < n3tot; j += 2) {
+          uint32_t r[32];
+          tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 32), r);
+          if (lane == 0) tma_store_wait_read<0>();
+          tmem_ld_wait();
+          __syncwarp();
+          store_row_sw128(stg, lane, r);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tm_o3, stg, j * 32, grow); tma_store_commit(); }   // columns >= N, rows >= M clipped
+        }
+      } else {
+        for (int j = g; j * 64 < n3tot; j += 2) {
+          uint32_t r0[32], r1[32], pk[32];
+          tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 64), r0);
+          tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 64 + 32), r1);
+          if (lane == 0) tma_store_wait_read<0>();
+          tmem_ld_wait();
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * u]), __uint_as_float(r0[2 * u + 1]));
+            const __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * u]), __uint_as_float(r1[2 * u + 1]));
+            pk[u] = *reinterpret_cast<const uint32_t*>(&h0);
+            pk[16 + u] = *reinterpret_cast<const uint32_t*>(&h1);
+          }
+          store_row_sw128(stg, lane, pk);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tm_o3, stg, j * 64, grow); tma_store_commit(); }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->c3_empty);
+    }
+    if (BWD) {
+      // one global atomic per column per CTA
+      epi_bar_sync<32 * EPI_WARPS>();
+      const int et = (int)threadIdx.x - 64;
+      for (int n = et; n < HID; n += 32 * EPI_WARPS) {
+        if (p.dbias2 && s_x2[n] != 0.f) atomicAdd(p.dbias2 + n, s_x2[n]);
+        if (p.dbias1 && s_x1[n] != 0.f) atomicAdd(p.dbias1 + n, s_x1[n]);
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+struct Variant { int NH, N3, nhb, c3_col, deferred, nstages; size_t smem; };
+
+static bool pick_variant(int mode, int64_t K1, int64_t n3tot, Variant* v) {
+  if (K1 <= 0 || K1 % 64 != 0 || n3tot <= 0 || n3tot % 16 != 0) return false;
+  if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
+  else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 8; v->c3_col = COL_H; v->deferred = 1; }
+  else return false;
+  const size_t fixed = (size_t)(K1 / 64) * 16384 + (size_t)v->nhb * HB_BYTES + (mode == MODE_BWD ? EPI_WARPS * 4096 : 0) +
+                       4 * HID * sizeof(float) + sizeof(Shared) + 64;
+  const size_t budget = 227 * 1024;
+  if (fixed + 3 * (size_t)STAGE_BYTES > budget) return false;
+  int s = (int)((budget - fixed) / STAGE_BYTES);
+  v->nstages = s > MAX_STAGES ? MAX_STAGES : s;
+  v->smem = fixed + (size_t)v->nstages * STAGE_BYTES;
+  return true;
+}
+
+bool chain_supported(int backward, int64_t K1, int64_t hidden, int64_t n3tot) {
+  Variant v;
+  return hidden == HID && tc_available() && pick_variant(backward ? MODE_BWD : MODE_FWD, K1, n3tot, &v);
+}
+
+template <int MODE>
+static int launch_chain(const CUtensorMap* tm, const Params& p, size_t smem, cudaStream_t st) {
+  auto kern = cnet_chain_kernel<MODE>;
+  GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, THREADS, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], tm[6], tm[7], tm[8], p);
+  GLOWK_CHECK_LAUNCH("glowk_cnet_chain(tcgen05)");
+  return GLOWK_OK;
+}
+
+// A: [M][K1] (lda), W1: [512][K1], W2: [512][512], W3: [n3tot][512]; o1/o2/y1/y2: [M][512] bf16 (ldh);
+// o3: forward fp32 [M][n3tot] (ldo3), backward bf16 [M][n3tot] (ldo3).
+int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
+                 const void* W3, int64_t ldw3, int64_t M, int64_t K1, int64_t n3tot, const float* bias1,
+                 const float* logs1, float f1, const float* bias2, const float* logs2, float f2, void* o1, void* o2,
+                 int64_t ldh, const void* y1, const void* y2, void* o3, int64_t ldo3, float* dbias1, float* dbias2,
+                 cudaStream_t st) {
+  const int mode = backward ? MODE_BWD : MODE_FWD;
+  Variant v;
+  if (!pick_variant(mode, K1, n3tot, &v))
+    return fail(GLOWK_EUNSUP, "glowk_cnet_%s: unsupported shape K1=%lld N3=%lld", backward ? "backward" : "forward",
+                (long long)K1, (long long)n3tot);
+  GLOWK_CHECK_ARG(M > 0 && M < (1ll << 31), "glowk_cnet: bad M");
+  GLOWK_CHECK_ARG(lda % 8 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0 && ldw3 % 8 == 0 && ldh % 8 == 0,
+                  "glowk_cnet: bf16 row pitches must be multiples of 8 elements");
+  GLOWK_CHECK_ARG((((uintptr_t)A | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)W3 | (uintptr_t)o1 | (uintptr_t)o2 |
+                    (uintptr_t)o3 | (uintptr_t)y1 | (uintptr_t)y2) % 16) == 0, "glowk_cnet: operands must be 16-byte aligned");
+  GLOWK_CHECK_ARG((ldo3 * (backward ? 2 : 4)) % 16 == 0, "glowk_cnet: output row pitch must be a multiple of 16 bytes");
+  CUtensorMap tm[9];
+  int rc;
+  const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  if ((rc = make_map_2d(&tm[0], A, BF, 2, (uint64_t)K1, (uint64_t)M, (uint64_t)lda, 64, 128))) return rc;
+  if ((rc = make_map_2d(&tm[1], W1, BF, 2, (uint64_t)K1, (uint64_t)HID, (uint64_t)ldw1, 64, 64))) return rc;
+  if ((rc = make_map_2d(&tm[2], W2, BF, 2, (uint64_t)HID, (uint64_t)HID, (uint64_t)ldw2, 64, 64))) return rc;
+  if ((rc = make_map_2d(&tm[3], W3, BF, 2, (uint64_t)HID, (uint64_t)n3tot, (uint64_t)ldw3, 64, (uint32_t)v.N3))) return rc;
+  const void* o1m = o1 ? o1 : A;   // unused maps still need a valid encoding
+  const void* o2m = o2 ? o2 : A;
+  if (o1) { if ((rc = make_map_2d(&tm[4], o1m, BF, 2, (uint64_t)HID, (uint64_t)M, (uint64_t)ldh, 64, 32))) return rc; } else tm[4] = tm[0];
+  if (o2) { if ((rc = make_map_2d(&tm[5], o2m, BF, 2, (uint64_t)HID, (uint64_t)M, (uint64_t)ldh, 64, 32))) return rc; } else tm[5] = tm[0];
+  if (backward) {
+    if ((rc = make_map_2d(&tm[6], o3, BF, 2, (uint64_t)n3tot, (uint64_t)M, (uint64_t)ldo3, 64, 32))) return rc;
+    if ((rc = make_map_2d(&tm[7], y1, BF, 2, (uint64_t)HID, (uint64_t)M, (uint64_t)ldh, 64, 32))) return rc;
+    if ((rc = make_map_2d(&tm[8], y2, BF, 2, (uint64_t)HID, (uint64_t)M, (uint64_t)ldh, 64, 32))) return rc;
+  } else {
+    if ((rc = make_map_2d(&tm[6], o3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)n3tot, (uint64_t)M, (uint64_t)ldo3, 32, 32))) return rc;
+    tm[7] = tm[0]; tm[8] = tm[0];
+  }
+  Params p;
+  p.M = (int)M; p.K1B = (int)(K1 / 64); p.N3 = v.N3; p.NH = v.NH; p.nhb = v.nhb; p.c3_col = v.c3_col;
+  p.deferred = v.deferred; p.nstages = v.nstages;
+  p.save1 = o1 != nullptr; p.save2 = o2 != nullptr;
+  p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
+  p.dbias1 = dbias1; p.dbias2 = dbias2;
+  return backward ? launch_chain<MODE_BWD>(tm, p, v.smem, st) : launch_chain<MODE_FWD>(tm, p, v.smem, st);
+}
+
+}  // namespace cnet
+}  // namespace glowk
+
+using namespace glowk;
+
+extern "C" int glowk_cnet_fused_supported(int backward, int64_t K1, int64_t hidden, int64_t N3) {
+  return cnet::chain_supported(backward, K1, hidden, N3) ? 1 : 0;
+}
+
+extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2,
+                                  int64_t ldw2, const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden,
+                                  int64_t N3, const float* bias1, const float* logs1, float f1, const float* bias2,
+                                  const float* logs2, float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save,
+                                  int64_t ldh, void* stream) {
+  if (M == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(a1 && w1 && w2 && w3 && p3 && bias1 && logs1 && bias2 && logs2, "glowk_cnet_forward: null pointer");
+  GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_forward: hidden must be %d", cnet::HID);
+  GLOWK_CHECK_ARG(lda >= K1 && ldw1 >= K1 && ldw2 >= hidden && ldw3 >= hidden && ldp3 >= N3, "glowk_cnet_forward: leading dimensions too small");
+  GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward: ldh too small");
+  return cnet::chain_launch(0, a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1, bias2, logs2, f2,
+                            h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr, nullptr,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
+                                   int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t M, int64_t K3,
+                                   int64_t hidden, int64_t K1p, const float* logs2, float f2, const float* logs1,
+                                   float f1, const void* h2, const void* h1, void* d2, void* d1, int64_t ldh,
+                                   void* da1, int64_t ldda1, float* dbias2, float* dbias1, void* stream) {
+  if (M == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(d3col && w3t && w2t && w1t && logs2 && logs1 && h2 && h1 && d2 && d1 && da1, "glowk_cnet_backward: null pointer");
+  GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_backward: hidden must be %d", cnet::HID);
+  GLOWK_CHECK_ARG(ldd3 >= K3 && ldw3t >= K3 && ldw2t >= hidden && ldw1t >= hidden && ldh >= hidden && ldda1 >= K1p,
+                  "glowk_cnet_backward: leading dimensions too small");
+  // chain order: GEMM1 uses (w3t, logs2 / h2 mask), GEMM2 (w2t, logs1 / h1 mask), GEMM3 w1t
+  return cnet::chain_launch(1, d3col, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2, nullptr,
+                            logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
+}

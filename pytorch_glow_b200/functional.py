@@ -210,6 +210,44 @@ def gemm_wgrad(a, b, mo, no, dw):
     return dw
 
 
+def cnet_fused_supported(backward, k1, hidden, n3):
+    """True iff glowk_cnet_forward / glowk_cnet_backward serve this shape on the current device."""
+    return bool(_C.lib().glowk_cnet_fused_supported(int(bool(backward)), int(k1), int(hidden), int(n3)))
+
+
+def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2, ldp3=None, save=False, ldh=None):
+    """The coupling net's three convs in one tcgen05 kernel (glowk_cnet_forward).  a1: [M][k1p] bf16 im2col rows.
+    Returns (p3 [M][ldp3] fp32, h1, h2) with h1/h2 [M][ldh] bf16 when `save`, else None."""
+    check_cuda(a1, w1, w2, w3)
+    assert a1.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16
+    m, k1 = a1.shape
+    ldp3 = n3 if ldp3 is None else ldp3
+    ldh = hidden if ldh is None else ldh
+    p3 = torch.empty(m, ldp3, device=a1.device, dtype=torch.float32)
+    h1 = torch.empty(m, ldh, device=a1.device, dtype=torch.bfloat16) if save else None
+    h2 = torch.empty(m, ldh, device=a1.device, dtype=torch.bfloat16) if save else None
+    call("glowk_cnet_forward", ptr(a1), k1, ptr(w1), w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], m, k1,
+         hidden, n3, ptr(bias1), ptr(logs1), float(f1), ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1),
+         ptr(h2), ldh)
+    return p3, h1, h2
+
+
+def cnet_backward(d3col, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h1, dbias2=None, dbias1=None):
+    """The dgrad chain of the coupling net in one tcgen05 kernel (glowk_cnet_backward).
+    Returns (d2, d1 [M][ldh] bf16, da1 [M][k1p] bf16)."""
+    check_cuda(d3col, w3t, w2t, w1t, h2, h1)
+    m, k3 = d3col.shape
+    ldh = h1.shape[1]
+    assert h2.shape[1] == ldh and d3col.dtype == torch.bfloat16
+    d2 = torch.empty(m, ldh, device=d3col.device, dtype=torch.bfloat16)
+    d1 = torch.empty(m, ldh, device=d3col.device, dtype=torch.bfloat16)
+    da1 = torch.empty(m, k1p, device=d3col.device, dtype=torch.bfloat16)
+    call("glowk_cnet_backward", ptr(d3col), k3, ptr(w3t), w3t.shape[1], ptr(w2t), w2t.shape[1], ptr(w1t), w1t.shape[1],
+         m, k3, hidden, k1p, ptr(logs2), float(f2), ptr(logs1), float(f1), ptr(h2), ptr(h1), ptr(d2), ptr(d1), ldh,
+         ptr(da1), k1p, ptr(dbias2), ptr(dbias1))
+    return d2, d1, da1
+
+
 # ------------------------------------------------------------------ coupling / logdet / prior
 def coupling(p_rows, bias3, logs3, z, affine, reverse, logscale_factor=3.0, save_h=False):
     """In-place coupling on z[:, C/2:] from the tap-GEMM output p_rows.  model.py:105-115 / 131-140.

@@ -1,0 +1,105 @@
+"""The fused coupling-network kernels (glowk_cnet_forward / glowk_cnet_backward, csrc/cnet_fused_sm100.cu) against
+(i) the three-GEMM path they replace -- bit for bit on the same bf16 operands -- and (ii) a plain fp32 torch
+restatement of network/module.py:300-319 in its GEMM form, with the bf16 tolerance written out."""
+import pytest
+import torch
+
+from pytorch_glow_b200 import _C
+from pytorch_glow_b200 import functional as K
+
+pytestmark = pytest.mark.gpu
+
+HID = 512
+
+
+def _mk(m, k1, n3, seed):
+    g = torch.Generator().manual_seed(seed)
+    dev = "cuda"
+    a1 = (torch.randn(m, k1, generator=g) * 0.5).to(dev).bfloat16()
+    w1 = (torch.randn(HID, k1, generator=g) * 0.05).to(dev).bfloat16()
+    w2 = (torch.randn(HID, HID, generator=g) * 0.05).to(dev).bfloat16()
+    w3 = (torch.randn(n3, HID, generator=g) * 0.05).to(dev).bfloat16()
+    vec = lambda s: (torch.randn(HID, generator=g) * s).to(dev)
+    return a1, w1, w2, w3, vec(0.1), vec(0.1), vec(0.1), vec(0.1)
+
+
+def _three_gemms(a1, w1, w2, w3, b1, l1, b2, l2, n3, k1):
+    h1 = K.gemm(a1, w1, HID, k1, _C.EPI_ACTNORM_RELU, b1, l1, 3.0, out_dtype=_C.BF16)
+    h2 = K.gemm(h1, w2, HID, HID, _C.EPI_ACTNORM_RELU, b2, l2, 3.0, out_dtype=_C.BF16)
+    p3 = K.gemm(h2, w3, n3, HID, _C.EPI_STORE, out_dtype=_C.F32)
+    return h1, h2, p3
+
+
+# (pixels, K1 = padded 9*Cin, N3 = padded 9*Cout): level 1 affine (54 -> 64, 108 -> 112), level 1 additive (54 -> 64),
+# a ragged last tile, more tiles than SMs, level 2 affine (108 -> 128, 216 -> 224: GEMM3 deferred), K1 = 256
+SHAPES = [(2048, 64, 112), (1024, 64, 64), (1000, 64, 112), (148 * 128 * 2 + 128, 64, 112), (768, 128, 224),
+          (300, 128, 128), (512, 256, 128), (256, 192, 16)]
+
+
+@pytest.mark.parametrize("m,k1,n3", SHAPES)
+@pytest.mark.parametrize("save", [False, True])
+def test_cnet_forward_matches_three_gemms(m, k1, n3, save):
+    if not _C.has_tcgen05():
+        pytest.skip("needs sm_100")
+    assert K.cnet_fused_supported(False, k1, HID, n3)
+    a1, w1, w2, w3, b1, l1, b2, l2 = _mk(m, k1, n3, 7 + m)
+    h1r, h2r, p3r = _three_gemms(a1, w1, w2, w3, b1, l1, b2, l2, n3, k1)
+    p3, h1, h2 = K.cnet_forward(a1, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0, save=save)
+    torch.cuda.synchronize()
+    if save:
+        assert torch.equal(h1, h1r), "h1 differs: max %g" % (h1.float() - h1r.float()).abs().max().item()
+        assert torch.equal(h2, h2r), "h2 differs: max %g" % (h2.float() - h2r.float()).abs().max().item()
+    else:
+        assert h1 is None and h2 is None
+    assert torch.equal(p3, p3r), "p3 differs: max %g" % (p3 - p3r).abs().max().item()
+    # fp32 restatement (bf16 operands, fp32 accumulate, bf16 rounding of the hidden activations)
+    f = lambda t: t.float()
+    h1t = torch.relu((f(a1) @ f(w1).t() + b1) * torch.exp(3.0 * l1)).bfloat16()
+    h2t = torch.relu((f(h1t) @ f(w2).t() + b2) * torch.exp(3.0 * l2)).bfloat16()
+    p3t = f(h2t) @ f(w3).t()
+    err = (p3 - p3t).abs().max().item()
+    assert err <= 2e-2 * max(1.0, p3t.abs().max().item()), err       # one-ulp bf16 flips of h1/h2 propagate
+
+
+def _mk_bwd(m, k3, k1p, seed):
+    g = torch.Generator().manual_seed(seed)
+    dev = "cuda"
+    d3 = (torch.randn(m, k3, generator=g) * 0.5).to(dev).bfloat16()
+    w3t = (torch.randn(HID, k3, generator=g) * 0.05).to(dev).bfloat16()
+    w2t = (torch.randn(HID, HID, generator=g) * 0.05).to(dev).bfloat16()
+    w1t = (torch.randn(k1p, HID, generator=g) * 0.05).to(dev).bfloat16()
+    h2 = torch.relu(torch.randn(m, HID, generator=g)).to(dev).bfloat16()
+    h1 = torch.relu(torch.randn(m, HID, generator=g)).to(dev).bfloat16()
+    l2 = (torch.randn(HID, generator=g) * 0.1).to(dev)
+    l1 = (torch.randn(HID, generator=g) * 0.1).to(dev)
+    return d3, w3t, w2t, w1t, h2, h1, l2, l1
+
+
+# (pixels, K3 = padded 9*Cout, K1p): level 1 affine (108 -> 128, 64), level 1 additive (54 -> 64), ragged,
+# many tiles, level 2 (216 -> 256, 128)
+BWD_SHAPES = [(2048, 128, 64), (1024, 64, 64), (1000, 128, 64), (148 * 128 + 256, 128, 64), (768, 256, 128)]
+
+
+@pytest.mark.parametrize("m,k3,k1p", BWD_SHAPES)
+def test_cnet_backward_matches_three_gemms(m, k3, k1p):
+    if not _C.has_tcgen05():
+        pytest.skip("needs sm_100")
+    assert K.cnet_fused_supported(True, k3, HID, k1p)
+    d3, w3t, w2t, w1t, h2, h1, l2, l1 = _mk_bwd(m, k3, k1p, 11 + m)
+    db2r = torch.zeros(HID, device="cuda")
+    db1r = torch.zeros(HID, device="cuda")
+    d2r = K.gemm(d3, w3t, HID, k3, _C.EPI_RELU_BWD, None, l2, 3.0, y=h2, dlogs=None, dbias=db2r, out_dtype=_C.BF16)
+    d1r = K.gemm(d2r, w2t, HID, HID, _C.EPI_RELU_BWD, None, l1, 3.0, y=h1, dlogs=None, dbias=db1r, out_dtype=_C.BF16)
+    da1r = K.gemm(d1r, w1t, k1p, HID, _C.EPI_STORE, out_dtype=_C.BF16)
+    db2 = torch.zeros(HID, device="cuda")
+    db1 = torch.zeros(HID, device="cuda")
+    d2, d1, da1 = K.cnet_backward(d3, w3t, w2t, w1t, HID, k1p, l2, 3.0, l1, 3.0, h2, h1, dbias2=db2, dbias1=db1)
+    torch.cuda.synchronize()
+    assert torch.equal(d2, d2r), "d2 differs: max %g" % (d2.float() - d2r.float()).abs().max().item()
+    assert torch.equal(d1, d1r), "d1 differs: max %g" % (d1.float() - d1r.float()).abs().max().item()
+    assert torch.equal(da1, da1r), "da1 differs: max %g" % (da1.float() - da1r.float()).abs().max().item()
+    # bias gradients = column sums of the STORED (bf16) gradients here; the GEMM epilogue sums before rounding
+    for got, stored, ref in ((db2, d2, db2r), (db1, d1, db1r)):
+        exact = stored.float().sum(0)
+        assert torch.allclose(got, exact, rtol=1e-4, atol=1e-3 * max(1.0, exact.abs().max().item()))
+        assert torch.allclose(got, ref, rtol=2e-2, atol=2e-2 * max(1.0, ref.abs().max().item()))
