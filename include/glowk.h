@@ -167,6 +167,11 @@ int glowk_gemm_wgrad(const void* A, int64_t lda, const void* B, int64_t ldb, int
  *   h1_save / h2_save : NULL when sampling; [M][ldh] bf16 to keep the activations for glowk_cnet_backward
  * Results are bit-identical to three glowk_gemm calls (EPI_ACTNORM_RELU, EPI_ACTNORM_RELU, EPI_STORE).
  * glowk_cnet_fused_supported(backward, K1, hidden, N3) tells whether a shape is served (else: glowk_gemm). */
+/* Profiling aid: with GLOWK_CNET_DEBUG=1 CTA 0 of the fused kernels records the cycles its roles spent waiting on
+ * each other (layout: csrc/cnet_fused_sm100.cu); this copies the 16 counters to a HOST array (synchronises). */
+int glowk_debug_cnet_trace(unsigned long long* out16_host);
+/* Same for the event timeline of one tile (GLOWK_CNET_DEBUG bit 16; 64 SM-clock stamps). */
+int glowk_debug_cnet_timeline(unsigned long long* out64_host);
 int glowk_cnet_fused_supported(int backward, int64_t K1, int64_t hidden, int64_t N3);
 int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2, int64_t ldw2,
                        const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden, int64_t N3,

@@ -43,6 +43,8 @@ SIGNATURES = {
     "glowk_gemm_ex": [_p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _p, _p, _f32, _p, _i64, _p, _p,
                       _p, _i32, _i64, _i32, _i32, _p],
     "glowk_gemm_wgrad": [_p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _p, _i64, _p],
+    "glowk_debug_cnet_trace": [_p],
+    "glowk_debug_cnet_timeline": [_p],
     "glowk_cnet_fused_supported": [_i32, _i64, _i64, _i64],
     "glowk_cnet_forward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32,
                            _p, _i64, _p, _p, _i64, _p],

@@ -1,10 +1,10 @@
 // The coupling network f() (reference network/module.py:300-319) as ONE tcgen05 kernel per direction, sm_100a.
 //
 // Forward, per 128-pixel tile (hidden = 512):
-//   GEMM1  acc[128][512] = a1[128][K1] . W1[512][K1]^T        conv1 3x3 in im2col form, SS-mode MMA, eight 64-column chunks
+//   GEMM1  acc[128][512] = a1[128][K1] . W1[512][K1]^T        conv1 3x3 in im2col form, SS-mode MMA, four 128-column chunks
 //   EPI1   h1 = relu(acc*s1 + t1) -> bf16 -> TMEM (tcgen05.st)  (+ optional TMA store of h1 for the backward pass)
 //   GEMM2  acc[128][512] = h1 . W2[512][512]^T                 conv2 1x1, **A operand read from TMEM** (TS-mode MMA)
-//   EPI2   h2 = relu(acc*s2 + t2) -> bf16 -> 16 KB shared-memory chunk (K-major, SWIZZLE_128B) (+ optional TMA store)
+//   EPI2   h2 = relu(acc*s2 + t2) -> bf16 -> 32 KB shared-memory chunk (K-major, SWIZZLE_128B) (+ optional TMA store)
 //   GEMM3  P3[128][N3] += h2 chunk . W3[N3][chunk]^T           conv3 as nine pointwise GEMMs folded into N (tap form)
 //   EPI3   P3 fp32 -> staging -> TMA store
 // so h1 / h2 never touch HBM when sampling and are written exactly once (never re-read) when training.
@@ -16,13 +16,17 @@
 //
 // Roles (320 threads, one CTA per SM, persistent over tiles):
 //   warp 0      TMA producer: the tile's A operand (resident for the whole tile) + every weight box, in issue order,
-//               through a ring of 16 KB stages
-//   warp 1      MMA issuer (one lane)
-//   warps 2..9  epilogue: two groups of four warps (one warp per TMEM lane quarter); group g owns the chunks c = g mod 2,
-//               accumulator buffer g and shared-memory chunk buffers b = g mod 2
-// TMEM (512 columns): [0,256) h1 / d2 as bf16 pairs, [256,320) + [320,384) chunk accumulators (ping-pong),
-//   [384,512) GEMM3 accumulator.  When N3 > 128 (level 2 forward: 9*24 = 216) GEMM3's accumulator aliases the
-//   h1 columns instead: all eight h2 chunks stay in shared memory and GEMM3 runs after GEMM2 ("deferred").
+//               through a ring of stages (one or two 16 KB boxes each)
+//   warp 1      MMA issuer: the warp runs warp-uniform, one elected lane issues (see elect_one_sync)
+//   warps 2..9  epilogue: warp (g, q) owns TMEM lane quarter q and the column half g of every 128-column chunk
+// TMEM (512 columns): [0,256) h1 / d2 as bf16 pairs; [256,384) chunk accumulator; [384,512) GEMM3's accumulator,
+//   which doubles as the second chunk accumulator of GEMM1 (ping-pong while EPI1 is the bottleneck).  GEMM2 runs on
+//   the single accumulator: while EPI2 drains chunk c the tensor pipe works on GEMM3's partial sum for chunk c-1.
+//   When N3 > 128 (level 2 forward: 9*24 = 216) GEMM3's accumulator aliases the h1 columns instead: all four h2
+//   chunks stay in shared memory and GEMM3 runs after GEMM2 ("deferred").
+// Measured on B200 (tools/micro/mma_rate.cu, profiles/r2_mma_rate.txt): TS-mode MMAs run at N/2 cycles for any N,
+//   SS-mode MMAs at max(N/2, 32 + N/4) (the 4 KB A read from shared memory), and the issuing warp needs ~300 cycles
+//   per pipeline stage (try_wait + fence + elect + commit) -- hence 128-wide MMAs and >= 256 cycles of MMAs per stage.
 #include "tc_common.cuh"
 #include "gemm_epilogue.cuh"
 
@@ -32,15 +36,14 @@ namespace cnet {
 using namespace tc;
 
 constexpr int HID = 512;
-constexpr int NC = 64;                    // chunk width (columns of GEMM1 / GEMM2 per accumulator buffer)
-constexpr int NCHUNK = HID / NC;          // 8
-constexpr int STAGE_BYTES = 16384;
-constexpr int BOX_BYTES = 8192;           // one [64 n][64 k] bf16 weight box
-constexpr int HB_BYTES = 16384;           // one [128][64] bf16 chunk
+constexpr int NC = 128;                   // chunk width (columns of GEMM1 / GEMM2 per accumulator)
+constexpr int NCHUNK = HID / NC;          // 4
+constexpr int BOX_BYTES = 16384;          // one [128 n][64 k] bf16 weight box (also one K-block of an A tile)
+constexpr int HB_BYTES = 32768;           // one [128][128] bf16 chunk = two K-blocks
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int COL_H = 0, COL_ACC0 = 256, COL_ACC1 = 320, COL_C3 = 384;
-constexpr int MAX_STAGES = 8, MAX_HB = 8;
+constexpr int COL_H = 0, COL_ACC0 = 256, COL_ACC1 = 384, COL_C3 = 384;
+constexpr int MAX_STAGES = 8, MAX_HB = 4;
 
 enum { MODE_FWD = 0, MODE_BWD = 1 };
 
@@ -56,12 +59,45 @@ struct Shared {
 };
 
 struct Params {
-  int M, K1B, N3, NH, nhb, c3_col, deferred, nstages;
-  int save1, save2;
+  int M, K1B, N3, NH, nhb, c3_col, deferred, nstages, bps;
+  int save1, save2, dbg;
   const float *bias1, *logs1, *bias2, *logs2;
   float f1, f2;
   float *dbias1, *dbias2;     // backward: column sums of the stored d2 (EPI1) / d1 (EPI2), nullable
 };
+
+// Profiling aid (GLOWK_CNET_DEBUG=1): wait cycles of CTA 0's roles, read back by glowk_debug_cnet_trace.
+//   MMA warp : [0] a_full  [1] acc_empty (GEMM1)  [2] ring_full (GEMM1)  [3] h1_full  [4] acc_empty (GEMM2)
+//              [5] ring_full (GEMM2)  [6] h2_full + c3_empty  [7] ring_full (GEMM3)  [8] total  [9] tiles
+//   producer : [10] ring_empty + a_empty  [11] total
+//   epilogue warp 0: [12] acc_full (EPI1)  [13] acc_full (EPI2)  [14] c3_full  [15] total
+// Further bits switch work off (results invalid): 2 = no weight loads, 4 = no epilogue math / stores, 8 = no MMAs.
+__device__ unsigned long long g_cnet_trace[16];
+// Timeline of CTA 0's 6th tile (GLOWK_CNET_DEBUG bit 16): SM clock at
+//   MMA warp  [0] tile start  [1] a_full  [2+2c] GEMM1 chunk c: accumulator free  [3+2c] ... issued
+//             [10] h1_full  [11+3c] GEMM2 chunk c: accumulator free  [12+3c] issued  [13+3c] GEMM3 partial issued (c-1; tail: 3)
+//             [24] c3_full committed
+//   epilogue warp 0  [32+3c] EPI1 chunk c: acc_full seen  [33+3c] accumulator released  [34+3c] h1 chunk published
+//             [44+3c] EPI2 chunk c: acc_full seen  [45+3c] released  [46+3c] h2 chunk published
+//             [56] c3_full seen  [57] c3 drained
+__device__ unsigned long long g_cnet_timeline[64];
+#define CNET_TS(on, id) do { if (on) g_cnet_timeline[id] = (unsigned long long)clock64(); } while (0)
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, bool on, unsigned long long& acc) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += (unsigned long long)(clock64() - t0);
+}
+// non-blocking probe: lets the issuing warp start a barrier read a stage ahead of needing its answer
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 
 __device__ __forceinline__ void tcgen05_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                                     uint32_t accumulate) {
@@ -106,7 +142,7 @@ __device__ __forceinline__ void box_colsum_bf16(const uint8_t* box, int lane, fl
   atomicAdd(acc + 2 * lane + 1, s1);
 }
 
-template <int MODE>
+template <int MODE, int BPS>
 __global__ void __launch_bounds__(THREADS, 1)
 cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
@@ -115,9 +151,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_y2, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr bool BWD = MODE == MODE_BWD;
-  uint8_t* a_smem = smem;                                          // K1B boxes [128][64] bf16
-  uint8_t* ring = a_smem + (size_t)p.K1B * 16384;
-  uint8_t* hb = ring + (size_t)p.nstages * STAGE_BYTES;            // nhb chunk buffers [128][64] bf16
+  constexpr uint32_t stage_bytes = (uint32_t)BPS * BOX_BYTES;
+  uint8_t* a_smem = smem;                                          // K1B K-blocks [128][64] bf16
+  uint8_t* ring = a_smem + (size_t)p.K1B * BOX_BYTES;
+  uint8_t* hb = ring + (size_t)p.nstages * stage_bytes;            // nhb chunk buffers [128][128] bf16
   uint8_t* ysm = hb + (size_t)p.nhb * HB_BYTES;                    // BWD: one [32][64] bf16 mask box per epilogue warp
   float* s_vec = reinterpret_cast<float*>(ysm + (BWD ? EPI_WARPS * 4096 : 0));
   float* s_sc1 = s_vec;                 // [512] exp(f*logs)
@@ -139,9 +176,9 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (BWD) { prefetch_tensormap(&tm_y1); prefetch_tensormap(&tm_y2); }
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&sh->ring_full[s], 1); mbar_init(&sh->ring_empty[s], 1); }
     mbar_init(&sh->a_full, 1); mbar_init(&sh->a_empty, 1);
-    for (int g = 0; g < 2; ++g) { mbar_init(&sh->acc_full[g], 1); mbar_init(&sh->acc_empty[g], 4); }
-    mbar_init(&sh->h1_full, 4 * NCHUNK);
-    for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], 4); mbar_init(&sh->h2_empty[b], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&sh->acc_full[g], 1); mbar_init(&sh->acc_empty[g], EPI_WARPS); }
+    mbar_init(&sh->h1_full, EPI_WARPS * NCHUNK);
+    for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], EPI_WARPS); mbar_init(&sh->h2_empty[b], 1); }
     mbar_init(&sh->c3_full, 1); mbar_init(&sh->c3_empty, EPI_WARPS);
     for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,186 +202,229 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      auto next_stage = [&]() { if (++stage == p.nstages) { stage = 0; phase ^= 1; } };
-      auto fill_w3 = [&](int cc) {
-        for (int h = 0; h < p.NH; ++h) {
-          mbar_wait(&sh->ring_empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)p.N3 * 128u);
-          tma_load_2d(&tm_w3, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES, cc * NC, h * p.N3);
-          next_stage();
+      const bool tr = (p.dbg & 1) && blockIdx.x == 0;
+      unsigned long long w_e = 0;
+      const long long t_begin = clock64();
+      // one stage = up to bps boxes: box i of `nbox` at (col0 + i*64, row0), `bbytes` each
+      auto fill = [&](const CUtensorMap* tm, int nbox, int col0, int row0, uint32_t bbytes) {
+        for (int i = 0; i < nbox; i += BPS) {
+          const int nb = nbox - i < BPS ? nbox - i : BPS;
+          wait_t(&sh->ring_empty[stage], phase ^ 1, tr, w_e);
+          uint8_t* dst = ring + (size_t)stage * stage_bytes;
+          if (p.dbg & 2) mbar_arrive(&sh->ring_full[stage]);       // profiling: no operand traffic
+          else {
+            mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)nb * bbytes);
+            for (int b = 0; b < nb; ++b) tma_load_2d(tm, &sh->ring_full[stage], dst + (size_t)b * bbytes, col0 + (i + b) * BLOCK_K, row0);
+          }
+          if (++stage == p.nstages) { stage = 0; phase ^= 1; }
         }
+      };
+      auto fill_w3 = [&](int cc) {
+        for (int h = 0; h < p.NH; ++h) fill(&tm_w3, NC / BLOCK_K, cc * NC, h * p.N3, (uint32_t)p.N3 * 128u);
       };
       uint32_t tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        mbar_wait(&sh->a_empty, (tcount & 1) ^ 1);
-        mbar_arrive_expect_tx(&sh->a_full, (uint32_t)p.K1B * 16384u);
+        wait_t(&sh->a_empty, (tcount & 1) ^ 1, tr, w_e);
+        mbar_arrive_expect_tx(&sh->a_full, (uint32_t)p.K1B * BOX_BYTES);
         for (int kb = 0; kb < p.K1B; ++kb)
-          tma_load_2d(&tm_a, &sh->a_full, a_smem + (size_t)kb * 16384, kb * BLOCK_K, tile * BLOCK_M);
-        for (int c = 0; c < NCHUNK; ++c)
-          for (int kb = 0; kb < p.K1B; kb += 2) {
-            const int nb = p.K1B - kb < 2 ? 1 : 2;
-            mbar_wait(&sh->ring_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)nb * BOX_BYTES);
-            for (int b = 0; b < nb; ++b)
-              tma_load_2d(&tm_w1, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES + b * BOX_BYTES,
-                          (kb + b) * BLOCK_K, c * NC);
-            next_stage();
-          }
+          tma_load_2d(&tm_a, &sh->a_full, a_smem + (size_t)kb * BOX_BYTES, kb * BLOCK_K, tile * BLOCK_M);
+        for (int c = 0; c < NCHUNK; ++c) fill(&tm_w1, p.K1B, 0, c * NC, BOX_BYTES);
         for (int c = 0; c < NCHUNK; ++c) {
-          for (int kp = 0; kp < HID / 128; ++kp) {
-            mbar_wait(&sh->ring_empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&sh->ring_full[stage], 2u * BOX_BYTES);
-            tma_load_2d(&tm_w2, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES, kp * 128, c * NC);
-            tma_load_2d(&tm_w2, &sh->ring_full[stage], ring + (size_t)stage * STAGE_BYTES + BOX_BYTES, kp * 128 + 64, c * NC);
-            next_stage();
-          }
+          fill(&tm_w2, HID / BLOCK_K, 0, c * NC, BOX_BYTES);
           if (!p.deferred && c >= 1) fill_w3(c - 1);
         }
         if (!p.deferred) fill_w3(NCHUNK - 1);
         else for (int c = 0; c < NCHUNK; ++c) fill_w3(c);
       }
+      if (tr) { g_cnet_trace[10] = w_e; g_cnet_trace[11] = (unsigned long long)(clock64() - t_begin); }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp runs this loop (warp-uniform control flow: descriptors and addresses stay in uniform registers);
-    // one elected lane issues the tcgen05.mma / tcgen05.commit instructions.
-    {
-      const uint32_t idesc_c = make_idesc(NC, 0, 0);
-      const uint32_t idesc_3 = make_idesc(p.N3, 0, 0);
-      const uint32_t a_base = smem_u32(a_smem), ring_base = smem_u32(ring), hb_base = smem_u32(hb);
-      int stage = 0; uint32_t phase = 0;
-      auto next_stage = [&]() { if (++stage == p.nstages) { stage = 0; phase ^= 1; } };
-      uint32_t tcount = 0;
-      auto gemm3_partial = [&](int cc) {
-        const int b = cc % p.nhb;
-        const uint32_t idx = tcount * (uint32_t)upt + (uint32_t)(cc / p.nhb);
-        mbar_wait(&sh->h2_full[b], idx & 1);
-        if (cc == 0 && !p.deferred) mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
-        tcgen05_fence_after();
-        const uint64_t adesc = make_smem_desc(hb_base + (uint32_t)b * HB_BYTES, 16, 1024);
-        for (int h = 0; h < p.NH; ++h) {
-          mbar_wait(&sh->ring_full[stage], phase);
-          tcgen05_fence_after();
-          const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
-          const uint32_t d = tmem_base + (uint32_t)(p.c3_col + h * p.N3);
-          if (elect_one_sync()) {
+    // one elected lane issues the tcgen05.mma / tcgen05.commit instructions.  Per stage the warp pays a barrier
+    // probe, a fence, an elect, the MMA issue and a commit: the probe of stage s+1 is issued BEFORE the MMAs of
+    // stage s so that its ~150-cycle latency hides behind them.
+    const uint32_t idesc_c = make_idesc(NC, 0, 0);
+    const uint32_t idesc_3 = make_idesc(p.N3, 0, 0);
+    const uint32_t ring_base = smem_u32(ring);
+    const uint64_t a_desc = make_smem_desc(smem_u32(a_smem), 16, 1024);
+    const uint64_t hb_desc = make_smem_desc(smem_u32(hb), 16, 1024);
+    const uint64_t ring_desc = make_smem_desc(ring_base, 16, 1024);
+    const uint32_t stage16 = stage_bytes >> 4;                     // descriptor address fields count 16-byte units
+    const uint32_t n3_box16 = (uint32_t)p.N3 * 8u;                 // one W3 box (N3 rows x 128 B) in 16-byte units
+    int stage = 0; uint32_t phase = 0;
+    const bool tr = (p.dbg & 1) && blockIdx.x == 0;
+    const bool no_mma = (p.dbg & 8) != 0;
+    unsigned long long w0 = 0, w1 = 0, w2 = 0, w3 = 0, w4 = 0, w5 = 0, w6 = 0, w7 = 0;
+    const long long t_begin = clock64();
+    bool ready = mbar_test(&sh->ring_full[0], 0);
+    int nstage = 0; uint32_t nphase = 0;                           // the stage after `stage`
+    auto acquire = [&](unsigned long long& w) {                    // -> stage is loaded; starts the probe of the next one
+      if (!ready) wait_t(&sh->ring_full[stage], phase, tr, w);
+      tcgen05_fence_after();
+      nstage = stage + 1; nphase = phase;
+      if (nstage == p.nstages) { nstage = 0; nphase ^= 1; }
+      ready = mbar_test(&sh->ring_full[nstage], nphase);
+    };
+    auto advance = [&]() { __syncwarp(); stage = nstage; phase = nphase; };
+    uint32_t tcount = 0;
+    auto gemm3_partial = [&](int cc) {
+      const int b = cc % p.nhb;
+      const uint32_t idx = tcount * (uint32_t)upt + (uint32_t)(cc / p.nhb);
+      wait_t(&sh->h2_full[b], idx & 1, tr, w6);
+      tcgen05_fence_after();
+      const uint64_t adesc0 = hb_desc + (uint64_t)((uint32_t)b * (HB_BYTES / 16));
+      for (int h = 0; h < p.NH; ++h) {
+        const uint32_t d = tmem_base + (uint32_t)(p.c3_col + h * p.N3);
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              tcgen05_mma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_3, (cc | k) != 0);
+        for (int i = 0; i < NC / BLOCK_K; i += BPS) {
+          acquire(w7);
+          const uint64_t bdesc0 = ring_desc + (uint64_t)((uint32_t)stage * stage16);
+          if (elect_one_sync()) {
+            if (!no_mma) {
+#pragma unroll
+              for (int bb = 0; bb < BPS; ++bb) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                  tcgen05_mma_bf16(d, adesc0 + (uint64_t)((i + bb) * (BOX_BYTES / 16) + k * 2),
+                                   bdesc0 + (uint64_t)(bb * n3_box16 + k * 2), idesc_3, (cc | i | bb | k) != 0);
+              }
+            }
             tcgen05_commit(&sh->ring_empty[stage]);
           }
-          __syncwarp();
-          next_stage();
+          advance();
         }
-        if (elect_one_sync()) tcgen05_commit(&sh->h2_empty[b]);
-        __syncwarp();
-      };
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        // ---- GEMM1: A from shared memory
-        mbar_wait(&sh->a_full, tcount & 1);
-        tcgen05_fence_after();
-        for (int c = 0; c < NCHUNK; ++c) {
-          const int g = c & 1;
-          const uint32_t idx = tcount * 8u + (uint32_t)(c >> 1);
-          mbar_wait(&sh->acc_empty[g], (idx & 1) ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(g ? COL_ACC1 : COL_ACC0);
-          for (int kb = 0; kb < p.K1B; kb += 2) {
-            const int nb = p.K1B - kb < 2 ? 1 : 2;
-            mbar_wait(&sh->ring_full[stage], phase);
-            tcgen05_fence_after();
-            const uint64_t adesc = make_smem_desc(a_base + (uint32_t)kb * 16384u, 16, 1024);
-            const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                tcgen05_mma_bf16(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_c, (kb | k) != 0);
-              if (nb == 2) {
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)   // second box: A +16 KB, B +8 KB (descriptor units of 16 B)
-                  tcgen05_mma_bf16(d, adesc + (uint64_t)(1024 + k * 2), bdesc + (uint64_t)(512 + k * 2), idesc_c, 1u);
-              }
-              tcgen05_commit(&sh->ring_empty[stage]);
-            }
-            __syncwarp();
-            next_stage();
-          }
-          if (elect_one_sync()) tcgen05_commit(&sh->acc_full[g]);
-          __syncwarp();
-        }
-        if (elect_one_sync()) tcgen05_commit(&sh->a_empty);
-        __syncwarp();
-        // ---- GEMM2: A = h1 / d2 in TMEM (bf16 pairs: 16 k = 8 columns); GEMM3 partial sums interleaved
-        mbar_wait(&sh->h1_full, tcount & 1);
-        tcgen05_fence_after();
-        for (int c = 0; c < NCHUNK; ++c) {
-          const int g = c & 1;
-          const uint32_t idx = tcount * 8u + 4u + (uint32_t)(c >> 1);
-          mbar_wait(&sh->acc_empty[g], (idx & 1) ^ 1);
-          tcgen05_fence_after();
-          const uint32_t d = tmem_base + (uint32_t)(g ? COL_ACC1 : COL_ACC0);
-#pragma unroll
-          for (int kp = 0; kp < HID / 128; ++kp) {
-            mbar_wait(&sh->ring_full[stage], phase);
-            tcgen05_fence_after();
-            const uint64_t bdesc = make_smem_desc(ring_base + (uint32_t)stage * STAGE_BYTES, 16, 1024);
-            const uint32_t ta = tmem_base + (uint32_t)(COL_H + kp * 64);
-            if (elect_one_sync()) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)      // 8 k-steps of 16: box k/4 (+8 KB = +512 descriptor units), 32 B steps inside
-                tcgen05_mma_bf16_ts(d, ta + (uint32_t)(k * 8), bdesc + (uint64_t)((k >> 2) * 512 + (k & 3) * 2), idesc_c,
-                                    (kp | k) != 0);
-              tcgen05_commit(&sh->ring_empty[stage]);
-            }
-            __syncwarp();
-            next_stage();
-          }
-          if (elect_one_sync()) tcgen05_commit(&sh->acc_full[g]);
-          __syncwarp();
-          if (!p.deferred && c >= 1) gemm3_partial(c - 1);
-        }
-        if (!p.deferred) gemm3_partial(NCHUNK - 1);
-        else for (int c = 0; c < NCHUNK; ++c) gemm3_partial(c);
-        if (elect_one_sync()) tcgen05_commit(&sh->c3_full);
-        __syncwarp();
       }
+      if (elect_one_sync()) tcgen05_commit(&sh->h2_empty[b]);
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      // ---- GEMM1: A from shared memory; accumulators ping-pong between [256,384) and [384,512)
+      const bool tl = (p.dbg & 16) && blockIdx.x == 0 && tcount == 5 && lane == 0;
+      CNET_TS(tl, 0);
+      wait_t(&sh->a_full, tcount & 1, tr, w0);
+      CNET_TS(tl, 1);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int buf = c & 1;
+        const uint32_t idx = buf ? tcount * 2u + (uint32_t)(c >> 1) : tcount * 6u + (uint32_t)(c >> 1);
+        wait_t(&sh->acc_empty[buf], (idx & 1) ^ 1, tr, w1);
+        if (c == 1 && !p.deferred) wait_t(&sh->c3_empty, (tcount & 1) ^ 1, tr, w1);   // [384,512) was GEMM3's accumulator
+        CNET_TS(tl, 2 + 2 * c);
+        const uint32_t d = tmem_base + (uint32_t)(buf ? COL_ACC1 : COL_ACC0);
+        for (int kb = 0; kb < p.K1B; kb += BPS) {
+          const int nb = p.K1B - kb < BPS ? p.K1B - kb : BPS;
+          acquire(w2);
+          const uint64_t adesc0 = a_desc + (uint64_t)((uint32_t)kb * (BOX_BYTES / 16));
+          const uint64_t bdesc0 = ring_desc + (uint64_t)((uint32_t)stage * stage16);
+          if (elect_one_sync()) {
+            if (!no_mma) {
+#pragma unroll
+              for (int bb = 0; bb < BPS; ++bb) {
+                if (bb < nb) {
+#pragma unroll
+                  for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                    tcgen05_mma_bf16(d, adesc0 + (uint64_t)(bb * (BOX_BYTES / 16) + k * 2),
+                                     bdesc0 + (uint64_t)(bb * (BOX_BYTES / 16) + k * 2), idesc_c, (kb | bb | k) != 0);
+                }
+              }
+            }
+            tcgen05_commit(&sh->ring_empty[stage]);
+          }
+          advance();
+        }
+        if (elect_one_sync()) tcgen05_commit(&sh->acc_full[buf]);
+        __syncwarp();
+        CNET_TS(tl, 3 + 2 * c);
+      }
+      if (elect_one_sync()) tcgen05_commit(&sh->a_empty);
+      __syncwarp();
+      // ---- GEMM2: A = h1 / d2 in TMEM (bf16 pairs: 16 k = 8 columns); GEMM3 partial sums interleaved
+      wait_t(&sh->h1_full, tcount & 1, tr, w3);
+      CNET_TS(tl, 10);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const uint32_t idx = tcount * 6u + 2u + (uint32_t)c;
+        wait_t(&sh->acc_empty[0], (idx & 1) ^ 1, tr, w4);
+        CNET_TS(tl, 11 + 3 * c);
+        const uint32_t d = tmem_base + (uint32_t)COL_ACC0;
+#pragma unroll
+        for (int kb = 0; kb < HID / BLOCK_K; kb += BPS) {
+          acquire(w5);
+          const uint64_t bdesc0 = ring_desc + (uint64_t)((uint32_t)stage * stage16);
+          const uint32_t ta = tmem_base + (uint32_t)(COL_H + kb * 32);
+          if (elect_one_sync()) {
+            if (!no_mma) {
+#pragma unroll
+              for (int bb = 0; bb < BPS; ++bb) {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                  tcgen05_mma_bf16_ts(d, ta + (uint32_t)(bb * 32 + k * 8), bdesc0 + (uint64_t)(bb * (BOX_BYTES / 16) + k * 2),
+                                      idesc_c, (kb | bb | k) != 0);
+              }
+            }
+            tcgen05_commit(&sh->ring_empty[stage]);
+          }
+          advance();
+        }
+        if (elect_one_sync()) tcgen05_commit(&sh->acc_full[0]);
+        __syncwarp();
+        CNET_TS(tl, 12 + 3 * c);
+        if (!p.deferred && c >= 1) { gemm3_partial(c - 1); CNET_TS(tl, 13 + 3 * c); }
+      }
+      if (!p.deferred) gemm3_partial(NCHUNK - 1);
+      else for (int c = 0; c < NCHUNK; ++c) gemm3_partial(c);
+      CNET_TS(tl, 13);
+      if (elect_one_sync()) tcgen05_commit(&sh->c3_full);
+      __syncwarp();
+      CNET_TS(tl, 24);
+    }
+    if (tr && lane == 0) {
+      g_cnet_trace[0] = w0; g_cnet_trace[1] = w1; g_cnet_trace[2] = w2; g_cnet_trace[3] = w3; g_cnet_trace[4] = w4;
+      g_cnet_trace[5] = w5; g_cnet_trace[6] = w6; g_cnet_trace[7] = w7;
+      g_cnet_trace[8] = (unsigned long long)(clock64() - t_begin); g_cnet_trace[9] = tcount;
     }
   } else {
     // ===================== epilogue warps =====================
     const int ew = warp - 2, g = ew >> 2, quarter = warp & 3;      // TMEM lane quarter = warp % 4 (hardware rule)
     const int row0 = quarter * 32;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)row0 << 16);
-    const uint32_t acc_col = g ? COL_ACC1 : COL_ACC0;
-    uint8_t* stg = hb + (size_t)g * HB_BYTES + (size_t)quarter * 4096;   // this warp's 32 rows of chunk buffer g
+    const size_t my_off = (size_t)g * BOX_BYTES + (size_t)quarter * 4096;   // this warp's [32 rows][64 k] slice of a chunk buffer
     uint8_t* ybox = ysm + (size_t)ew * 4096;
     uint32_t ycount = 0;
-    // mask boxes (BWD): this warp's sequence is tile-major, then EPI1 chunks g, g+2, .. (y1), then EPI2 chunks (y2)
+    const bool no_epi = (p.dbg & 4) != 0;
+    // mask boxes (BWD): this warp's sequence is tile-major, then EPI1 chunks 0..3 (y1), then EPI2 chunks 0..3 (y2)
     auto issue_y = [&](int tile, int ph, int c) {
       if (lane == 0) {
         mbar_arrive_expect_tx(&sh->y_bar[ew], 4096);
-        tma_load_2d(ph ? &tm_y2 : &tm_y1, &sh->y_bar[ew], ybox, c * NC, tile * BLOCK_M + row0);
+        tma_load_2d(ph ? &tm_y2 : &tm_y1, &sh->y_bar[ew], ybox, c * NC + g * 64, tile * BLOCK_M + row0);
       }
     };
     auto issue_next_y = [&](int tile, int ph, int c) {
-      c += 2;
-      if (c >= NCHUNK) { c = g; ph ^= 1; if (ph == 0) tile += gridDim.x; }
+      if (++c == NCHUNK) { c = 0; ph ^= 1; if (ph == 0) tile += gridDim.x; }
       if (tile < num_tiles) issue_y(tile, ph, c);
     };
-    if (BWD && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, g);
+    if (BWD && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, 0);
 
-    // accumulator chunk -> bf16 pairs (64 columns of this lane's row)
-    auto epilogue_chunk = [&](int c, int ph, uint32_t (&pk)[32]) {
+    // this warp's 32 rows x 64 columns of a chunk accumulator -> bf16 pairs; releases the accumulator
+    auto epilogue_chunk = [&](int c, int ph, uint32_t acc_col, uint64_t* rel_bar, uint32_t (&pk)[32]) {
+      if (no_epi) {                                                // profiling: barrier protocol only
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(rel_bar);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) pk[j] = 0u;
+        return;
+      }
       uint32_t r0[32], r1[32];
-      tmem_ld32_async(lane_taddr + acc_col, r0);
-      tmem_ld32_async(lane_taddr + acc_col + 32, r1);
+      tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64), r0);
+      tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64 + 32), r1);
       if (BWD) mbar_wait(&sh->y_bar[ew], ycount & 1);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->acc_empty[g]);              // accumulator buffer is in registers now
-      const float* sc = (ph ? s_sc2 : s_sc1) + c * NC;
+      if (lane == 0) mbar_arrive(rel_bar);                         // accumulator columns are in registers now
+      const float* sc = (ph ? s_sc2 : s_sc1) + c * NC + g * 64;
       if (!BWD) {
-        const float* sf = (ph ? s_x2 : s_x1) + c * NC;
+        const float* sf = (ph ? s_x2 : s_x1) + c * NC + g * 64;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float a = fmaxf(fmaf(__uint_as_float(r0[2 * j]), sc[2 * j], sf[2 * j]), 0.f);
@@ -368,7 +448,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const float2 yv = __bfloat1622float2(yp[u]);
-            const int j = j4 * 8 + u * 2;                          // column within the chunk
+            const int j = j4 * 8 + u * 2;                          // column within this warp's 64
             const float ra = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
             const float rb = __uint_as_float(j < 32 ? r0[j + 1] : r1[j - 31]);
             const float a = (yv.x > 0.f ? ra : 0.f) * sc[j];
@@ -383,62 +463,76 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     };
 
     uint32_t tcount = 0;
+    const bool tr = (p.dbg & 1) && blockIdx.x == 0 && ew == 0;
+    unsigned long long e1 = 0, e2 = 0, e3 = 0;
+    const long long t_begin = clock64();
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int grow = tile * BLOCK_M + row0;
+      const bool tl = (p.dbg & 16) && blockIdx.x == 0 && tcount == 5 && ew == 0 && lane == 0;
       // ---- EPI1: chunk accumulators -> bf16 -> TMEM (A operand of GEMM2)
-      for (int c = g; c < NCHUNK; c += 2) {
-        const uint32_t idx = tcount * 8u + (uint32_t)(c >> 1);
-        mbar_wait(&sh->acc_full[g], idx & 1);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int buf = c & 1;
+        const uint32_t idx = buf ? tcount * 2u + (uint32_t)(c >> 1) : tcount * 6u + (uint32_t)(c >> 1);
+        wait_t(&sh->acc_full[buf], idx & 1, tr, e1);
+        CNET_TS(tl, 32 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 0, pk);
+        epilogue_chunk(c, 0, buf ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf], pk);
+        CNET_TS(tl, 33 + 3 * c);
         if (BWD) issue_next_y(tile, 0, c);                         // next mask box of this warp's sequence
-        if (p.deferred && c == g) {                                // GEMM3's accumulator of the previous tile aliases h1
+        if (p.deferred && c == 0) {                                // GEMM3's accumulator of the previous tile aliases h1
           mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
           tcgen05_fence_after();
         }
-        tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2)), pk);
+        if (!no_epi) tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2) + g * 32), pk);
         if (BWD || p.save1) {
+          uint8_t* stg = hb + (size_t)buf * HB_BYTES + my_off;     // chunk buffers are idle until EPI2
           if (lane == 0) tma_store_wait_read<0>();                 // my previous store out of this staging box
           __syncwarp();
           store_row_sw128(stg, lane, pk);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tma_store_2d(&tm_o1, stg, c * NC, grow); tma_store_commit(); }
-          if (BWD && p.dbias2) box_colsum_bf16(stg, lane, s_x2 + c * NC);
+          if (lane == 0) { tma_store_2d(&tm_o1, stg, c * NC + g * 64, grow); tma_store_commit(); }
+          if (BWD && p.dbias2) box_colsum_bf16(stg, lane, s_x2 + c * NC + g * 64);
         }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->h1_full);
+        CNET_TS(tl, 34 + 3 * c);
       }
       // ---- EPI2: chunk accumulators -> bf16 -> shared-memory chunk (A operand of GEMM3)
-      for (int c = g; c < NCHUNK; c += 2) {
-        const uint32_t idx = tcount * 8u + 4u + (uint32_t)(c >> 1);
-        mbar_wait(&sh->acc_full[g], idx & 1);
+      for (int c = 0; c < NCHUNK; ++c) {
+        const uint32_t idx = tcount * 6u + 2u + (uint32_t)c;
+        wait_t(&sh->acc_full[0], idx & 1, tr, e2);
+        CNET_TS(tl, 44 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 1, pk);
+        epilogue_chunk(c, 1, COL_ACC0, &sh->acc_empty[0], pk);
+        CNET_TS(tl, 45 + 3 * c);
         if (BWD) issue_next_y(tile, 1, c);
         const int b = c % p.nhb;
         const uint32_t hidx = tcount * (uint32_t)upt + (uint32_t)(c / p.nhb);
         mbar_wait(&sh->h2_empty[b], (hidx & 1) ^ 1);               // GEMM3 partial that last read this buffer retired
         if (lane == 0) tma_store_wait_read<0>();                   // ... and so has my TMA store out of it
         __syncwarp();
-        uint8_t* slice = hb + (size_t)b * HB_BYTES + (size_t)quarter * 4096;
-        store_row_sw128(slice, lane, pk);
+        uint8_t* slice = hb + (size_t)b * HB_BYTES + my_off;
+        if (!no_epi) store_row_sw128(slice, lane, pk);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (BWD || p.save2) { tma_store_2d(&tm_o2, slice, c * NC, grow); tma_store_commit(); }
+          if (BWD || p.save2) { tma_store_2d(&tm_o2, slice, c * NC + g * 64, grow); tma_store_commit(); }
           mbar_arrive(&sh->h2_full[b]);
         }
-        if (BWD && p.dbias1) box_colsum_bf16(slice, lane, s_x1 + c * NC);
+        if (BWD && p.dbias1) box_colsum_bf16(slice, lane, s_x1 + c * NC + g * 64);
+        CNET_TS(tl, 46 + 3 * c);
       }
       // ---- EPI3: GEMM3 accumulator -> global
-      mbar_wait(&sh->c3_full, tcount & 1);
+      wait_t(&sh->c3_full, tcount & 1, tr, e3);
+      CNET_TS(tl, 56);
       tcgen05_fence_after();
       const int n3tot = p.NH * p.N3;
+      uint8_t* stg = hb + my_off;                                  // every GEMM3 partial of this tile has retired
       if (!BWD) {
         for (int j = g; j * 32 < n3tot; j += 2) {
           uint32_t r[32];
@@ -475,6 +569,11 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->c3_empty);
+      CNET_TS(tl, 57);
+    }
+    if (tr && lane == 0) {
+      g_cnet_trace[12] = e1; g_cnet_trace[13] = e2; g_cnet_trace[14] = e3;
+      g_cnet_trace[15] = (unsigned long long)(clock64() - t_begin);
     }
     if (BWD) {
       // one global atomic per column per CTA
@@ -499,20 +598,24 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------
-struct Variant { int NH, N3, nhb, c3_col, deferred, nstages; size_t smem; };
+struct Variant { int NH, N3, nhb, c3_col, deferred, nstages, bps; size_t smem; };
 
 static bool pick_variant(int mode, int64_t K1, int64_t n3tot, Variant* v) {
   if (K1 <= 0 || K1 % 64 != 0 || n3tot <= 0 || n3tot % 16 != 0) return false;
   if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
-  else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 8; v->c3_col = COL_H; v->deferred = 1; }
+  else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 4; v->c3_col = COL_H; v->deferred = 1; }
   else return false;
-  const size_t fixed = (size_t)(K1 / 64) * 16384 + (size_t)v->nhb * HB_BYTES + (mode == MODE_BWD ? EPI_WARPS * 4096 : 0) +
+  const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES + (mode == MODE_BWD ? EPI_WARPS * 4096 : 0) +
                        4 * HID * sizeof(float) + sizeof(Shared) + 64;
   const size_t budget = 227 * 1024;
-  if (fixed + 3 * (size_t)STAGE_BYTES > budget) return false;
-  int s = (int)((budget - fixed) / STAGE_BYTES);
+  if (fixed + 3 * (size_t)BOX_BYTES > budget) return false;
+  // two boxes per stage (8 MMAs = 512 tensor cycles per barrier round trip) when at least three such stages fit
+  const char* e = getenv("GLOWK_CNET_BPS");
+  v->bps = (fixed + 3 * 2 * (size_t)BOX_BYTES <= budget) ? 2 : 1;
+  if (e && (e[0] == '1' || e[0] == '2') && fixed + 3 * (size_t)(e[0] - '0') * BOX_BYTES <= budget) v->bps = e[0] - '0';
+  int s = (int)((budget - fixed) / ((size_t)v->bps * BOX_BYTES));
   v->nstages = s > MAX_STAGES ? MAX_STAGES : s;
-  v->smem = fixed + (size_t)v->nstages * STAGE_BYTES;
+  v->smem = fixed + (size_t)v->nstages * v->bps * BOX_BYTES;
   return true;
 }
 
@@ -521,9 +624,9 @@ bool chain_supported(int backward, int64_t K1, int64_t hidden, int64_t n3tot) {
   return hidden == HID && tc_available() && pick_variant(backward ? MODE_BWD : MODE_FWD, K1, n3tot, &v);
 }
 
-template <int MODE>
+template <int MODE, int BPS>
 static int launch_chain(const CUtensorMap* tm, const Params& p, size_t smem, cudaStream_t st) {
-  auto kern = cnet_chain_kernel<MODE>;
+  auto kern = cnet_chain_kernel<MODE, BPS>;
   GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -554,8 +657,8 @@ int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64
   int rc;
   const auto BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   if ((rc = make_map_2d(&tm[0], A, BF, 2, (uint64_t)K1, (uint64_t)M, (uint64_t)lda, 64, 128))) return rc;
-  if ((rc = make_map_2d(&tm[1], W1, BF, 2, (uint64_t)K1, (uint64_t)HID, (uint64_t)ldw1, 64, 64))) return rc;
-  if ((rc = make_map_2d(&tm[2], W2, BF, 2, (uint64_t)HID, (uint64_t)HID, (uint64_t)ldw2, 64, 64))) return rc;
+  if ((rc = make_map_2d(&tm[1], W1, BF, 2, (uint64_t)K1, (uint64_t)HID, (uint64_t)ldw1, 64, NC))) return rc;
+  if ((rc = make_map_2d(&tm[2], W2, BF, 2, (uint64_t)HID, (uint64_t)HID, (uint64_t)ldw2, 64, NC))) return rc;
   if ((rc = make_map_2d(&tm[3], W3, BF, 2, (uint64_t)HID, (uint64_t)n3tot, (uint64_t)ldw3, 64, (uint32_t)v.N3))) return rc;
   const void* o1m = o1 ? o1 : A;   // unused maps still need a valid encoding
   const void* o2m = o2 ? o2 : A;
@@ -571,17 +674,33 @@ int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64
   }
   Params p;
   p.M = (int)M; p.K1B = (int)(K1 / 64); p.N3 = v.N3; p.NH = v.NH; p.nhb = v.nhb; p.c3_col = v.c3_col;
-  p.deferred = v.deferred; p.nstages = v.nstages;
+  p.deferred = v.deferred; p.nstages = v.nstages; p.bps = v.bps;
   p.save1 = o1 != nullptr; p.save2 = o2 != nullptr;
+  { const char* e = getenv("GLOWK_CNET_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
   p.dbias1 = dbias1; p.dbias2 = dbias2;
-  return backward ? launch_chain<MODE_BWD>(tm, p, v.smem, st) : launch_chain<MODE_FWD>(tm, p, v.smem, st);
+  if (v.bps == 2) return backward ? launch_chain<MODE_BWD, 2>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 2>(tm, p, v.smem, st);
+  return backward ? launch_chain<MODE_BWD, 1>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 1>(tm, p, v.smem, st);
+}
+
+int debug_trace(unsigned long long* out16) {
+  GLOWK_CUDA(cudaDeviceSynchronize());
+  GLOWK_CUDA(cudaMemcpyFromSymbol(out16, g_cnet_trace, 16 * sizeof(unsigned long long)));
+  return GLOWK_OK;
+}
+int debug_timeline(unsigned long long* out64) {
+  GLOWK_CUDA(cudaDeviceSynchronize());
+  GLOWK_CUDA(cudaMemcpyFromSymbol(out64, g_cnet_timeline, 64 * sizeof(unsigned long long)));
+  return GLOWK_OK;
 }
 
 }  // namespace cnet
 }  // namespace glowk
 
 using namespace glowk;
+
+extern "C" int glowk_debug_cnet_trace(unsigned long long* out16_host) { return cnet::debug_trace(out16_host); }
+extern "C" int glowk_debug_cnet_timeline(unsigned long long* out64_host) { return cnet::debug_timeline(out64_host); }
 
 extern "C" int glowk_cnet_fused_supported(int backward, int64_t K1, int64_t hidden, int64_t N3) {
   return cnet::chain_supported(backward, K1, hidden, N3) ? 1 : 0;

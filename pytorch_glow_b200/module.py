@@ -7,6 +7,8 @@ arithmetic runs in libglowk.so (hand-written sm_100a CUDA); there is no CPU path
 
 Citations are file:line in corenel/pytorch-glow.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -281,6 +283,21 @@ class CouplingNet(nn.Sequential):
     def dtype(self, override=None):
         return config.resolve_conv_dtype(self.hidden_channels, override)
 
+    def fused(self, backward):
+        """True iff the fused coupling-net kernels (glowk_cnet_forward / glowk_cnet_backward) serve this net's
+        shapes on the current device; GLOWK_CNET_FUSED=0 forces the three-GEMM path (A/B runs)."""
+        key = "_fused_bwd" if backward else "_fused_fwd"
+        ok = self.__dict__.get(key)
+        if ok is None:
+            if os.environ.get("GLOWK_CNET_FUSED", "1") == "0":
+                ok = False
+            elif backward:
+                ok = K.cnet_fused_supported(True, round_up(self.n3, 64), self.hidden_channels, self.k1p)
+            else:
+                ok = K.cnet_fused_supported(False, self.k1p, self.hidden_channels, self.n3p)
+            self.__dict__[key] = ok
+        return ok
+
     def packed(self, which, dt):
         """GEMM-layout weight copies, cached per parameter version (see glowk_pack_conv_weight)."""
         c1, c2, c3 = self[0], self[2], self[4]
@@ -325,6 +342,17 @@ class CouplingNet(nn.Sequential):
         kh = round_up(hid, 64)
         w1 = self.packed("w1", dt)
         an1, an2 = c1.actnorm, c2.actnorm
+        if dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False):
+            # one tcgen05 kernel for the three convs: h1 stays in tensor memory, h2 in shared memory
+            # (csrc/cnet_fused_sm100.cu); bit-identical to the three GEMMs below
+            p3, h1, h2 = K.cnet_forward(a1, w1, self.packed("w2", dt), self.packed("w3", dt), hid, self.n3p,
+                                        an1.bias.detach().reshape(-1), an1.logs.detach().reshape(-1),
+                                        an1.logscale_factor, an2.bias.detach().reshape(-1),
+                                        an2.logs.detach().reshape(-1), an2.logscale_factor, ldp3=self.n3p,
+                                        save=save is not None, ldh=kh)
+            if save is not None:
+                save.update(a1=a1, h1=h1, h2=h2)
+            return p3
         if an1.needs_init:
             an1.initialize_from_rows(K.gemm(a1, w1, hid, self.k1p, _C.EPI_STORE, out_dtype=_C.F32))
         h1 = K.gemm(a1, w1, hid, self.k1p, _C.EPI_ACTNORM_RELU, an1.bias.detach().reshape(-1),

@@ -404,23 +404,33 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     ones = _ones_col(net, dt) if defer else -1        # a1 carries a ones column: dbias of an1 = that column of dW1
     if ones >= 0:
         db1 = None
-    d2 = K.gemm(d3col, net.packed("w3t", dt), hid, k3p, _C.EPI_RELU_BWD, None, an2.logs.detach().reshape(-1),
-                an2.logscale_factor, y=h2, dlogs=dl2, dbias=db2, out_dtype=dt, ldo=kh)
+    k1p = net.k1p
+    wide = _is_wide(c)
+    fused = defer and not wide and net.fused(True)
+    if fused:
+        # dgrad3 -> ReLU' / ActNorm scale -> dgrad2 -> ReLU' / ActNorm scale -> dgrad1 in ONE kernel: d2 feeds dgrad2
+        # from tensor memory, d1 feeds dgrad1 from shared memory; both are stored once for the wgrad GEMMs
+        d2, d1, da1 = K.cnet_backward(d3col, net.packed("w3t", dt), net.packed("w2t", dt), net.packed("w1t", dt), hid,
+                                      k1p, an2.logs.detach().reshape(-1), an2.logscale_factor,
+                                      an1.logs.detach().reshape(-1), an1.logscale_factor, h2, h1, dbias2=db2, dbias1=db1)
+    else:
+        d2 = K.gemm(d3col, net.packed("w3t", dt), hid, k3p, _C.EPI_RELU_BWD, None, an2.logs.detach().reshape(-1),
+                    an2.logscale_factor, y=h2, dlogs=dl2, dbias=db2, out_dtype=dt, ldo=kh)
     # (3) conv2 (1x1)
     dw2 = plan.view(step, "w2")
     K.gemm_wgrad(d2, h1, hid, hid, dw2)
-    d1 = K.gemm(d2, net.packed("w2t", dt), hid, hid, _C.EPI_RELU_BWD, None, an1.logs.detach().reshape(-1),
-                an1.logscale_factor, y=h1, dlogs=dl1, dbias=db1, out_dtype=dt, ldo=kh)
+    if not fused:
+        d1 = K.gemm(d2, net.packed("w2t", dt), hid, hid, _C.EPI_RELU_BWD, None, an1.logs.detach().reshape(-1),
+                    an1.logscale_factor, y=h1, dlogs=dl1, dbias=db1, out_dtype=dt, ldo=kh)
     # (4) conv1 (im2col form); its dgrad is gather-summed inside the mix adjoint below
-    k1p = net.k1p
     K.gemm_wgrad(d1, a1, hid, k1p, plan.view(step, "w1"))
     if defer:
         plan.defer_dlogs(net.packed("w2", dt), dw2, an2, db2, hid, hid)
         plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
     # bf16 path: the nine-tap partial gradients are stored in bf16 (they are products of bf16 operands already) and
     # summed in fp32 by the mix adjoint
-    wide = _is_wide(c)
-    da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32 if wide else dt)
+    if not fused:
+        da1 = K.gemm(d1, net.packed("w1t", dt), k1p, hid, _C.EPI_STORE, out_dtype=_C.F32 if wide else dt)
     # (5) ActNorm + mix
     dense = step.permutation == 'invconv' and not step.invconv.lu_decomposition
     gw = _gbuf(step.invconv.weight) if dense else None

@@ -28,6 +28,33 @@ def timeit(fn, iters, warmup=3):
     return e0.elapsed_time(e1) / iters * 1e3      # us
 
 
+def trace(label):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 16)()
+    _C.lib().glowk_debug_cnet_trace(buf)
+    v = list(buf)
+    tiles = max(1, v[9])
+    names = ["a_full", "acc_empty1", "ring1", "h1_full", "acc_empty2", "ring2", "h2_full", "ring3", "MMA_total", "tiles",
+             "prod_wait", "prod_total", "epi_acc1", "epi_acc2", "epi_c3", "epi_total"]
+    print("  trace %s (cycles per tile, CTA 0, %d tiles): " % (label, tiles) +
+          "  ".join("%s=%d" % (n, x // tiles) for n, x in zip(names, v) if n != "tiles"))
+
+
+def timeline(label):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 64)()
+    _C.lib().glowk_debug_cnet_timeline(buf)
+    v = list(buf)
+    t0 = v[0]
+    rel = lambda i: (v[i] - t0) if v[i] else -1
+    print("  timeline %s (cycles from tile start)" % label)
+    print("    MMA : a_full %d | GEMM1 free/issued %s | h1_full %d" % (rel(1), [(rel(2 + 2 * c), rel(3 + 2 * c)) for c in range(4)], rel(10)))
+    print("          GEMM2 free/issued/g3 %s | c3 commit %d" % ([(rel(11 + 3 * c), rel(12 + 3 * c), rel(13 + 3 * c)) for c in range(4)], rel(24)))
+    print("    EPI1: seen/released/published %s" % [(rel(32 + 3 * c), rel(33 + 3 * c), rel(34 + 3 * c)) for c in range(4)])
+    print("    EPI2: seen/released/published %s" % [(rel(44 + 3 * c), rel(45 + 3 * c), rel(46 + 3 * c)) for c in range(4)])
+    print("    EPI3: c3_full seen %d drained %d" % (rel(56), rel(57)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--m", type=int, default=524288)
@@ -36,6 +63,7 @@ def main():
     ap.add_argument("--k3", type=int, default=128)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--skip-bwd", action="store_true")
+    ap.add_argument("--fused-only", action="store_true")
     a = ap.parse_args()
     m, k1, n3, k3 = a.m, a.k1, a.n3, a.k3
     dev = "cuda"
@@ -51,12 +79,16 @@ def main():
         h2 = K.gemm(h1, w2, HID, HID, _C.EPI_ACTNORM_RELU, b2, l2, 3.0, out_dtype=_C.BF16)
         return K.gemm(h2, w3, n3, HID, _C.EPI_STORE, out_dtype=_C.F32)
 
-    t3 = timeit(three, a.iters)
+    t3 = 1.0 if a.fused_only else timeit(three, a.iters)
     print("fwd three GEMMs      : %8.1f us  %7.1f TFLOP/s" % (t3, flops_f / t3 * 1e-6))
     if K.cnet_fused_supported(False, k1, HID, n3):
         for save in (False, True):
             tf = timeit(lambda: K.cnet_forward(a1, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0, save=save), a.iters)
             print("fwd fused (save=%d)   : %8.1f us  %7.1f TFLOP/s  (x%.2f)" % (save, tf, flops_f / tf * 1e-6, t3 / tf))
+            if os.environ.get("GLOWK_CNET_DEBUG"):
+                trace("fwd save=%d" % save)
+                if int(os.environ["GLOWK_CNET_DEBUG"]) & 16:
+                    timeline("fwd save=%d" % save)
     else:
         print("fwd fused: shape not supported")
     if a.skip_bwd:
@@ -81,6 +113,10 @@ def main():
         print("bwd fused (dbias2)   : %8.1f us  %7.1f TFLOP/s  (x%.2f)" % (tf, flops_b / tf * 1e-6, t3 / tf))
         tf = timeit(lambda: K.cnet_backward(d3, w3t, w2t, w1t, HID, k1p, l2, 3.0, l1, 3.0, h2, h1), a.iters)
         print("bwd fused (no dbias) : %8.1f us  %7.1f TFLOP/s  (x%.2f)" % (tf, flops_b / tf * 1e-6, t3 / tf))
+        if os.environ.get("GLOWK_CNET_DEBUG"):
+            trace("bwd")
+            if int(os.environ["GLOWK_CNET_DEBUG"]) & 16:
+                timeline("bwd")
     else:
         print("bwd fused: shape not supported")
 
