@@ -265,6 +265,11 @@ int glowk_optim_clip_norm(float* grads, int64_t n, float clip_value, float max_n
 int glowk_optim_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                      const float* norm_coef, const float* sched_dev, float lr, float beta1, float beta2,
                      float eps, int64_t step, void* stream);
+/* Fills sched_dev = [noam_lr(step), 1-beta1^(step+1), sqrt(1-beta2^(step+1))] from the DEVICE counter *step_dev
+ * (int64, completed iterations) and increments it: misc/lr_scheduler.py:18-37 (noam_decay; warmup_steps = 0 gives
+ * the constant base_lr, min_lr < 0 = none) + the bias corrections of torch.optim.Adam, inside a captured graph. */
+int glowk_optim_schedule(void* step_dev, float* sched_dev, float base_lr, int64_t warmup_steps, float min_lr,
+                         float beta1, float beta2, void* stream);
 
 /* =========================== pixel-major ("rows") flow state ================================
  * FlowModel.encode / decode (network/model.py:263-294) keep the flow state between the NCHW tensors of

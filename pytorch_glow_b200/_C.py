@@ -63,6 +63,7 @@ SIGNATURES = {
     "glowk_optim_workspace_floats": [],
     "glowk_optim_clip_norm": [_p, _i64, _f32, _f32, _p, _p],
     "glowk_optim_adam": [_p, _p, _p, _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _i64, _p],
+    "glowk_optim_schedule": [_p, _p, _f32, _i64, _f32, _f32, _f32, _p],
     "glowk_rows_max_channels": [],
     "glowk_rows_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p],
     "glowk_rows_coupling_nblk": [_i64, _i64],

@@ -54,7 +54,7 @@ struct Shared {
   uint64_t h1_full;
   uint64_t h2_full[MAX_HB], h2_empty[MAX_HB];
   uint64_t c3_full, c3_empty;
-  uint64_t y_bar[EPI_WARPS];
+  uint64_t y_bar[2 * EPI_WARPS];   // backward: two mask boxes in flight per epilogue warp
   uint32_t tmem_base;
 };
 
@@ -118,6 +118,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // two fp32 FMAs in one instruction
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b),
+                     uc = *reinterpret_cast<unsigned long long*>(&c), ud;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  return *reinterpret_cast<float2*>(&ud);
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 128-byte row `lane` of a [32 rows][128 B] SWIZZLE_128B box: 16-byte piece j lives at (j ^ (lane & 7)) * 16
@@ -155,8 +161,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   uint8_t* a_smem = smem;                                          // K1B K-blocks [128][64] bf16
   uint8_t* ring = a_smem + (size_t)p.K1B * BOX_BYTES;
   uint8_t* hb = ring + (size_t)p.nstages * stage_bytes;            // nhb chunk buffers [128][128] bf16
-  uint8_t* ysm = hb + (size_t)p.nhb * HB_BYTES;                    // BWD: one [32][64] bf16 mask box per epilogue warp
-  float* s_vec = reinterpret_cast<float*>(ysm + (BWD ? EPI_WARPS * 4096 : 0));
+  float* s_vec = reinterpret_cast<float*>(hb + (size_t)p.nhb * HB_BYTES);
   float* s_sc1 = s_vec;                 // [512] exp(f*logs)
   float* s_sc2 = s_vec + HID;
   float* s_x1 = s_vec + 2 * HID;        // FWD: shift = bias*scale ; BWD: column sums (dbias)
@@ -180,7 +185,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     mbar_init(&sh->h1_full, EPI_WARPS * NCHUNK);
     for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], EPI_WARPS); mbar_init(&sh->h2_empty[b], 1); }
     mbar_init(&sh->c3_full, 1); mbar_init(&sh->c3_empty, EPI_WARPS);
-    for (int q = 0; q < EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
+    for (int q = 0; q < 2 * EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -388,24 +393,23 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int row0 = quarter * 32;
     const uint32_t lane_taddr = tmem_base + ((uint32_t)row0 << 16);
     const size_t my_off = (size_t)g * BOX_BYTES + (size_t)quarter * 4096;   // this warp's [32 rows][64 k] slice of a chunk buffer
-    uint8_t* ybox = ysm + (size_t)ew * 4096;
-    uint32_t ycount = 0;
     const bool no_epi = (p.dbg & 4) != 0;
-    // mask boxes (BWD): this warp's sequence is tile-major, then EPI1 chunks 0..3 (y1), then EPI2 chunks 0..3 (y2)
+    // Backward: the ReLU masks (the saved forward activations, [32 rows][64 columns] bf16 per warp and chunk) are
+    // TMA-loaded straight into this warp's slice of chunk buffer (c & 1) -- the slice the gradient of the same chunk
+    // is then written to in place -- so two mask boxes are in flight per warp (they come from HBM: ~1500 cycles)
+    // without any extra shared memory.  A slice may be refilled once the TMA store / GEMM3 partial that last read it
+    // has retired.
     auto issue_y = [&](int tile, int ph, int c) {
       if (lane == 0) {
-        mbar_arrive_expect_tx(&sh->y_bar[ew], 4096);
-        tma_load_2d(ph ? &tm_y2 : &tm_y1, &sh->y_bar[ew], ybox, c * NC + g * 64, tile * BLOCK_M + row0);
+        uint64_t* bar = &sh->y_bar[ew * 2 + (c & 1)];
+        mbar_arrive_expect_tx(bar, 4096);
+        tma_load_2d(ph ? &tm_y2 : &tm_y1, bar, hb + (size_t)(c & 1) * HB_BYTES + my_off, c * NC + g * 64, tile * BLOCK_M + row0);
       }
-    };
-    auto issue_next_y = [&](int tile, int ph, int c) {
-      if (++c == NCHUNK) { c = 0; ph ^= 1; if (ph == 0) tile += gridDim.x; }
-      if (tile < num_tiles) issue_y(tile, ph, c);
     };
     if (BWD && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, 0);
 
     // this warp's 32 rows x 64 columns of a chunk accumulator -> bf16 pairs; releases the accumulator
-    auto epilogue_chunk = [&](int c, int ph, uint32_t acc_col, uint64_t* rel_bar, uint32_t (&pk)[32]) {
+    auto epilogue_chunk = [&](int c, int ph, uint32_t acc_col, uint64_t* rel_bar, uint32_t (&pk)[32], int tl_rel, uint32_t tcnt) {
       if (no_epi) {                                                // profiling: barrier protocol only
         tcgen05_fence_before();
         __syncwarp();
@@ -417,30 +421,36 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t r0[32], r1[32];
       tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64), r0);
       tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64 + 32), r1);
-      if (BWD) mbar_wait(&sh->y_bar[ew], ycount & 1);
+      if (BWD) mbar_wait(&sh->y_bar[ew * 2 + (c & 1)], (tcnt * 4u + (uint32_t)(ph * 2 + (c >> 1))) & 1);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(rel_bar);                         // accumulator columns are in registers now
+      // keep the release AHEAD of the arithmetic: without this ptxas schedules the FMAs (which only depend on the
+      // loaded registers) before the arrive, and the MMA warp gets its accumulator back ~1000 cycles later
+#pragma unroll
+      for (int j = 0; j < 32; ++j) asm volatile("" : "+r"(r0[j]), "+r"(r1[j]));
+      if (tl_rel >= 0) CNET_TS(true, tl_rel);
       const float* sc = (ph ? s_sc2 : s_sc1) + c * NC + g * 64;
       if (!BWD) {
-        const float* sf = (ph ? s_x2 : s_x1) + c * NC + g * 64;
+        // packed arithmetic: one FFMA2 (fma.rn.f32x2) + one F2FP + one HMNMX2 per PAIR of elements.  relu after the
+        // bf16 rounding equals relu before it (rounding is monotonic and keeps the sign), so results stay bit-identical
+        // to the three-GEMM path.  Scale / shift come as LDS.128 broadcasts (warp-uniform addresses).
+        const float4* sc4 = reinterpret_cast<const float4*>(sc);
+        const float4* sf4 = reinterpret_cast<const float4*>((ph ? s_x2 : s_x1) + c * NC + g * 64);
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(fmaf(__uint_as_float(r0[2 * j]), sc[2 * j], sf[2 * j]), 0.f);
-          const float b = fmaxf(fmaf(__uint_as_float(r0[2 * j + 1]), sc[2 * j + 1], sf[2 * j + 1]), 0.f);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-          pk[j] = *reinterpret_cast<const uint32_t*>(&h);
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = fmaxf(fmaf(__uint_as_float(r1[2 * j]), sc[32 + 2 * j], sf[32 + 2 * j]), 0.f);
-          const float b = fmaxf(fmaf(__uint_as_float(r1[2 * j + 1]), sc[32 + 2 * j + 1], sf[32 + 2 * j + 1]), 0.f);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-          pk[16 + j] = *reinterpret_cast<const uint32_t*>(&h);
+          const float4 s4 = sc4[j], t4 = sf4[j];
+          const uint32_t* r = j < 8 ? &r0[4 * j] : &r1[4 * j - 32];
+          const float2 v0 = ffma2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(s4.x, s4.y), make_float2(t4.x, t4.y));
+          const float2 v1 = ffma2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
+          const __nv_bfloat162 h0 = __hmax2(__float22bfloat162_rn(v0), zero2), h1 = __hmax2(__float22bfloat162_rn(v1), zero2);
+          pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
+          pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
         }
       } else {
-        const uint8_t* yrow = ybox + lane * 128;
+        const uint8_t* yrow = hb + (size_t)(c & 1) * HB_BYTES + my_off + lane * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const uint4 yraw = *reinterpret_cast<const uint4*>(yrow + ((j4 ^ (lane & 7)) * 16));
@@ -451,14 +461,14 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const int j = j4 * 8 + u * 2;                          // column within this warp's 64
             const float ra = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
             const float rb = __uint_as_float(j < 32 ? r0[j + 1] : r1[j - 31]);
-            const float a = (yv.x > 0.f ? ra : 0.f) * sc[j];
-            const float b = (yv.y > 0.f ? rb : 0.f) * sc[j + 1];
+            const float2 s2 = *reinterpret_cast<const float2*>(sc + j);
+            const float a = (yv.x > 0.f ? ra : 0.f) * s2.x;
+            const float b = (yv.y > 0.f ? rb : 0.f) * s2.y;
             const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
             pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
           }
         }
-        ++ycount;
-        __syncwarp();                                              // every lane has read the mask box
+        __syncwarp();                                              // every lane has read its row of the mask box
       }
     };
 
@@ -473,17 +483,21 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       for (int c = 0; c < NCHUNK; ++c) {
         const int buf = c & 1;
         const uint32_t idx = buf ? tcount * 2u + (uint32_t)(c >> 1) : tcount * 6u + (uint32_t)(c >> 1);
+        if (BWD) {                                                 // next mask box -> the other slice
+          if (lane == 0) tma_store_wait_read<0>();                 // (my TMA store that last read it has retired)
+          __syncwarp();
+          if (c + 1 < NCHUNK) issue_y(tile, 0, c + 1); else issue_y(tile, 1, 0);
+        }
         wait_t(&sh->acc_full[buf], idx & 1, tr, e1);
         CNET_TS(tl, 32 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 0, buf ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf], pk);
-        CNET_TS(tl, 33 + 3 * c);
-        if (BWD) issue_next_y(tile, 0, c);                         // next mask box of this warp's sequence
+        epilogue_chunk(c, 0, buf ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf], pk, tl ? 33 + 3 * c : -1, tcount);
         if (p.deferred && c == 0) {                                // GEMM3's accumulator of the previous tile aliases h1
           mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
           tcgen05_fence_after();
         }
+        CNET_TS(tl && c == 1, 58);
         if (!no_epi) tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2) + g * 32), pk);
         if (BWD || p.save1) {
           uint8_t* stg = hb + (size_t)buf * HB_BYTES + my_off;     // chunk buffers are idle until EPI2
@@ -496,6 +510,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (BWD && p.dbias2) box_colsum_bf16(stg, lane, s_x2 + c * NC + g * 64);
         }
         tmem_st_wait();
+        CNET_TS(tl && c == 1, 59);
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->h1_full);
@@ -508,23 +523,32 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         CNET_TS(tl, 44 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 1, COL_ACC0, &sh->acc_empty[0], pk);
-        CNET_TS(tl, 45 + 3 * c);
-        if (BWD) issue_next_y(tile, 1, c);
+        epilogue_chunk(c, 1, COL_ACC0, &sh->acc_empty[0], pk, tl ? 45 + 3 * c : -1, tcount);
+        CNET_TS(tl && c == 1, 60);
         const int b = c % p.nhb;
         const uint32_t hidx = tcount * (uint32_t)upt + (uint32_t)(c / p.nhb);
         mbar_wait(&sh->h2_empty[b], (hidx & 1) ^ 1);               // GEMM3 partial that last read this buffer retired
         if (lane == 0) tma_store_wait_read<0>();                   // ... and so has my TMA store out of it
         __syncwarp();
+        CNET_TS(tl && c == 1, 61);
         uint8_t* slice = hb + (size_t)b * HB_BYTES + my_off;
         if (!no_epi) store_row_sw128(slice, lane, pk);
+        CNET_TS(tl && c == 1, 62);
         fence_proxy_async();
         __syncwarp();
+        CNET_TS(tl && c == 1, 63);
         if (lane == 0) {
           if (BWD || p.save2) { tma_store_2d(&tm_o2, slice, c * NC + g * 64, grow); tma_store_commit(); }
           mbar_arrive(&sh->h2_full[b]);
         }
         if (BWD && p.dbias1) box_colsum_bf16(slice, lane, s_x1 + c * NC + g * 64);
+        if (BWD && c + 1 < NCHUNK) {
+          // mask box of chunk c+1 -> slice (c+1)&1: GEMM3's partial sum for chunk c-1 read it last
+          if (c >= 1) mbar_wait(&sh->h2_empty[(c + 1) & 1], (tcount * (uint32_t)upt + (uint32_t)((c - 1) / p.nhb)) & 1);
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          issue_y(tile, 1, c + 1);
+        }
         CNET_TS(tl, 46 + 3 * c);
       }
       // ---- EPI3: GEMM3 accumulator -> global
@@ -532,20 +556,52 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       CNET_TS(tl, 56);
       tcgen05_fence_after();
       const int n3tot = p.NH * p.N3;
-      uint8_t* stg = hb + my_off;                                  // every GEMM3 partial of this tile has retired
+      // every GEMM3 partial of this tile has retired: the chunk buffers are free staging space.  The accumulator is
+      // released as soon as it sits in registers (GEMM1 of the next tile reuses its columns), the stores follow.
       if (!BWD) {
-        for (int j = g; j * 32 < n3tot; j += 2) {
-          uint32_t r[32];
-          tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 32), r);
+        for (int j = g; j * 32 < n3tot; j += 4) {                  // this warp: boxes j and j + 2 (32 fp32 columns each)
+          const bool two = (j + 2) * 32 < n3tot;
+          const bool last = (j + 4) * 32 >= n3tot;
+          uint32_t ra[32], rb[32];
+          tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 32), ra);
+          if (two) tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + (j + 2) * 32), rb);
           if (lane == 0) tma_store_wait_read<0>();
           tmem_ld_wait();
-          __syncwarp();
-          store_row_sw128(stg, lane, r);
+          if (last) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->c3_empty);
+#pragma unroll
+            for (int q = 0; q < 32; ++q) asm volatile("" : "+r"(ra[q]));
+            if (two) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) asm volatile("" : "+r"(rb[q]));
+            }
+          } else __syncwarp();
+          uint8_t* stg0 = hb + my_off;
+          uint8_t* stg1 = hb + HB_BYTES + my_off;
+          store_row_sw128(stg0, lane, ra);
+          if (two) store_row_sw128(stg1, lane, rb);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tma_store_2d(&tm_o3, stg, j * 32, grow); tma_store_commit(); }   // columns >= N, rows >= M clipped
+          if (lane == 0) {                                          // columns >= N and rows >= M are clipped by TMA
+            tma_store_2d(&tm_o3, stg0, j * 32, grow);
+            if (two) tma_store_2d(&tm_o3, stg1, (j + 2) * 32, grow);
+            tma_store_commit();
+          }
+        }
+        if (g * 32 >= n3tot) {                                      // (narrow N3: this warp had no box)
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh->c3_empty);
         }
       } else {
+        if ((int)(tile + gridDim.x) < num_tiles) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          issue_y(tile + gridDim.x, 0, 0);                          // first mask box of my next tile -> slice 0
+        }
+        uint8_t* stg = hb + HB_BYTES + my_off;
         for (int j = g; j * 64 < n3tot; j += 2) {
           uint32_t r0[32], r1[32], pk[32];
           tmem_ld32_async(lane_taddr + (uint32_t)(p.c3_col + j * 64), r0);
@@ -565,10 +621,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           __syncwarp();
           if (lane == 0) { tma_store_2d(&tm_o3, stg, j * 64, grow); tma_store_commit(); }
         }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->c3_empty);
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->c3_empty);
       CNET_TS(tl, 57);
     }
     if (tr && lane == 0) {
@@ -602,10 +658,11 @@ struct Variant { int NH, N3, nhb, c3_col, deferred, nstages, bps; size_t smem; }
 
 static bool pick_variant(int mode, int64_t K1, int64_t n3tot, Variant* v) {
   if (K1 <= 0 || K1 % 64 != 0 || n3tot <= 0 || n3tot % 16 != 0) return false;
+  if (mode == MODE_BWD && n3tot > 128) return false;           // the in-place mask boxes assume two chunk buffers
   if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
   else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 4; v->c3_col = COL_H; v->deferred = 1; }
   else return false;
-  const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES + (mode == MODE_BWD ? EPI_WARPS * 4096 : 0) +
+  const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES + 
                        4 * HID * sizeof(float) + sizeof(Shared) + 64;
   const size_t budget = 227 * 1024;
   if (fixed + 3 * (size_t)BOX_BYTES > budget) return false;

@@ -488,3 +488,31 @@ extern "C" int glowk_optim_adam(float* params, float* grads, float* exp_avg, flo
   GLOWK_CHECK_LAUNCH("glowk_optim_adam");
   return GLOWK_OK;
 }
+
+// Noam learning-rate schedule (misc/lr_scheduler.py:18-37) + Adam bias corrections from a DEVICE step counter, so a
+// captured optimizer graph follows the schedule without reading host memory (a pinned-host source can be overwritten
+// by the CPU before the GPU executes the copy).  One thread; double precision like the host arithmetic it replaces.
+__global__ void optim_schedule_kernel(long long* __restrict__ step, float* __restrict__ sched, double base_lr,
+                                      double warmup, double min_lr, double beta1, double beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const long long gs = *step;                       // completed iterations
+  const double t = (double)gs + 1.0;
+  double lr = base_lr;
+  if (warmup > 0.0) {
+    lr = base_lr * sqrt(warmup) * fmin(t * pow(warmup, -1.5), 1.0 / sqrt(t));
+    if ((double)gs >= warmup && min_lr >= 0.0) lr = fmax(lr, min_lr);
+  }
+  sched[0] = (float)lr;
+  sched[1] = (float)(1.0 - pow(beta1, t));
+  sched[2] = (float)sqrt(1.0 - pow(beta2, t));
+  *step = gs + 1;
+}
+
+extern "C" int glowk_optim_schedule(void* step_dev, float* sched_dev, float base_lr, int64_t warmup_steps, float min_lr,
+                                    float beta1, float beta2, void* stream) {
+  GLOWK_CHECK_ARG(step_dev && sched_dev && warmup_steps >= 0, "glowk_optim_schedule: bad arguments");
+  optim_schedule_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((long long*)step_dev, sched_dev, (double)base_lr,
+                                                            (double)warmup_steps, (double)min_lr, (double)beta1, (double)beta2);
+  GLOWK_CHECK_LAUNCH("glowk_optim_schedule");
+  return GLOWK_OK;
+}

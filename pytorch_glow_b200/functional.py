@@ -371,6 +371,13 @@ def optim_adam(params, grads, exp_avg, exp_avg_sq, workspace, step, lr, beta1, b
          ptr(sched), float(lr), float(beta1), float(beta2), float(eps), int(step))
 
 
+def optim_schedule(step_dev, sched_dev, base_lr, warmup_steps, min_lr, beta1, beta2):
+    """sched_dev <- [lr, 1-beta1^t, sqrt(1-beta2^t)] for the iteration counted by the device int64 step_dev; ++step_dev."""
+    assert step_dev.dtype == torch.int64 and sched_dev.dtype == torch.float32
+    call("glowk_optim_schedule", ptr(step_dev), ptr(sched_dev), float(base_lr), int(warmup_steps),
+         -1.0 if min_lr is None else float(min_lr), float(beta1), float(beta2))
+
+
 # ------------------------------------------------------------------ pixel-major ("rows") flow state
 NCHW, ROWS = 0, 1
 

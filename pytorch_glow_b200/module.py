@@ -53,8 +53,10 @@ class _PackCache:
     def __init__(self):
         self._d = {}
 
-    def get(self, key, param, build):
-        tag = (param.data_ptr(), param._version, param.device, _WEIGHT_GENERATION[0])
+    def get(self, key, param, build, extra=()):
+        """`extra`: further validity components (versions of sibling parameters); a stale entry is OVERWRITTEN under
+        the same key, never accumulated."""
+        tag = (param.data_ptr(), param._version, param.device, _WEIGHT_GENERATION[0]) + tuple(extra)
         hit = self._d.get(key)
         if hit is not None and hit[0] == tag:
             return hit[1]
@@ -431,10 +433,11 @@ class Invertible1x1Conv(nn.Module):
             w = self.weight
             ld, winv = self._cache.get(("dense", need_inverse), w, lambda: K.invconv_prepare(w.detach(), need_inverse))
             return w.detach(), winv, ld
-        tagp = self.log_s  # all LU params change together under an optimizer step
-        key = ("lu", need_inverse, self.l._version, self.u._version)
-        w, winv, ld = self._cache.get(key, tagp, lambda: K.invconv_lu_assemble(
-            self.p, self.l.detach(), self.u.detach(), self.sign_s, self.log_s.detach(), need_inverse))
+        # fixed key: a torch optimizer bumps the versions of l / u / log_s every step, and a key that contained them
+        # would leave one dead (W, W^-1, logdet) triple per step behind; the versions are validity tags
+        extra = (self.l._version, self.u._version, self.l.data_ptr(), self.u.data_ptr())
+        w, winv, ld = self._cache.get(("lu", need_inverse), self.log_s, lambda: K.invconv_lu_assemble(
+            self.p, self.l.detach(), self.u.detach(), self.sign_s, self.log_s.detach(), need_inverse), extra=extra)
         return w, winv, ld
 
     def dense_weight(self):

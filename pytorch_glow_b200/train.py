@@ -99,9 +99,12 @@ class FusedTrainStep:
         self.exp_avg = torch.zeros_like(self.arena.flat)
         self.exp_avg_sq = torch.zeros_like(self.arena.flat)
         self.ws = K.optim_workspace(dev)
-        self.sched_host = torch.zeros(4, dtype=torch.float32).pin_memory() if dev.type == "cuda" else torch.zeros(4)
+        # [lr, 1-beta1^t, sqrt(1-beta2^t)] are computed ON THE DEVICE from a device step counter inside the
+        # (captured) optimizer step: no host memory is read when the GPU gets there, however far the CPU ran ahead
         self.sched_dev = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         self.global_step = 0
+        self._inited_ok = False
         self.use_graphs = use_graphs
         self._g_fb = self._g_opt = None
         self._static_x = None
@@ -116,13 +119,63 @@ class FusedTrainStep:
         if self.world_size > 1:
             dist.broadcast(self.arena.flat, src=0, group=self.pg)    # rank 0's initialisation wins
 
-    def _set_schedule(self):
-        lr = noam_lr(self.base_lr, self.global_step, self.warmup_steps, self.min_lr)
-        t = self.global_step + 1
-        self.sched_host[0] = lr
-        self.sched_host[1] = 1.0 - self.betas[0] ** t
-        self.sched_host[2] = math.sqrt(1.0 - self.betas[1] ** t)
-        return lr
+    @property
+    def lr(self):
+        """Learning rate of the NEXT iteration (host mirror of the device schedule, trainer.py:89-92)."""
+        return noam_lr(self.base_lr, self.global_step, self.warmup_steps, self.min_lr)
+
+    def _check_inited(self):
+        """The data-dependent ActNorm init must have run (init_actnorm / a loaded snapshot) before an iteration is
+        captured or stepped: a graph warm-up would otherwise initialise from the warm-up batch and then restore the
+        pre-init arena while the `inited` flags stay set."""
+        for m in self.glow.modules():
+            if m.__class__.__name__.find("ActNorm") >= 0 and not (m.bias_inited and m.logs_inited):
+                raise RuntimeError("FusedTrainStep.step: ActNorm layers are not initialised -- call init_actnorm(x) on "
+                                   "the first batch (trainer.py:112-115) or load a snapshot first")
+
+    # -- torch.optim.Adam wire format (builder.py:91-93 `optimizer.load_state_dict(state['optimizer'])`)
+    def state_dict(self):
+        """Adam state in torch.optim.Adam's layout, parameter indices in `glow.parameters()` order."""
+        index = {id(p): i for i, p in enumerate(self.glow.parameters())}
+        state = {}
+        step_t = float(self.global_step)
+        for p, o in zip(self.arena.params, self.arena.offsets):
+            n = p.numel()
+            state[index[id(p)]] = {"step": torch.tensor(step_t),
+                                   "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
+                                   "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "decoupled_weight_decay": False, "params": list(range(len(index)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        """Accepts what `state_dict()` / a torch.optim.Adam over `glow.parameters()` produced; restores the moments
+        and the iteration count (Noam schedule + bias corrections resume where they stopped)."""
+        index = {id(p): i for i, p in enumerate(self.glow.parameters())}
+        st = sd.get("state", {})
+        steps = []
+        for p, o in zip(self.arena.params, self.arena.offsets):
+            e = st.get(index[id(p)])
+            if e is None:
+                e = st.get(str(index[id(p)]))
+            n = p.numel()
+            if e is None:                       # a parameter that never received a gradient has no entry
+                self.exp_avg[o:o + n].zero_(); self.exp_avg_sq[o:o + n].zero_()
+                continue
+            self.exp_avg[o:o + n].copy_(e["exp_avg"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(e["exp_avg_sq"].reshape(-1))
+            steps.append(int(float(e["step"])))
+        if steps:
+            self.set_global_step(max(steps))
+        groups = sd.get("param_groups") or []
+        if groups:
+            self.betas = tuple(groups[0].get("betas", self.betas))
+            self.eps = groups[0].get("eps", self.eps)
+
+    def set_global_step(self, step):
+        self.global_step = int(step)
+        self.step_dev.fill_(int(step))
 
     def _forward_backward(self, x):
         self.arena.grad.zero_()
@@ -133,7 +186,8 @@ class FusedTrainStep:
         return loss.detach()
 
     def _optimizer(self):
-        self.sched_dev.copy_(self.sched_host, non_blocking=True)
+        K.optim_schedule(self.step_dev, self.sched_dev, self.base_lr, self.warmup_steps, self.min_lr, self.betas[0],
+                         self.betas[1])
         K.optim_clip_norm(self.arena.grad, self.max_grad_clip, self.max_grad_norm, self.ws)
         K.optim_adam(self.arena.flat, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.ws, self.global_step + 1,
                      0.0, self.betas[0], self.betas[1], self.eps, sched=self.sched_dev)
@@ -146,7 +200,9 @@ class FusedTrainStep:
         """One training iteration on the device batch x [B,3,H,W] in [0,1).  Returns the loss (bits/dim)
         as a 0-dim device tensor."""
         self.glow.train()
-        self._set_schedule()
+        if not self._inited_ok:
+            self._check_inited()
+            self._inited_ok = True
         if not self.use_graphs:
             loss = self._forward_backward(x)
             self._allreduce()
@@ -175,7 +231,7 @@ class FusedTrainStep:
         # that every pack / LU kernel is part of the graph and re-runs on each replay
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
-        saved = (self.arena.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone())
+        saved = (self.arena.flat.clone(), self.exp_avg.clone(), self.exp_avg_sq.clone(), self.step_dev.clone())
         with torch.cuda.stream(s):
             for _ in range(2):
                 _module.bump_weight_generation()
@@ -184,6 +240,7 @@ class FusedTrainStep:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.arena.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
+        self.step_dev.copy_(saved[3])
         _module.bump_weight_generation()
         from . import _C
         c0 = _C.launch_count

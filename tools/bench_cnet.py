@@ -53,6 +53,8 @@ def timeline(label):
     print("    EPI1: seen/released/published %s" % [(rel(32 + 3 * c), rel(33 + 3 * c), rel(34 + 3 * c)) for c in range(4)])
     print("    EPI2: seen/released/published %s" % [(rel(44 + 3 * c), rel(45 + 3 * c), rel(46 + 3 * c)) for c in range(4)])
     print("    EPI3: c3_full seen %d drained %d" % (rel(56), rel(57)))
+    print("    EPI1 chunk 1: math done %d, tmem st done %d | EPI2 chunk 1: math done %d, buffer free %d, stored %d, fenced %d"
+          % (rel(58), rel(59), rel(60), rel(61), rel(62), rel(63)))
 
 
 def main():
