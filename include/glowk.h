@@ -177,6 +177,17 @@ int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1
                        const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden, int64_t N3,
                        const float* bias1, const float* logs1, float f1, const float* bias2, const float* logs2,
                        float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* stream);
+/* Same with conv1 as an IMPLICIT GEMM (module.py:252 F.conv2d 3x3, SAME zero padding): the kernel gathers the
+ * im2col tile of channels c0 .. c0+Cin-1 of the pixel-major flow state z ([N*H*W][ld_z] fp32) itself -- exactly what
+ * glowk_im2col_rows would have written (k = tap*Cin + ci, bf16 rounding, zero padding columns, ones_col >= 9*Cin set
+ * to 1.0 or -1) -- so neither that kernel nor its output exist when sampling.  a1_save (nullable, [M][lda] bf16)
+ * receives the tile for the weight gradient of conv1 when training. */
+int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H, int64_t W,
+                                int64_t ones_col, void* a1_save, int64_t lda, const void* w1, int64_t ldw1,
+                                const void* w2, int64_t ldw2, const void* w3, int64_t ldw3, int64_t K1, int64_t hidden,
+                                int64_t N3, const float* bias1, const float* logs1, float f1, const float* bias2,
+                                const float* logs2, float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save,
+                                int64_t ldh, void* stream);
 /* Adjoint chain of the same network (autograd of module.py:300-319) in one kernel:
  *   d2 = [h2 > 0] * (d3col . w3t^T) * exp(f2*logs2)   -> TMEM A operand + stored [M][ldh] bf16 (wgrad operand)
  *   d1 = [h1 > 0] * (d2 . w2t^T) * exp(f1*logs1)      -> shared-memory chunk + stored [M][ldh] bf16

@@ -48,6 +48,8 @@ SIGNATURES = {
     "glowk_cnet_fused_supported": [_i32, _i64, _i64, _i64],
     "glowk_cnet_forward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32,
                            _p, _i64, _p, _p, _i64, _p],
+    "glowk_cnet_forward_implicit": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
+                                    _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p],
     "glowk_cnet_backward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _f32, _p, _f32, _p, _p,
                             _p, _p, _i64, _p, _i64, _p, _p, _p],
     "glowk_coupling_nblk": [_i64],

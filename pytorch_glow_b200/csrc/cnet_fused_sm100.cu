@@ -41,7 +41,8 @@ constexpr int NCHUNK = HID / NC;          // 4
 constexpr int BOX_BYTES = 16384;          // one [128 n][64 k] bf16 weight box (also one K-block of an A tile)
 constexpr int HB_BYTES = 32768;           // one [128][128] bf16 chunk = two K-blocks
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
+constexpr int GATHER_WARPS = 2;               // implicit-GEMM conv1: these warps build the im2col tile in shared memory
+constexpr int THREADS = 64 + 32 * EPI_WARPS + 32 * GATHER_WARPS;
 constexpr int COL_H = 0, COL_ACC0 = 256, COL_ACC1 = 384, COL_C3 = 384;
 constexpr int MAX_STAGES = 8, MAX_HB = 4;
 
@@ -64,6 +65,10 @@ struct Params {
   const float *bias1, *logs1, *bias2, *logs2;
   float f1, f2;
   float *dbias1, *dbias2;     // backward: column sums of the stored d2 (EPI1) / d1 (EPI2), nullable
+  // implicit conv1 (forward): the A tile is gathered in-kernel from the pixel-major flow state z [P][ld_z] fp32,
+  // channels c0 .. c0+Cin-1, 3x3 taps with zero padding, k = tap*Cin + ci (glowk_im2col_rows); gather = 0: TMA load
+  const float* z;
+  int gather, ld_z, c0, Cin, H, W, ones_col, save_a;
 };
 
 // Profiling aid (GLOWK_CNET_DEBUG=1): wait cycles of CTA 0's roles, read back by glowk_debug_cnet_trace.
@@ -180,7 +185,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (BWD || p.save2) prefetch_tensormap(&tm_o2);
     if (BWD) { prefetch_tensormap(&tm_y1); prefetch_tensormap(&tm_y2); }
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&sh->ring_full[s], 1); mbar_init(&sh->ring_empty[s], 1); }
-    mbar_init(&sh->a_full, 1); mbar_init(&sh->a_empty, 1);
+    mbar_init(&sh->a_full, p.gather ? GATHER_WARPS : 1); mbar_init(&sh->a_empty, 1);
     for (int g = 0; g < 2; ++g) { mbar_init(&sh->acc_full[g], 1); mbar_init(&sh->acc_empty[g], EPI_WARPS); }
     mbar_init(&sh->h1_full, EPI_WARPS * NCHUNK);
     for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], EPI_WARPS); mbar_init(&sh->h2_empty[b], 1); }
@@ -229,10 +234,12 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       };
       uint32_t tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
-        wait_t(&sh->a_empty, (tcount & 1) ^ 1, tr, w_e);
-        mbar_arrive_expect_tx(&sh->a_full, (uint32_t)p.K1B * BOX_BYTES);
-        for (int kb = 0; kb < p.K1B; ++kb)
-          tma_load_2d(&tm_a, &sh->a_full, a_smem + (size_t)kb * BOX_BYTES, kb * BLOCK_K, tile * BLOCK_M);
+        if (!p.gather) {
+          wait_t(&sh->a_empty, (tcount & 1) ^ 1, tr, w_e);
+          mbar_arrive_expect_tx(&sh->a_full, (uint32_t)p.K1B * BOX_BYTES);
+          for (int kb = 0; kb < p.K1B; ++kb)
+            tma_load_2d(&tm_a, &sh->a_full, a_smem + (size_t)kb * BOX_BYTES, kb * BLOCK_K, tile * BLOCK_M);
+        }
         for (int c = 0; c < NCHUNK; ++c) fill(&tm_w1, p.K1B, 0, c * NC, BOX_BYTES);
         for (int c = 0; c < NCHUNK; ++c) {
           fill(&tm_w2, HID / BLOCK_K, 0, c * NC, BOX_BYTES);
@@ -386,6 +393,64 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       g_cnet_trace[0] = w0; g_cnet_trace[1] = w1; g_cnet_trace[2] = w2; g_cnet_trace[3] = w3; g_cnet_trace[4] = w4;
       g_cnet_trace[5] = w5; g_cnet_trace[6] = w6; g_cnet_trace[7] = w7;
       g_cnet_trace[8] = (unsigned long long)(clock64() - t_begin); g_cnet_trace[9] = tcount;
+    }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ===================== conv1 operand gather (implicit GEMM) =====================
+    // One thread per pair of tile rows (pixels): reads the nine 3x3 taps of channels c0..c0+Cin-1 of the fp32 flow
+    // state, rounds to bf16 and writes the K-major, 128B-swizzled A tile the MMA warp reads -- the job of
+    // glowk_im2col_rows, without the HBM round trip of its output.  Training keeps the tile for the weight gradient
+    // of conv1 (TMA store to a1_save) and sets the ones column (bias gradient through the wgrad GEMM).
+    if (!BWD && p.gather) {
+      const int gt = (int)threadIdx.x - 32 * (2 + EPI_WARPS);      // 0 .. 63
+      const int HW = p.H * p.W, K = 9 * p.Cin, K1 = p.K1B * BLOCK_K;
+      uint32_t tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+        mbar_wait(&sh->a_empty, (tcount & 1) ^ 1);                 // GEMM1 of the previous tile has read the tile
+        if (p.save_a) {
+          if (gt == 0) tma_store_wait_read<0>();                   // ... and so has my TMA store of it
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * GATHER_WARPS) : "memory");
+        }
+        for (int rr = 0; rr < BLOCK_M / (32 * GATHER_WARPS); ++rr) {
+          const int r = rr * 32 * GATHER_WARPS + gt;
+          const int pix = tile * BLOCK_M + r;
+          const bool row_ok = pix < p.M;
+          const int nimg = pix / HW, rem = pix - nimg * HW;
+          const int yy = rem / p.W, xx = rem - yy * p.W;
+          const uint32_t row_base = smem_u32(a_smem) + (uint32_t)r * 128u;
+          const uint32_t sw = (uint32_t)(r & 7);
+          int k = 0;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const bool ok = row_ok && (unsigned)(yy + dy) < (unsigned)p.H && (unsigned)(xx + dx) < (unsigned)p.W;
+            const float* src = p.z + (int64_t)(pix + dy * p.W + dx) * p.ld_z + p.c0;
+            for (int ci = 0; ci < p.Cin; ci += 2, k += 2) {
+              float2 v = make_float2(0.f, 0.f);
+              if (ok) v = *reinterpret_cast<const float2*>(src + ci);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+              const uint32_t addr = row_base + (uint32_t)(k >> 6) * BOX_BYTES + ((((uint32_t)(k & 63) >> 3) ^ sw) << 4) + (uint32_t)(k & 7) * 2u;
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
+            }
+          }
+          for (; k < K1; k += 2) {                                  // zero padding (+ the ones column)
+            const float lo = (k == p.ones_col) ? 1.f : 0.f, hi = (k + 1 == p.ones_col) ? 1.f : 0.f;
+            const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+            const uint32_t addr = row_base + (uint32_t)(k >> 6) * BOX_BYTES + ((((uint32_t)(k & 63) >> 3) ^ sw) << 4) + (uint32_t)(k & 7) * 2u;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h)) : "memory");
+          }
+          (void)K;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->a_full);
+        if (p.save_a) {
+          asm volatile("bar.sync 2, %0;" ::"n"(32 * GATHER_WARPS) : "memory");
+          if (gt == 0) {
+            for (int kb = 0; kb < p.K1B; ++kb) tma_store_2d(&tm_a, a_smem + (size_t)kb * BOX_BYTES, kb * BLOCK_K, tile * BLOCK_M);
+            tma_store_commit();
+          }
+        }
+      }
+      if (p.save_a && gt == 0) tma_store_wait_all();
     }
   } else {
     // ===================== epilogue warps =====================
@@ -694,7 +759,9 @@ static int launch_chain(const CUtensorMap* tm, const Params& p, size_t smem, cud
 
 // A: [M][K1] (lda), W1: [512][K1], W2: [512][512], W3: [n3tot][512]; o1/o2/y1/y2: [M][512] bf16 (ldh);
 // o3: forward fp32 [M][n3tot] (ldo3), backward bf16 [M][n3tot] (ldo3).
-int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
+struct Gather { const float* z; int64_t ld_z, c0, Cin, H, W, ones_col; };
+
+int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
                  const void* W3, int64_t ldw3, int64_t M, int64_t K1, int64_t n3tot, const float* bias1,
                  const float* logs1, float f1, const float* bias2, const float* logs2, float f2, void* o1, void* o2,
                  int64_t ldh, const void* y1, const void* y2, void* o3, int64_t ldo3, float* dbias1, float* dbias2,
@@ -705,6 +772,15 @@ int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64
     return fail(GLOWK_EUNSUP, "glowk_cnet_%s: unsupported shape K1=%lld N3=%lld", backward ? "backward" : "forward",
                 (long long)K1, (long long)n3tot);
   GLOWK_CHECK_ARG(M > 0 && M < (1ll << 31), "glowk_cnet: bad M");
+  int gth_save_a = 0;
+  if (gth) {
+    gth_save_a = A != nullptr;
+    GLOWK_CHECK_ARG(!backward && gth->z && gth->Cin > 0 && gth->Cin % 2 == 0 && gth->c0 % 2 == 0 && gth->ld_z % 2 == 0 &&
+                    ((uintptr_t)gth->z) % 8 == 0 && 9 * gth->Cin <= K1 && gth->H > 0 && gth->W > 0 && M % (gth->H * gth->W) == 0 &&
+                    (gth->ones_col < 0 || (gth->ones_col >= 9 * gth->Cin && gth->ones_col < K1)),
+                    "glowk_cnet_forward_implicit: bad gather arguments");
+    if (!A) { A = W1; lda = K1; }                       // no a1 copy kept: any valid encoding for the unused map
+  }
   GLOWK_CHECK_ARG(lda % 8 == 0 && ldw1 % 8 == 0 && ldw2 % 8 == 0 && ldw3 % 8 == 0 && ldh % 8 == 0,
                   "glowk_cnet: bf16 row pitches must be multiples of 8 elements");
   GLOWK_CHECK_ARG((((uintptr_t)A | (uintptr_t)W1 | (uintptr_t)W2 | (uintptr_t)W3 | (uintptr_t)o1 | (uintptr_t)o2 |
@@ -736,6 +812,10 @@ int chain_launch(int backward, const void* A, int64_t lda, const void* W1, int64
   { const char* e = getenv("GLOWK_CNET_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
   p.dbias1 = dbias1; p.dbias2 = dbias2;
+  p.z = gth ? gth->z : nullptr; p.gather = gth ? 1 : 0;
+  if (gth) { p.ld_z = (int)gth->ld_z; p.c0 = (int)gth->c0; p.Cin = (int)gth->Cin; p.H = (int)gth->H; p.W = (int)gth->W; p.ones_col = (int)gth->ones_col; }
+  else { p.ld_z = p.c0 = p.Cin = p.H = p.W = 0; p.ones_col = -1; }
+  p.save_a = gth_save_a;
   if (v.bps == 2) return backward ? launch_chain<MODE_BWD, 2>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 2>(tm, p, v.smem, st);
   return backward ? launch_chain<MODE_BWD, 1>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 1>(tm, p, v.smem, st);
 }
@@ -773,9 +853,28 @@ extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, i
   GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_forward: hidden must be %d", cnet::HID);
   GLOWK_CHECK_ARG(lda >= K1 && ldw1 >= K1 && ldw2 >= hidden && ldw3 >= hidden && ldp3 >= N3, "glowk_cnet_forward: leading dimensions too small");
   GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward: ldh too small");
-  return cnet::chain_launch(0, a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1, bias2, logs2, f2,
+  return cnet::chain_launch(0, nullptr, a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1, bias2, logs2, f2,
                             h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr, nullptr,
                             (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
+                                           int64_t W, int64_t ones_col, void* a1_save, int64_t lda, const void* w1,
+                                           int64_t ldw1, const void* w2, int64_t ldw2, const void* w3, int64_t ldw3,
+                                           int64_t K1, int64_t hidden, int64_t N3, const float* bias1, const float* logs1,
+                                           float f1, const float* bias2, const float* logs2, float f2, float* p3,
+                                           int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* stream) {
+  const int64_t M = N * H * W;
+  if (M == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(z && w1 && w2 && w3 && p3 && bias1 && logs1 && bias2 && logs2, "glowk_cnet_forward_implicit: null pointer");
+  GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_forward_implicit: hidden must be %d", cnet::HID);
+  GLOWK_CHECK_ARG(ld_z >= c0 + Cin && ldw1 >= K1 && ldw2 >= hidden && ldw3 >= hidden && ldp3 >= N3 && (!a1_save || lda >= K1),
+                  "glowk_cnet_forward_implicit: leading dimensions too small");
+  GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward_implicit: ldh too small");
+  cnet::Gather g{z, ld_z, c0, Cin, H, W, ones_col};
+  return cnet::chain_launch(0, &g, a1_save, a1_save ? lda : K1, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1,
+                            bias2, logs2, f2, h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr,
+                            nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
@@ -789,6 +888,6 @@ extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* 
   GLOWK_CHECK_ARG(ldd3 >= K3 && ldw3t >= K3 && ldw2t >= hidden && ldw1t >= hidden && ldh >= hidden && ldda1 >= K1p,
                   "glowk_cnet_backward: leading dimensions too small");
   // chain order: GEMM1 uses (w3t, logs2 / h2 mask), GEMM2 (w2t, logs1 / h1 mask), GEMM3 w1t
-  return cnet::chain_launch(1, d3col, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2, nullptr,
+  return cnet::chain_launch(1, nullptr, d3col, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2, nullptr,
                             logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
 }

@@ -232,6 +232,27 @@ def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2,
     return p3, h1, h2
 
 
+def cnet_forward_implicit(z, n, h, w, c0, cin, k1p, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2, ldp3=None,
+                          save=False, ldh=None, ones_col=-1):
+    """glowk_cnet_forward_implicit: conv1's im2col operand is gathered in-kernel from the rows z [n*h*w][ld] fp32.
+    Returns (p3, a1, h1, h2); a1 / h1 / h2 are None unless `save` (training)."""
+    check_cuda(z, w1, w2, w3)
+    assert z.dtype == torch.float32 and z.dim() == 2 and w1.dtype == torch.bfloat16
+    m = n * h * w
+    assert z.shape[0] == m
+    ldp3 = n3 if ldp3 is None else ldp3
+    ldh = hidden if ldh is None else ldh
+    dev = z.device
+    p3 = torch.empty(m, ldp3, device=dev, dtype=torch.float32)
+    a1 = torch.empty(m, k1p, device=dev, dtype=torch.bfloat16) if save else None
+    h1 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16) if save else None
+    h2 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16) if save else None
+    call("glowk_cnet_forward_implicit", ptr(z), z.shape[1], c0, cin, n, h, w, int(ones_col), ptr(a1), k1p, ptr(w1),
+         w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], k1p, hidden, n3, ptr(bias1), ptr(logs1), float(f1),
+         ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1), ptr(h2), ldh)
+    return p3, a1, h1, h2
+
+
 def cnet_backward(d3col, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h1, dbias2=None, dbias1=None):
     """The dgrad chain of the coupling net in one tcgen05 kernel (glowk_cnet_backward).
     Returns (d2, d1 [M][ldh] bf16, da1 [M][k1p] bf16)."""

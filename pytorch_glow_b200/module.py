@@ -334,6 +334,25 @@ class CouplingNet(nn.Sequential):
         a1 = K.im2col(z, 0, self.in_channels, 3, dt, self.k1p)
         return self.tap_rows_from_a1(a1, dt, save)
 
+    def tap_rows_from_rows(self, z, n, h, w, dt, save=None, ones_col=-1):
+        """P3 rows [P][n3p] fp32 from channels 0..Cin-1 of the pixel-major flow state z [P][C] fp32.  On the fused
+        bf16 path conv1 is an implicit GEMM: the kernel gathers its im2col operand itself (no glowk_im2col_rows, no
+        a1 in HBM when sampling).  `save`, if a dict, receives a1 / h1 / h2 for the backward pass."""
+        an1, an2 = self[0].actnorm, self[2].actnorm
+        if (dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False)
+                and self.in_channels % 2 == 0 and os.environ.get("GLOWK_CNET_IMPLICIT", "1") != "0"):
+            p3, a1, h1, h2 = K.cnet_forward_implicit(
+                z, n, h, w, 0, self.in_channels, self.k1p, self.packed("w1", dt), self.packed("w2", dt),
+                self.packed("w3", dt), self.hidden_channels, self.n3p, an1.bias.detach().reshape(-1),
+                an1.logs.detach().reshape(-1), an1.logscale_factor, an2.bias.detach().reshape(-1),
+                an2.logs.detach().reshape(-1), an2.logscale_factor, ldp3=self.n3p, save=save is not None,
+                ldh=round_up(self.hidden_channels, 64), ones_col=ones_col)
+            if save is not None:
+                save.update(a1=a1, h1=h1, h2=h2)
+            return p3
+        a1 = K.im2col_rows(z, n, h, w, 0, self.in_channels, 3, dt, self.k1p, ones_col=ones_col)
+        return self.tap_rows_from_a1(a1, dt, save)
+
     def tap_rows_from_a1(self, a1, dt, save=None):
         """The three GEMMs of the coupling net on a1 = im2col(z1) ([P][k1p]); returns P3 rows [P][n3p] fp32.
 

@@ -344,9 +344,8 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save):
         z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
     net = step.f
     dt = net.dtype(step.conv_dtype)
-    a1 = K.im2col_rows(z, n, h, w, 0, net.in_channels, 3, dt, net.k1p, ones_col=_ones_col(net, dt) if save else -1)
     sv = {} if save else None
-    p3 = net.tap_rows_from_a1(a1, dt, sv)
+    p3 = net.tap_rows_from_rows(z, n, h, w, dt, sv, ones_col=_ones_col(net, dt) if save else -1)
     c3 = net[4]
     affine = step.coupling == 'affine'
     ld_out, hrows = K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), z, n, h, w, affine, False,
@@ -364,8 +363,7 @@ def _step_reverse(step, x, n, c, h, w, ws):
     an = step.actnorm
     net = step.f
     dt = net.dtype(step.conv_dtype)
-    a1 = K.im2col_rows(x, n, h, w, 0, net.in_channels, 3, dt, net.k1p)
-    p3 = net.tap_rows_from_a1(a1, dt)
+    p3 = net.tap_rows_from_rows(x, n, h, w, dt)
     c3 = net[4]
     K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
                     c3.logscale_factor)

@@ -103,3 +103,34 @@ def test_cnet_backward_matches_three_gemms(m, k3, k1p):
         exact = stored.float().sum(0)
         assert torch.allclose(got, exact, rtol=1e-4, atol=1e-3 * max(1.0, exact.abs().max().item()))
         assert torch.allclose(got, ref, rtol=2e-2, atol=2e-2 * max(1.0, ref.abs().max().item()))
+
+
+# (N, H, W, C): level 1 / 2 shapes of the 64x64 and 32x32 models, a ragged pixel count, with and without the ones column
+IMPL_SHAPES = [(2, 32, 32, 12, -1), (3, 16, 16, 24, -1), (1, 10, 6, 12, -1), (2, 32, 32, 12, 54), (5, 16, 16, 12, 54)]
+
+
+@pytest.mark.parametrize("n,h,w,c,ones", IMPL_SHAPES)
+@pytest.mark.parametrize("save", [False, True])
+def test_cnet_forward_implicit_matches_explicit_im2col(n, h, w, c, ones, save):
+    """conv1 as an implicit GEMM (in-kernel 3x3 gather, network/module.py:252) == glowk_im2col_rows + the explicit path."""
+    if not _C.has_tcgen05():
+        pytest.skip("needs sm_100")
+    cin = c // 2
+    k1p = K.round_up(9 * cin, 64)
+    n3 = K.round_up(9 * c, 16)
+    if not K.cnet_fused_supported(False, k1p, HID, n3):
+        pytest.skip("shape not served by the fused kernel")
+    g = torch.Generator().manual_seed(n * 1000 + h)
+    z = torch.randn(n * h * w, c, generator=g).cuda()
+    _, w1, w2, w3, b1, l1, b2, l2 = _mk(8, k1p, n3, 3)
+    w1[:, 9 * cin:] = 0
+    a1r = K.im2col_rows(z, n, h, w, 0, cin, 3, _C.BF16, k1p, ones_col=ones)
+    p3r, h1r, h2r = K.cnet_forward(a1r, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0, save=True)
+    p3, a1, h1, h2 = K.cnet_forward_implicit(z, n, h, w, 0, cin, k1p, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0,
+                                             save=save, ones_col=ones)
+    torch.cuda.synchronize()
+    assert torch.equal(p3, p3r), (p3 - p3r).abs().max().item()
+    if save:
+        assert torch.equal(a1, a1r) and torch.equal(h1, h1r) and torch.equal(h2, h2r)
+    else:
+        assert a1 is None and h1 is None and h2 is None
