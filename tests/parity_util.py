@@ -88,3 +88,28 @@ def tiny_glow_parity(device="cuda:0", conv_dtype="fp32"):
         xs = glow.flow.decode(top, eps_list=eps)
     torch.cuda.synchronize()
     return (rel(zz, z[tag + "z"]), rel(nll, z[tag + "nll"]), rel(xs, z[tag + "sample/x"]))
+
+
+def bf16_steps_parity(device="cuda:0"):
+    """The tensor-core path the benchmark runs, on two small FlowSteps with the full 512-wide hidden layer: level-1
+    shape (C=12: fused coupling-net kernel with in-kernel conv1 gather, csrc/cnet_fused_sm100.cu) and level-3 shape
+    (C=48: three tcgen05 GEMMs, csrc/gemm_sm100.cu), forward and reverse, against the fp32 oracle.
+    Returns the worst (rel err z, rel err logdet, rel err of reverse(forward(x)))."""
+    worst = [0.0, 0.0, 0.0]
+    for c, hw, seed in ((12, 16, 4), (48, 8, 5)):
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        fs = G.FlowStep(c, 512, permutation="invconv", coupling="affine")
+        sd = randomize_({k: v.clone() for k, v in fs.state_dict().items()}, seed + 1)
+        adopt(fs, sd)
+        fs.conv_dtype = "bf16"
+        fs = fs.to(device).eval()
+        x = torch.randn(4, c, hw, hw, generator=torch.Generator().manual_seed(seed + 2))
+        z_ref, ld_ref = O.flowstep(x, torch.zeros(4), sd, "", "invconv", "affine")
+        with torch.no_grad():
+            z, ld = fs(x.to(device), torch.zeros(4, device=device))
+            xr, _ = fs(z.clone(), ld, reverse=True)
+        torch.cuda.synchronize()
+        for i, e in enumerate((rel(z, z_ref), rel(ld, ld_ref), rel(xr, x))):
+            worst[i] = max(worst[i], e)
+    return tuple(worst)
