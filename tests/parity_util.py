@@ -91,25 +91,26 @@ def tiny_glow_parity(device="cuda:0", conv_dtype="fp32"):
 
 
 def bf16_steps_parity(device="cuda:0"):
-    """The tensor-core path the benchmark runs, on two small FlowSteps with the full 512-wide hidden layer: level-1
-    shape (C=12: fused coupling-net kernel with in-kernel conv1 gather, csrc/cnet_fused_sm100.cu) and level-3 shape
-    (C=48: three tcgen05 GEMMs, csrc/gemm_sm100.cu), forward and reverse, against the fp32 oracle.
-    Returns the worst (rel err z, rel err logdet, rel err of reverse(forward(x)))."""
-    worst = [0.0, 0.0, 0.0]
-    for c, hw, seed in ((12, 16, 4), (48, 8, 5)):
-        np.random.seed(seed)
-        torch.manual_seed(seed)
-        fs = G.FlowStep(c, 512, permutation="invconv", coupling="affine")
-        sd = randomize_({k: v.clone() for k, v in fs.state_dict().items()}, seed + 1)
-        adopt(fs, sd)
-        fs.conv_dtype = "bf16"
-        fs = fs.to(device).eval()
-        x = torch.randn(4, c, hw, hw, generator=torch.Generator().manual_seed(seed + 2))
-        z_ref, ld_ref = O.flowstep(x, torch.zeros(4), sd, "", "invconv", "affine")
-        with torch.no_grad():
-            z, ld = fs(x.to(device), torch.zeros(4, device=device))
-            xr, _ = fs(z.clone(), ld, reverse=True)
-        torch.cuda.synchronize()
-        for i, e in enumerate((rel(z, z_ref), rel(ld, ld_ref), rel(xr, x))):
-            worst[i] = max(worst[i], e)
-    return tuple(worst)
+    """The tensor-core path the benchmark runs, on a small FlowModel (32x32x3, K=1, L=3) with the full 512-wide hidden
+    layer: level 1 (C=12) and level 2 (C=24) run the fused coupling-net kernel with the in-kernel conv1 gather
+    (csrc/cnet_fused_sm100.cu; level 2 in its deferred-GEMM3 layout), level 3 (C=48) three tcgen05 GEMMs
+    (csrc/gemm_sm100.cu).  Forward and reverse against the fp32 oracle.
+    Returns (rel err z, rel err logdet, rel err of the decoded x)."""
+    np.random.seed(4)
+    torch.manual_seed(4)
+    fm = G.FlowModel((32, 32, 3), 512, K=1, L=3, permutation="invconv", coupling="affine")
+    sd = randomize_({k: v.clone() for k, v in fm.state_dict().items()}, 5, coupling_std=0.01)
+    adopt(fm, sd)
+    fm.set_conv_dtype("bf16")
+    fm = fm.to(device).eval()
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(4, 3, 32, 32, generator=g)
+    z_ref, ld_ref = O.flow_encode(x, torch.zeros(4), sd, (32, 32, 3), 1, 3, "invconv", "affine", prefix="")
+    top = torch.randn(4, 48, 4, 4, generator=g) * 0.7
+    eps = [torch.randn(4, 12, 8, 8, generator=g) * 0.7, torch.randn(4, 6, 16, 16, generator=g) * 0.7]
+    x_ref = O.flow_decode(top.clone(), sd, (32, 32, 3), 1, 3, "invconv", "affine", eps_list=[e.clone() for e in eps], prefix="")
+    with torch.no_grad():
+        z, ld = fm(x.to(device), torch.zeros(4, device=device))
+        xs = fm.decode(top.to(device), eps_list=[e.to(device) for e in eps])
+    torch.cuda.synchronize()
+    return (rel(z, z_ref), rel(ld, ld_ref), rel(xs, x_ref))
