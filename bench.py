@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="celeba64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (0 = workload default)")
     ap.add_argument("--sample-batch", type=int, default=256, help="per-GPU sampling batch (BASELINE config 4)")
@@ -50,6 +50,12 @@ def parse():
     ap.add_argument("--no-sample", action="store_true")
     ap.add_argument("--conv-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the torch-eager reference on the same GPU")
+    ap.add_argument("--ref-gpu-batch", type=int, default=64, help="batch of the torch-eager reference on the GPU "
+                    "(its fp32 activations are ~0.35 GB/img: 512 does not fit)")
+    ap.add_argument("--sweep", default=None, help="comma-separated per-GPU batches for the batch sweep "
+                    "(default at N=1: 25,64,128,256; 'none' to skip)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (ncu --profile-from-start off ...)")
     ap.add_argument("--profile-step", action="store_true",
@@ -105,7 +111,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU baseline (oracle)
-def cpu_train_baseline(workload, batch, steps, warmup, state_dict=None):
+def cpu_train_baseline(workload, batch, steps, warmup, state_dict=None, device="cpu"):
     """The reference's arithmetic (CPU oracle port, torch fp32 on the host cores): full train iterations
     on a bounded batch.  Returns (img/s, cores, seconds per step)."""
     from oracle import glow_oracle as O
@@ -117,16 +123,18 @@ def cpu_train_baseline(workload, batch, steps, warmup, state_dict=None):
         from pytorch_glow_b200.hps import make_hps
         np.random.seed(2384); torch.manual_seed(2384)
         state_dict = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=batch)).state_dict()
-    p = {k: v.detach().float().cpu().clone().requires_grad_(k != "h_top") for k, v in state_dict.items()}
+    p = {k: v.detach().float().to(device).clone().requires_grad_(k != "h_top") for k, v in state_dict.items()}
     names = [k for k in p if k != "h_top"]
     ms = {k: torch.zeros_like(p[k]) for k in names}
     vs = {k: torch.zeros_like(p[k]) for k in names}
     g = torch.Generator().manual_seed(1234)
-    x = torch.rand(batch, shape[2], shape[0], shape[1], generator=g)
+    x = torch.rand(batch, shape[2], shape[0], shape[1], generator=g).to(device)
     times = []
     for t in range(warmup + steps):
+        if device != "cpu":
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        noise = torch.rand(x.shape, generator=g) / 256
+        noise = (torch.rand(x.shape, generator=g) / 256).to(device)
         for k in names:
             p[k].grad = None
         _, nll = O.glow_nll(x, noise, p, shape, K, L, "invconv", coupling)
@@ -136,25 +144,99 @@ def cpu_train_baseline(workload, batch, steps, warmup, state_dict=None):
         with torch.no_grad():
             for k in names:
                 O.adam_step_(p[k], p[k].grad, ms[k], vs[k], t + 1, O.noam_lr(1e-3, t, 4000, 1e-4))
+        if device != "cpu":
+            torch.cuda.synchronize()
         if t >= warmup:
             times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
     return batch / sec, cores, sec
 
 
+def _ref_hps(workload, batch, device):
+    from pytorch_glow_b200.hps import make_hps
+    shape, K, L, hidden, coupling, _, _ = WORKLOADS[workload]
+    return make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=batch, devices=(device,)), shape
+
+
+def reference_cpu(workload, batch, steps, warmup, state_dict=None):
+    """Train iterations of the reference on the host cores: the REAL reference when it is staged under
+    baseline/_ref (kind "reference"), else the oracle port (kind "port").  -> (img/s, cores, s/step, kind)."""
+    from baseline import ref_harness as R
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    if R.available():
+        hps, shape = _ref_hps(workload, batch, "cpu")
+        ips, sec, _ = R.time_train(hps, "cpu", batch, shape, steps, warmup)
+        return ips, cores, sec, "reference"
+    ips, cores, sec = cpu_train_baseline(workload, batch, steps, warmup, state_dict)
+    return ips, cores, sec, "port"
+
+
+def reference_gpu(workload, batch, steps, warmup, device="cuda:0"):
+    """The reference's modules in torch eager (cuDNN / cuBLAS) on the same GPU -- the GPU bar SURVEY section 2 names --
+    with TF32 off (the reference's default numerics) and on.  Falls back to the oracle port on the device."""
+    from baseline import ref_harness as R
+    out = {"per_gpu_batch": batch, "steps": steps, "warmup": warmup}
+    if R.available():
+        out["kind"] = "reference (baseline/_ref, torch eager, F3 patch)"
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            hps, shape = _ref_hps(workload, batch, device)
+            ips, sec, loss = R.time_train(hps, device, batch, shape, steps, warmup, tf32=tf32)
+            e2e, _, _ = R.time_train(hps, device, batch, shape, steps, 1, tf32=tf32, pinned_e2e=True) if tag == "tf32" else (None, None, None)
+            out[tag] = {"train_img_s": ips, "ms_per_step": sec * 1e3, "loss_bits_per_dim": loss}
+            if e2e:
+                out[tag]["train_e2e_img_s"] = e2e
+            torch.cuda.empty_cache()
+        sb = min(256, 4 * batch)
+        hps, _ = _ref_hps(workload, sb, device)
+        sips, ssec = R.time_sample(hps, device, sb, max(2, steps), 1, tf32=True)
+        out["tf32"]["sample_img_s"] = sips
+        out["sample_batch"] = sb
+        torch.cuda.empty_cache()
+    else:
+        out["kind"] = "port (oracle/glow_oracle.py on the device)"
+        for tag, tf32 in (("fp32", False), ("tf32", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            ips, _, sec = cpu_train_baseline(workload, batch, steps, warmup, None, device=device)
+            out[tag] = {"train_img_s": ips, "ms_per_step": sec * 1e3}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.impl == "reference-gpu":
+        steps, warmup = max(2, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        torch.cuda.set_device(0)
+        r = reference_gpu(args.workload, args.ref_gpu_batch, steps, warmup)
+        best = r["tf32"]["train_img_s"]
+        line = {
+            "impl": "reference-gpu", "metric": "train_images_per_sec", "value": best, "unit": "img/s", "n_gpus": 1,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["tf32"]["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "per_gpu_batch": args.ref_gpu_batch,
+                       "device": "cuda:0, torch eager (cuDNN)"},
+            "gpu_eager_baseline": r,
+            "e2e": {"value": r["tf32"].get("train_e2e_img_s", best), "unit": "img/s",
+                    "h2d_bytes_per_step": args.ref_gpu_batch * 3 * 64 * 64 * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line), flush=True)
+        return
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))   # bounded: ~4 s per CPU step
-    ips, cores, sec = cpu_train_baseline(args.workload, args.cpu_batch, steps, warmup)
-    sample = "%d train iterations (+%d warm-up) of the oracle port on a batch of %d" % (steps, warmup, args.cpu_batch)
+    ips, cores, sec, kind = reference_cpu(args.workload, args.cpu_batch, steps, warmup)
+    sample = "%d train iterations (+%d warm-up) of %s on a batch of %d" % (
+        steps, warmup, "the reference (baseline/_ref, F3 patch)" if kind == "reference" else "the oracle port", args.cpu_batch)
     line = {
         "impl": "reference", "metric": "train_images_per_sec", "value": ips, "unit": "img/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "per_gpu_batch": args.cpu_batch, "device": "host CPU"},
-        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": ips, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": ips, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -237,36 +319,69 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
         return e0.elapsed_time(e1) / reps * 1e3
 
     gemm_flops = 2.0 * M * hidden * hidden
-    cases = [
-        ("dgrad2", "gemm_tc_kernel<RELU_BWD,bf16>: dgrad of conv2 + ReLU/ActNorm backward epilogue (M=%d N=K=%d)" % (M, hidden),
-         # as launched by the training step: no column sums in the epilogue (dbias = ones column of conv1's wgrad,
-         # dlogs from W, dW, dbias in the batched glowk_conv_actnorm_finish_batched pass, rows_path.GradPlan.finish)
+    # fused coupling-net kernels (csrc/cnet_fused_sm100.cu) at level 1: conv1 K = 9*C/2 -> k1p, conv3 N = 9*C -> n3p
+    cin = C // 2
+    k1p = (9 * cin + 63) // 64 * 64
+    k3p = (9 * C + 63) // 64 * 64
+    w1 = (rnd(hidden, k1p) * 0.05).to(bf); w1[:, 9 * cin:] = 0
+    w3 = (rnd(n3p, hidden) * 0.05).to(bf)
+    w3t = (rnd(hidden, k3p) * 0.05).to(bf); w2t = (rnd(hidden, hidden) * 0.05).to(bf); w1t = (rnd(k1p, hidden) * 0.05).to(bf)
+    d3 = [(rnd(M, k3p) * 0.5).to(bf) for _ in range(2)]
+    fwd_flops = 2.0 * M * (9 * cin * hidden + hidden * hidden + hidden * 9 * C)
+    bwd_flops = 2.0 * M * (k3p * hidden + hidden * hidden + hidden * k1p)
+    fused = KF.cnet_fused_supported(False, k1p, hidden, n3p) and KF.cnet_fused_supported(True, k3p, hidden, k1p)
+    # (id, description, launch, algorithmic bytes, algorithmic flops or None)
+    cases = []
+    if fused:
+        cases += [
+            ("cnet_bwd", "cnet_chain_kernel<BWD>: dgrad3 -> ReLU'/ActNorm -> dgrad2 -> ReLU'/ActNorm -> dgrad1 fused (M=%d, "
+             "K3=%d, hidden=%d, K1p=%d); reads dP3 + the two saved activations (masks), writes d2, d1, dA1" % (M, k3p, hidden, k1p),
+             lambda i: KF.cnet_backward(d3[i % 2], w3t, w2t, w1t, hidden, k1p, logs, 3.0, logs, 3.0, hs[i], hs[(i + 1) % R], dbias2=dbias),
+             2.0 * M * (k3p + 4 * hidden + k1p), bwd_flops),
+            ("cnet_fwd_train", "cnet_chain_kernel<FWD>, training: implicit conv1 -> conv2 -> conv3 fused, a1 / h1 / h2 stored "
+             "once for the backward pass (M=%d)" % M,
+             lambda i: KF.cnet_forward_implicit(zs[i], B, H, W, 0, cin, k1p, w1, w2, w3, hidden, n3p, bias, logs, 3.0, bias, logs,
+                                                3.0, save=True, ones_col=9 * cin),
+             M * (4.0 * cin + 4.0 * n3p + 2.0 * k1p + 4.0 * hidden), fwd_flops),
+            ("cnet_fwd_sample", "cnet_chain_kernel<FWD>, sampling: implicit conv1 -> conv2 -> conv3 fused, hidden activations "
+             "never leave the SM (M=%d)" % M,
+             lambda i: KF.cnet_forward_implicit(zs[i], B, H, W, 0, cin, k1p, w1, w2, w3, hidden, n3p, bias, logs, 3.0, bias, logs, 3.0),
+             M * (4.0 * cin + 4.0 * n3p), fwd_flops),
+        ]
+    cases += [
+        ("dgrad2", "gemm_tc_kernel<RELU_BWD,bf16>: dgrad of conv2 + ReLU/ActNorm backward epilogue (M=%d N=K=%d); levels the "
+         "fused kernel does not serve (conv3 N > 256)" % (M, hidden),
          lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_RELU_BWD, None, logs, 3.0, y=hs[(i + 1) % R], dlogs=None,
                            dbias=None, out_dtype=_C.BF16, out=outs[i]),
-         "hbm", 3.0 * M * hidden * 2, gemm_flops),
+         3.0 * M * hidden * 2, gemm_flops),
         ("wgrad2", "wgrad_tc_kernel: dW2 += d2^T h1 (P=%d, 512x512)" % M,
          lambda i: KF.gemm_wgrad(hs[i], hs[(i + 1) % R], hidden, hidden, dw),
-         "hbm", 2.0 * M * hidden * 2, gemm_flops),
+         2.0 * M * hidden * 2, gemm_flops),
         ("conv2", "gemm_tc_kernel<ACTNORM_RELU,bf16>: conv2 1x1 + ActNorm + ReLU (M=%d N=K=%d)" % (M, hidden),
          lambda i: KF.gemm(hs[i], w2, hidden, hidden, _C.EPI_ACTNORM_RELU, bias, logs, 3.0, out_dtype=_C.BF16, out=outs[i]),
-         "tensor", 2.0 * M * hidden * 2, gemm_flops),
+         2.0 * M * hidden * 2, gemm_flops),
         ("coupling", "rows_coupling_kernel: tap gather-sum + affine coupling + logdet (M=%d C=%d)" % (M, C),
          lambda i: KF.rows_coupling(p3[i], b3, l3, zs[i], B, H, W, True, False, 3.0, save_h=True, ld_in=ld_in,
                                     want_ld=True, an_logs=mb, logabsdet=ld_in[:1], partials=parts, tickets=tickets),
-         "hbm", 4.0 * M * (9 * C + C // 2 * 2 + C), None),
+         4.0 * M * (9 * C + C // 2 * 2 + C), None),
         ("actnorm_mix", "rows_mix_kernel: ActNorm + invertible 1x1 conv (M=%d C=%d)" % (M, C),
          lambda i: KF.rows_actnorm_mix(zs[i], wmix, None, mb, mb, 3.0, False),
-         "hbm", 8.0 * M * C, None),
+         8.0 * M * C, None),
     ]
     out = []
-    for kid, name, fn, bound, nbytes, flops in cases:
+    for kid, name, fn, nbytes, flops in cases:
         us = t_us(fn)
-        if bound == "hbm":
-            ach, peak, unit = nbytes / us / 1e3, hbm, "GB/s"
-        else:
-            ach, peak, unit = flops / us / 1e6, tfl, "TFLOP/s"
+        hbm_ach = nbytes / us / 1e3                      # GB/s
+        ten_ach = flops / us / 1e6 if flops else None    # TFLOP/s
+        hbm_frac = hbm_ach / hbm
+        ten_frac = ten_ach / tfl if flops else None
+        # the roofline that bounds the launch = the one whose floor (bytes / peak or flops / peak) is the longer time
+        bound = "tensor" if (flops and flops / tfl / 1e6 > nbytes / hbm / 1e3) else "hbm"
+        ach, peak, unit, frac = (ten_ach, tfl, "TFLOP/s", ten_frac) if bound == "tensor" else (hbm_ach, hbm, "GB/s", hbm_frac)
         out.append({"id": kid, "kernel": name, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                    "frac": ach / peak, "traffic": None, "us_per_launch": us, "algorithmic_bytes": nbytes,
+                    "frac": frac, "traffic": None, "us_per_launch": us, "algorithmic_bytes": nbytes,
+                    "algorithmic_flops": flops, "hbm_frac": hbm_frac, "hbm_gbs": hbm_ach, "tensor_frac": ten_frac,
+                    "tensor_tflops": ten_ach,
                     "peak_source": src + (" hbm_gbs (copy bandwidth)" if bound == "hbm" else " bf16_tflops (burst; kernel timed alone)")})
     return out
 
@@ -294,6 +409,10 @@ def run_b200(args):
 
     shape, K, L, hidden, coupling, default_b, gflop = WORKLOADS[args.workload]
     B = args.batch or default_b
+    if args.strong:
+        if B % world:
+            raise SystemExit("--strong: global batch %d is not divisible by %d ranks" % (B, world))
+        B //= world
     seed = 2384                                         # profile/celeba.json:66
     np.random.seed(seed); torch.manual_seed(seed)       # identical initial replicas on every rank
     glow = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=B)).to(device)
@@ -386,16 +505,27 @@ def run_b200(args):
         for _ in range(2):
             sample_fn(0)
         ssec, _, _ = timed(sample_fn, nrep, dist_on, device)
+        # end to end: every pass ends with the device->host copy of its images into pinned memory (what
+        # infer.py / Inferer.sample hand to make_grid, network/inferer.py:53-60)
+        host_img = torch.empty(SB, shape[2], shape[0], shape[1]).pin_memory()
+
+        def sample_e2e(i):
+            host_img.copy_(sampler_g(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        s2sec, _, _ = timed(sample_e2e, nrep, dist_on, device)
         sample = {"value": SB * world * nrep / ssec, "unit": "img/s", "per_gpu_batch": SB,
                   "eps_std": 0.7, "collective": "none", "cuda_graph": True,
-                  "eager_value": SB * world * nrep / esec}
+                  "eager_value": SB * world * nrep / esec,
+                  "e2e": {"value": SB * world * nrep / s2sec, "unit": "img/s", "h2d_bytes_per_step": 0,
+                          "d2h_bytes_per_step": host_img.numel() * 4 * world}}
         del sampler_g
         del glow_s
 
     # ---- rooflines of the kernels that dominate the step (level 1: C=12, 32x32, M = B*1024 pixels), each timed
     # alone with CUDA events on the launch stream over rotating buffers larger than L2.  "roofline" is the kernel
-    # with the largest share of the step in profiles/ (the conv2 dgrad with the fused ReLU/ActNorm-backward
-    # epilogue); "roofline_all" lists the others.  Algorithmic bytes / flops per launch: DESIGN.md section 4.
+    # with the largest share of the step in profiles/ (the fused backward chain of the coupling network);
+    # "roofline_all" lists the others, each with BOTH its HBM and its tensor fraction.  Algorithmic bytes / flops
+    # per launch: DESIGN.md section 4.
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -418,16 +548,49 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sd_cpu = {k: v.detach().cpu() for k, v in glow.state_dict().items()}
-        ips, cores, sec_cpu = cpu_train_baseline(args.workload, args.cpu_batch, 2, 1, sd_cpu)
-        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": "port",
-               "sample": "2 train iterations (+1 warm-up) of oracle/glow_oracle.py on a batch of %d (%.1f s/iteration)" % (args.cpu_batch, sec_cpu)}
+        ips, cores, sec_cpu, kind = reference_cpu(args.workload, args.cpu_batch, 2, 1, sd_cpu)
+        what = "the reference (baseline/_ref, F3 patch)" if kind == "reference" else "oracle/glow_oracle.py"
+        cpu = {"value": ips, "unit": "img/s", "cores": cores, "kind": kind,
+               "sample": "2 train iterations (+1 warm-up) of %s on a batch of %d (%.1f s/iteration)" % (what, args.cpu_batch, sec_cpu)}
+
+    # ---- batch sweep (same model, other per-GPU batches; 25 = profile/celeba.json:27 num_batch_train 50 over its
+    # two devices) and the torch-eager reference on this GPU.  The headline trainer is released first.
+    sweep = None
+    pts = args.sweep if args.sweep is not None else ("25,64,128,256" if (world == 1 and args.workload == "celeba64") else "none")
+    if pts != "none":
+        del ts
+        glow = None
+        torch.cuda.empty_cache()
+        sweep = [{"per_gpu_batch": B, "value": value, "ms_per_step": sec / args.steps * 1e3}]
+        for b in [int(v) for v in pts.split(",") if int(v) != B]:
+            np.random.seed(seed); torch.manual_seed(seed)
+            g2 = G.Glow(make_hps(shape, K=K, L=L, hidden_channels=hidden, coupling=coupling, batch=b)).to(device)
+            t2 = FusedTrainStep(g2, use_graphs=not args.no_graphs, world_size=world)
+            xb = [torch.rand(b, shape[2], shape[0], shape[1], generator=gen).to(device) for _ in range(2)]
+            t2.init_actnorm(xb[0])
+            for i in range(3):
+                t2.step(xb[i % 2])
+            n2 = max(5, args.steps)
+            sec2, _, _ = timed(lambda i: t2.step(xb[i % 2]), n2, dist_on, device)
+            sweep.append({"per_gpu_batch": b, "value": b * world * n2 / sec2, "ms_per_step": sec2 / n2 * 1e3})
+            del t2, g2, xb
+            torch.cuda.empty_cache()
+        sweep.sort(key=lambda r: r["per_gpu_batch"])
+    gpu_eager = None
+    if rank == 0 and world == 1 and not args.no_gpu_baseline and args.workload in ("celeba64", "cifar32", "tiny"):
+        try:
+            ts = None
+            torch.cuda.empty_cache()
+            gpu_eager = reference_gpu(args.workload, args.ref_gpu_batch, 3, 2, device="cuda:%d" % local_rank)
+        except Exception as e:                        # a baseline must never take the headline down
+            gpu_eager = {"error": repr(e)[:300]}
 
     if rank == 0:
         act_gb = None
         line = {
             "metric": "train_images_per_sec", "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": args.conv_dtype, "data": "synthetic",
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": args.conv_dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "global_batch": B * world, "per_gpu_batch": B,
                        "parallelism": "dp%d" % world, "cuda_graphs": not args.no_graphs,
                        "l2": "per-step working set (saved activations ~%.1f GB/GPU) >> 126 MB L2; 4 rotating input batches" % (B * 0.1),
@@ -437,7 +600,12 @@ def run_b200(args):
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": sec_e2e / args.steps * 1e3},
             "gpu_launches": gpu_launches, "clocks": clocks, "loss_bits_per_dim": last_loss,
             "roofline": roof, "roofline_all": roof_all, "cpu_baseline": cpu, "sample": sample,
+            "batch_sweep": sweep, "gpu_eager_baseline": gpu_eager,
         }
+        if gpu_eager and "tf32" in gpu_eager:
+            line["vs_gpu_eager_tf32"] = value / gpu_eager["tf32"]["train_img_s"]
+            if sample and gpu_eager["tf32"].get("sample_img_s"):
+                line["sample_vs_gpu_eager_tf32"] = sample["value"] / gpu_eager["tf32"]["sample_img_s"]
         if gflop:
             tf = value * gflop * 3 / 1e3          # fwd + dgrad + wgrad
             line["tensor_tflops_train"] = tf
@@ -449,7 +617,7 @@ def run_b200(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.impl in ("reference", "reference-gpu"):
         run_reference(a)
     else:
         run_b200(a)
