@@ -211,6 +211,15 @@ class GradPlan:
 
     def __init__(self, flow, device):
         steps, splits = _steps_and_splits(flow)
+        # level of every layer = number of Squeeze2d layers up to it, minus one (levels finish their backward pass
+        # top-down: `finish_level` lets the gradients of a finished level leave for the all-reduce while the lower
+        # levels are still being differentiated, train.FusedTrainStep)
+        self.level_of, lvl = {}, -1
+        for layer in flow.layers:
+            if isinstance(layer, module.Squeeze2d):
+                lvl += 1
+            self.level_of[id(layer)] = max(lvl, 0)
+        self.n_levels = max(lvl, 0) + 1
         items = []            # (owner, tag, param, layout, rows, ld)
         for st in steps:
             net = st.f
@@ -227,7 +236,6 @@ class GradPlan:
         numel = sum(it[4] * it[5] for it in items)
         ndb = sum(2 * round_up(st.f.hidden_channels, 64) for st in steps)
         self.arena = torch.zeros(numel + ndb, device=device, dtype=torch.float32)
-        jobs = np.zeros(len(items), dtype=_JOB)
         self.views = {}
         off = numel
         for st in steps:
@@ -235,47 +243,70 @@ class GradPlan:
             self.views[(id(st), "db1")] = self.arena[off:off + kh]
             self.views[(id(st), "db2")] = self.arena[off + kh:off + 2 * kh]
             off += 2 * kh
-        self._fin, self._fin_sig, self._fin_dev = [], None, None
-        off = blk = 0
-        for i, (owner, tag, prm, layout, rows, ld) in enumerate(items):
+        self._fin = [[] for _ in range(self.n_levels)]
+        self._fin_sig = [None] * self.n_levels
+        self._fin_dev = [None] * self.n_levels
+        self._done = [False] * self.n_levels
+        per_level = [[] for _ in range(self.n_levels)]
+        off = 0
+        for owner, tag, prm, layout, rows, ld in items:
             self.views[(id(owner), tag)] = self.arena[off:off + rows * ld].view(rows, ld)
-            jobs[i] = (_gbuf(prm).data_ptr(), self.arena.data_ptr() + off * 4, prm.shape[0], prm.shape[1],
-                       prm.shape[2], layout, rows, ld, blk)
+            per_level[self.level_of[id(owner)]].append((_gbuf(prm).data_ptr(), self.arena.data_ptr() + off * 4, prm.shape[0],
+                                                        prm.shape[1], prm.shape[2], layout, rows, ld, prm.numel()))
             off += rows * ld
-            blk += (prm.numel() + 255) // 256
-        self.jobs_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(device)
-        self.njobs, self.blocks = len(items), blk
+        self.level_jobs = []                 # per level: (device job array, njobs, blocks) of the unpack kernel
+        for lv in range(self.n_levels):
+            jobs = np.zeros(len(per_level[lv]), dtype=_JOB)
+            blk = 0
+            for i, (g, a, o, ii, ks, layout, rows, ld, numel_p) in enumerate(per_level[lv]):
+                jobs[i] = (g, a, o, ii, ks, layout, rows, ld, blk)
+                blk += (numel_p + 255) // 256
+            dev_jobs = torch.from_numpy(jobs.view(np.uint8).copy()).to(device) if len(jobs) else None
+            self.level_jobs.append((dev_jobs, len(jobs), blk))
 
     def valid(self):
         return self.sig == tuple(_gbuf(it[2]).data_ptr() for it in self.items)
 
     def begin(self):
         self.arena.zero_()
-        self._fin = []
+        self._fin = [[] for _ in range(self.n_levels)]
+        self._done = [False] * self.n_levels
 
     def view(self, owner, tag):
         return self.views[(id(owner), tag)]
 
-    def defer_dlogs(self, w_packed, dw, actnorm, db, n, k, ones_col=-1):
-        """Register one conv + ActNorm layer for the batched dbias / dlogs finish (bf16 path).  ones_col >= 0:
-        this pass's bias gradient is column `ones_col` of dw (the im2col operand carried a ones column)."""
+    def defer_dlogs(self, owner, w_packed, dw, actnorm, db, n, k, ones_col=-1):
+        """Register one conv + ActNorm layer of `owner` for the batched dbias / dlogs finish (bf16 path).
+        ones_col >= 0: this pass's bias gradient is column `ones_col` of dw (the im2col operand carried a ones column)."""
         if ones_col >= 0:
             db_ptr, stride = dw.data_ptr() + 4 * ones_col, dw.shape[1]
         else:
             db_ptr, stride = db.data_ptr(), 1
-        self._fin.append((w_packed.data_ptr(), dw.data_ptr(), actnorm.bias.data_ptr(), db_ptr,
-                          _gbuf(actnorm.bias).data_ptr(), _gbuf(actnorm.logs).data_ptr(), n, k, w_packed.shape[1],
-                          dw.shape[1], float(actnorm.logscale_factor), stride))
+        self._fin[self.level_of[id(owner)]].append(
+            (w_packed.data_ptr(), dw.data_ptr(), actnorm.bias.data_ptr(), db_ptr, _gbuf(actnorm.bias).data_ptr(),
+             _gbuf(actnorm.logs).data_ptr(), n, k, w_packed.shape[1], dw.shape[1], float(actnorm.logscale_factor), stride))
+
+    def finish_level(self, lv):
+        """Every layer of level `lv` has been differentiated: apply its deferred ActNorm gradients and scatter its
+        packed weight gradients into the .grad tensors (two launches).  After this the level's gradients are final."""
+        if self._done[lv]:
+            return
+        self._done[lv] = True
+        fin = self._fin[lv]
+        if fin:
+            sig = tuple(fin)
+            if sig != self._fin_sig[lv]:       # pointers are stable across steps: built once, before graph capture
+                jobs = np.array(fin, dtype=_FJOB)
+                self._fin_dev[lv] = torch.from_numpy(jobs.view(np.uint8).copy()).to(self.arena.device)
+                self._fin_sig[lv] = sig
+            K.conv_actnorm_finish_batched(self._fin_dev[lv], len(fin), max(j[6] for j in fin))
+        jobs_dev, njobs, blocks = self.level_jobs[lv]
+        if njobs:
+            K.unpack_weight_grads_batched(jobs_dev, njobs, blocks)
 
     def finish(self):
-        if self._fin:
-            sig = tuple(self._fin)
-            if sig != self._fin_sig:          # pointers are stable across steps: built once, before graph capture
-                jobs = np.array(self._fin, dtype=_FJOB)
-                self._fin_dev = torch.from_numpy(jobs.view(np.uint8).copy()).to(self.arena.device)
-                self._fin_sig = sig
-            K.conv_actnorm_finish_batched(self._fin_dev, len(self._fin), max(j[6] for j in self._fin))
-        K.unpack_weight_grads_batched(self.jobs_dev, self.njobs, self.blocks)
+        for lv in range(self.n_levels - 1, -1, -1):
+            self.finish_level(lv)
 
 
 def grad_plan(flow, device):
@@ -423,8 +454,8 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     # (4) conv1 (im2col form); its dgrad is gather-summed inside the mix adjoint below
     K.gemm_wgrad(d1, a1, hid, k1p, plan.view(step, "w1"))
     if defer:
-        plan.defer_dlogs(net.packed("w2", dt), dw2, an2, db2, hid, hid)
-        plan.defer_dlogs(net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
+        plan.defer_dlogs(step, net.packed("w2", dt), dw2, an2, db2, hid, hid)
+        plan.defer_dlogs(step, net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
     # bf16 path: the nine-tap partial gradients are stored in bf16 (they are products of bf16 operands already) and
     # summed in fp32 by the mix adjoint
     if not fused:
@@ -556,6 +587,7 @@ def backward(flow, tape, dz, dld):
     pitch = 2 * c if (tape and tape[-1][0] == "split") else c
     cur = torch.empty(n * h * w, pitch, device=dev, dtype=torch.float32)
     K.rows_squeeze(dz, NCHW, c * h * w, cur, ROWS, pitch, n, c, h, w, 1, False)
+    hook = flow.__dict__.get("_level_done_hook")      # train.FusedTrainStep: per-level gradient all-reduce
     for kind, layer, ctx in reversed(tape):
         if kind == "step":
             cur = _step_backward(layer, ctx, cur, dld, n, c, h, w, plan)
@@ -563,6 +595,11 @@ def backward(flow, tape, dz, dld):
             c = c * 2                       # `cur` is the [P][C] buffer the squeeze adjoint below left half-filled
             cur = _split_backward(layer, ctx, cur, dld, n, c, h, w, plan)
         else:
+            lv = plan.level_of.get(id(layer))
+            if lv is not None:              # the level that starts at this Squeeze2d is fully differentiated
+                plan.finish_level(lv)
+                if hook is not None:
+                    hook(lv, plan.n_levels)
             c0, h0, w0, layout, pitch = ctx
             if layout == NCHW:
                 dst = torch.empty(n, c0, h0, w0, device=dev, dtype=torch.float32)

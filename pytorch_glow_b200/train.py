@@ -11,6 +11,7 @@ gradient arena, so that
   * the whole step can be captured in CUDA graphs (launch-bound otherwise: ~2000 kernels/step).
 """
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -28,15 +29,58 @@ def noam_lr(base_lr, global_step, warmup_steps=4000, min_lr=None):
     return lr
 
 
-def allreduce_mean_(t, group=None):
+class _DivAfter:
+    """Work handle of a SUM all-reduce that still has to be divided by the world size (gloo has no AVG)."""
+
+    def __init__(self, work, t, n):
+        self.work, self.t, self.n = work, t, n
+
+    def wait(self):
+        self.work.wait()
+        self.t.div_(self.n)
+
+
+def allreduce_mean_(t, group=None, async_op=False):
     """In-place mean over the ranks of `group` (NCCL: one AVG all-reduce over NVLink; gloo has no AVG: SUM then
-    divide).  Gradients are averaged BEFORE clipping so that every rank clips identical tensors."""
+    divide).  Gradients are averaged BEFORE clipping so that every rank clips identical tensors.
+    async_op: returns a handle whose wait() orders the current stream after the collective."""
     if dist.get_backend(group) == "nccl":
-        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
-    else:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        t.div_(dist.get_world_size(group))
+        w = dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        return w if async_op else t
+    w = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:
+        return _DivAfter(w, t, dist.get_world_size(group))
+    t.div_(dist.get_world_size(group))
     return t
+
+
+def arena_level_ranges(glow, arena):
+    """[(lo, hi)] slices of the flat gradient arena per flow level (level = number of Squeeze2d layers up to the
+    layer, minus one), in level order.  named_parameters() walks flow.layers in order, so every level is one
+    contiguous slice; parameters outside `flow.layers` come after them."""
+    from .module import Squeeze2d
+    level_of_layer, lvl = {}, -1
+    for i, layer in enumerate(glow.flow.layers):
+        if isinstance(layer, Squeeze2d):
+            lvl += 1
+        level_of_layer[i] = max(lvl, 0)
+    n_levels = max(lvl, 0) + 1
+    ranges = [[None, None] for _ in range(n_levels)]
+    end_flow = 0
+    for name, p, off in zip(arena.names, arena.params, arena.offsets):
+        parts = name.split(".")
+        if len(parts) > 2 and parts[0] == "flow" and parts[1] == "layers":
+            lv = level_of_layer[int(parts[2])]
+            size = (p.numel() + 3) // 4 * 4
+            r = ranges[lv]
+            r[0] = off if r[0] is None else min(r[0], off)
+            r[1] = off + size if r[1] is None else max(r[1], off + size)
+            end_flow = max(end_flow, off + size)
+    out = [(r[0] or 0, r[1] or 0) if r[0] is not None else (0, 0) for r in ranges]
+    for (lo, hi), (lo2, hi2) in zip(out, out[1:]):
+        assert hi == lo2, "flow levels are not contiguous in the arena"
+    assert not out or out[0][0] == 0
+    return out
 
 
 def shard_batch(x, rank, world_size):
@@ -85,7 +129,7 @@ class FusedTrainStep:
     """
 
     def __init__(self, glow, lr=1e-3, betas=(0.9, 0.9999), eps=1e-8, max_grad_clip=5.0, max_grad_norm=100.0,
-                 warmup_steps=4000, min_lr=1e-4, use_graphs=False, process_group=None, world_size=1):
+                 warmup_steps=4000, min_lr=1e-4, use_graphs=False, process_group=None, world_size=1, overlap=None):
         self.glow = glow
         self.base_lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_clip, self.max_grad_norm = max_grad_clip, max_grad_norm
@@ -105,6 +149,17 @@ class FusedTrainStep:
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
         self.global_step = 0
         self._inited_ok = False
+        # Gradient all-reduce overlapped with the backward pass (the reference's DataParallel reduces
+        # after the whole backward, trainer.py:117-123,140): the flow differentiates its levels top-down, and as soon
+        # as a level is done its slice of the gradient arena leaves on NCCL's stream while the lower (larger-image,
+        # slower) levels are still running.  With CUDA graphs the collectives are captured into the iteration graph
+        # (one graph, no host round trip between backward, all-reduce and optimizer).  GLOWK_DDP_OVERLAP=0: one
+        # blocking all-reduce between two graphs (round-1 behaviour).
+        if overlap is None:
+            overlap = os.environ.get("GLOWK_DDP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap) and world_size > 1
+        self._pending = []
+        self.level_ranges = arena_level_ranges(glow, self.arena) if self.overlap else None
         self.use_graphs = use_graphs
         self._g_fb = self._g_opt = None
         self._static_x = None
@@ -177,12 +232,36 @@ class FusedTrainStep:
         self.global_step = int(step)
         self.step_dev.fill_(int(step))
 
+    def _level_done(self, level, n_levels):
+        """rows_path.backward finished a level: start the all-reduce of that level's gradient slice."""
+        lo, hi = self.level_ranges[level]
+        if hi > lo:
+            self._pending.append(allreduce_mean_(self.arena.grad[lo:hi], self.pg, async_op=True))
+
     def _forward_backward(self, x):
         self.arena.grad.zero_()
         self.arena.rebind_grads()
-        z, nll, _ = self.glow(x=x)
-        loss = self.glow.generative_loss(nll)
-        loss.backward()
+        if self.overlap:
+            self._pending = []
+            self.glow.flow.__dict__["_level_done_hook"] = self._level_done
+        try:
+            z, nll, _ = self.glow(x=x)
+            loss = self.glow.generative_loss(nll)
+            loss.backward()
+        finally:
+            self.glow.flow.__dict__.pop("_level_done_hook", None)
+        if self.overlap:
+            covered = sum(hi - lo for lo, hi in self.level_ranges)
+            if len(self._pending) != sum(1 for lo, hi in self.level_ranges if hi > lo):
+                # the flow did not run on the level-wise path (hybrid / NCHW fall-back): reduce everything now
+                for w in self._pending:
+                    w.wait()
+                self._pending = [allreduce_mean_(self.arena.grad, self.pg, async_op=True)]
+            elif covered < self.arena.numel:     # parameters outside the flow (learn_top, y_emb, classifier)
+                self._pending.append(allreduce_mean_(self.arena.grad[covered:], self.pg, async_op=True))
+            for w in self._pending:              # the current stream waits for NCCL's stream
+                w.wait()
+            self._pending = []
         return loss.detach()
 
     def _optimizer(self):
@@ -193,7 +272,7 @@ class FusedTrainStep:
                      0.0, self.betas[0], self.betas[1], self.eps, sched=self.sched_dev)
 
     def _allreduce(self):
-        if self.world_size > 1:
+        if self.world_size > 1 and not self.overlap:
             allreduce_mean_(self.arena.grad, self.pg)
 
     def step(self, x):
@@ -212,9 +291,10 @@ class FusedTrainStep:
             if self._g_fb is None:
                 self._capture(x)
             self._static_x.copy_(x, non_blocking=True)
-            self._g_fb.replay()
-            self._allreduce()
-            self._g_opt.replay()
+            self._g_fb.replay()                   # overlap: forward + backward + per-level all-reduces + optimizer
+            if self._g_opt is not None:
+                self._allreduce()
+                self._g_opt.replay()
             _module.bump_weight_generation()      # eager callers (sampling, eval) must re-pack the new weights
             loss = self._static_loss
         self.global_step += 1
@@ -245,11 +325,18 @@ class FusedTrainStep:
         from . import _C
         c0 = _C.launch_count
         self._g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_fb):
-            self._static_loss = self._forward_backward(self._static_x)
-        self._g_opt = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g_opt):
-            self._optimizer()
+        if self.overlap:
+            # NCCL collectives are captured with the kernels: one graph for the whole iteration
+            with torch.cuda.graph(self._g_fb):
+                self._static_loss = self._forward_backward(self._static_x)
+                self._optimizer()
+            self._g_opt = None
+        else:
+            with torch.cuda.graph(self._g_fb):
+                self._static_loss = self._forward_backward(self._static_x)
+            self._g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g_opt):
+                self._optimizer()
         self.captured_calls = _C.launch_count - c0     # glowk C-ABI launches replayed per step
         # the captures above only recorded; nothing has executed yet
 

@@ -80,3 +80,44 @@ def test_shard_batch_rejects_ragged_batches():
     from pytorch_glow_b200.train import shard_batch
     with pytest.raises(ValueError):
         shard_batch(torch.zeros(7, 3), 0, 2)
+
+
+def _worker_levels(rank, world, port, out):
+    """Per-level (bucketed, asynchronous) gradient averaging == one all-reduce of the whole arena."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        import pytorch_glow_b200 as G
+        from pytorch_glow_b200.hps import make_hps
+        from pytorch_glow_b200.train import FlatArena, allreduce_mean_, arena_level_ranges
+        np.random.seed(0); torch.manual_seed(0)
+        glow = G.Glow(make_hps((16, 16, 3), K=2, L=3, hidden_channels=8, batch=2, devices=("cpu",)))
+        glow.h_top.requires_grad_(False)
+        arena = FlatArena(glow)
+        ranges = arena_level_ranges(glow, arena)
+        assert len(ranges) == 3 and ranges[0][0] == 0 and ranges[-1][1] == arena.numel
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        # every parameter lies in the slice of its own level (flow.layers: squeeze, 2 steps, split, squeeze, ...)
+        for name, off in zip(arena.names, arena.offsets):
+            layer = int(name.split(".")[2])
+            level = 0 if layer < 4 else (1 if layer < 8 else 2)
+            assert ranges[level][0] <= off < ranges[level][1], (name, off, ranges)
+        g = torch.Generator().manual_seed(100 + rank)
+        arena.grad.copy_(torch.randn(arena.numel, generator=g))
+        whole = arena.grad.clone()
+        allreduce_mean_(whole)
+        works = [allreduce_mean_(arena.grad[lo:hi], async_op=True) for lo, hi in reversed(ranges)]   # top level first
+        for w in works:
+            w.wait()
+        out[rank] = bool(torch.allclose(arena.grad, whole, rtol=0, atol=1e-7))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_per_level_allreduce_matches_whole_arena_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_levels, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert len(out) == world and all(out[r] for r in range(world))
