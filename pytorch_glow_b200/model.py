@@ -173,6 +173,15 @@ class FlowModel(nn.Module):
                 m._cache.put(("dense", need_inverse), m.weight, (ld[i:i + 1], None if winv is None else winv[i]))
 
     def encode(self, z, logdet=0.):
+        if torch.is_grad_enabled() and getattr(self, "_is_replica", False):
+            # torch.nn.DataParallel replicas hold their weights as plain attributes (replicate() empties
+            # `_parameters`): the fused backward, which accumulates straight into param.grad, cannot reach the master
+            # module through them.  Inference under DataParallel works; training is one process per GPU.
+            raise RuntimeError(
+                "pytorch_glow_b200.FlowModel cannot be TRAINED under torch.nn.DataParallel (network/trainer.py:117-120): "
+                "its backward accumulates into param.grad of the module it runs on, and DataParallel replicas have no "
+                "parameters.  Use one process per GPU with pytorch_glow_b200.train.FusedTrainStep (flat gradient "
+                "arena + NCCL all-reduce), see INTEGRATION.md section 2; torch.no_grad() inference under DataParallel is fine.")
         use_autograd = torch.is_grad_enabled() and (z.requires_grad or any(p.requires_grad for p in self.parameters()))
         if z.is_cuda:
             self.prepare_invconvs(need_inverse=use_autograd)      # the adjoint needs W^-T (logdet term)

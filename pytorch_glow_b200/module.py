@@ -75,6 +75,17 @@ class _PackCache:
         self._d.clear()
 
 
+def _wants_grad(mod, x):
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in mod.parameters()))
+
+
+def _no_standalone_autograd(name):
+    raise NotImplementedError(
+        "pytorch_glow_b200.%s has no stand-alone autograd: its forward runs the CUDA kernels on detached weights.  "
+        "Gradients of the coupling network are produced by the fused FlowStep / FlowModel nodes "
+        "(FlowStep.forward, FlowModel.encode, Glow.forward); call it under torch.no_grad() or train through those." % name)
+
+
 # ------------------------------------------------------------------ ActNorm
 class ActNorm(nn.Module):
     """Activation normalisation (network/module.py:9-149)."""
@@ -205,6 +216,8 @@ class Conv2d(nn.Conv2d):
     def forward(self, x, conv_dtype=None):
         ks = self._check_supported()
         _C.check_cuda(x)
+        if _wants_grad(self, x):
+            _no_standalone_autograd("Conv2d")
         n, _, h, w = x.shape
         dt = config.resolve_conv_dtype(64, conv_dtype)   # K and N are padded to the tensor-core tiling
         f = 3.0
@@ -250,6 +263,12 @@ class Conv2dZeros(nn.Conv2d):
 
     def forward(self, x, conv_dtype=None):
         _C.check_cuda(x)
+        if _wants_grad(self, x):
+            # `Glow.prior` with ablation.learn_top (network/model.py:371-373) trains this conv on the all-zero h_top:
+            # a [B, 2C, H_top, W_top] side input off the flow's hot path.  It stays differentiable through ATen (like
+            # LinearZeros, which the reference also keeps in torch) instead of silently detaching its weights.
+            out = torch.nn.functional.conv2d(x, self.weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+            return out * torch.exp(self.logs * self.logscale_factor)
         n, cin, h, w = x.shape
         if tuple(self.kernel_size) == (3, 3):
             rows = self.forward_rows(x, 0, cin, conv_dtype)
@@ -392,6 +411,8 @@ class CouplingNet(nn.Sequential):
     def forward(self, x, conv_dtype=None):
         """Stand-alone NCHW -> NCHW evaluation (drop-in for the reference's nn.Sequential)."""
         _C.check_cuda(x)
+        if _wants_grad(self, x):
+            _no_standalone_autograd("f() / CouplingNet")
         x = x.contiguous()
         n, _, h, w = x.shape
         p3 = self.tap_rows(x, conv_dtype)

@@ -132,3 +132,27 @@ def test_rows_path_level_dispatch():
     assert hq_perm.layers[k - 2].in_channels == 96 and hq_perm.layers[k + 1].in_channels == 192
     k7 = rows_path._prefix_len(too_wide)
     assert isinstance(too_wide.layers[k7 - 1], G.Split2d) and too_wide.layers[k7 + 1].in_channels == 768
+
+
+def test_standalone_modules_refuse_silent_graph_cuts():
+    """stand-alone Conv2d / f() ran on detached weights and returned tensors without grad_fn.  They now
+    raise when a gradient is wanted; Conv2dZeros (learn_top, network/model.py:371-373) stays differentiable."""
+    import pytest
+    import pytorch_glow_b200 as G
+    from pytorch_glow_b200._C import GlowkError
+    conv = G.Conv2d(4, 8)
+    x = torch.zeros(1, 4, 4, 4)
+    with pytest.raises((GlowkError, NotImplementedError)):
+        conv(x)                                       # CPU tensor: no fallback either way
+    z = G.Conv2dZeros(4, 4)
+    out = torch.nn.functional.conv2d(x, z.weight, z.bias, padding=1) * torch.exp(z.logs * 3)
+    assert out.requires_grad                          # the torch formula the differentiable path uses
+
+
+def test_flowmodel_training_under_dataparallel_replica_raises():
+    import pytest
+    import pytorch_glow_b200 as G
+    fm = G.FlowModel((8, 8, 3), 8, K=1, L=1)
+    fm._is_replica = True                             # what torch.nn.parallel.replicate sets on replicas
+    with pytest.raises(RuntimeError, match="DataParallel"):
+        fm.encode(torch.zeros(1, 3, 8, 8))
