@@ -84,7 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   float* s_g = s_gy + EPI_NMAX;
   Shared* sh = reinterpret_cast<Shared*>(s_gy + (EPI == GLOWK_EPI_RELU_BWD ? 2 * EPI_NMAX : 0));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int csize = CM * CN;
   const uint32_t crank = csize > 1 ? cluster_ctarank() : 0;
   const int cm = (int)crank % CM, cn = (int)crank / CM;
@@ -177,7 +177,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && !(pair && crank != 0)) {      // pair mode: the leader CTA issues for both
+    // The whole warp runs the loop (warp-uniform control flow: descriptors stay in uniform registers, no R2UR + vote
+    // loop around every UTCHMMA); one elected lane issues.  Pair mode: the leader CTA issues for both.
+    if (!(pair && crank != 0)) {
       // M field: 128 for one CTA, 256 for the pair
       const uint32_t idesc = make_idesc(block_n, 0, 0) + (pair ? ((uint32_t)(BLOCK_M >> 4) << 24) : 0u);
       int stage = 0; uint32_t phase = 0;
@@ -196,32 +198,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, 16, 1024);
           const uint64_t bdesc = make_smem_desc(sa + a_bytes, 16, 1024);
-          if constexpr (PAIR) {
+          if (elect_one_sync()) {
+            if constexpr (PAIR) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-              tcgen05_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            tcgen05_commit_pair(&sh->empty_bar[stage]);            // frees the slot in both CTAs
-            if (++stage == num_stages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          if (!(dbg & 2)) {
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                tcgen05_mma_bf16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              tcgen05_commit_pair(&sh->empty_bar[stage]);            // frees the slot in both CTAs
+            } else {
+              if (!(dbg & 2)) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span (>>4 => +2)
-              tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                  // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle span (>>4 => +2)
+                  tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                }
+              }
+              // smem slot reusable once these MMAs retire: tell every CTA that writes into it
+              if (dbg & 8) {}
+              else if (csize == 1) tcgen05_commit(&sh->empty_bar[stage]);
+              else tcgen05_commit_mc(&sh->empty_bar[stage], mask_all);
             }
           }
-          // smem slot reusable once these MMAs retire: tell every CTA that writes into it
-          if (dbg & 8) {}
-          else if (csize == 1) tcgen05_commit(&sh->empty_bar[stage]);
-          else tcgen05_commit_mc(&sh->empty_bar[stage], mask_all);
+          __syncwarp();
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        if constexpr (PAIR) tcgen05_commit_pair(&sh->tmem_full_bar[acc]);        // accumulator complete (both CTAs' halves)
-        else tcgen05_commit(&sh->tmem_full_bar[acc]);
+        if (elect_one_sync()) {
+          if constexpr (PAIR) tcgen05_commit_pair(&sh->tmem_full_bar[acc]);        // accumulator complete (both CTAs' halves)
+          else tcgen05_commit(&sh->tmem_full_bar[acc]);
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (tr) { g_gemm_trace[2] = w_full; g_gemm_trace[3] = w_acc; g_gemm_trace[4] = (unsigned long long)(clock64() - t_begin); g_gemm_trace[9] = ntile; }
+      if (tr && lane == 0) { g_gemm_trace[2] = w_full; g_gemm_trace[3] = w_acc; g_gemm_trace[4] = (unsigned long long)(clock64() - t_begin); g_gemm_trace[9] = ntile; }
     }
   } else if constexpr (EPI == GLOWK_EPI_RELU_BWD) {
     // ===================== ReLU-backward epilogue: 16 warps, 32-column chunks =====================
@@ -550,7 +557,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   uint8_t* staging = smem + (size_t)num_stages * stage_bytes;     // one [32][32] fp32 box per epilogue warp
   Shared* sh = reinterpret_cast<Shared*>(staging + STAGING_BYTES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int m_blocks = (Mo + BLOCK_M - 1) / BLOCK_M;
   const int n_blocks = (No + block_n - 1) / block_n;
   const int total_kb = (P + BLOCK_K - 1) / BLOCK_K;
@@ -601,7 +608,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       pdl_trigger_drain();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // the whole warp runs the loop (warp-uniform control flow keeps descriptors in uniform registers: no R2UR +
+    // vote loop around every UTCHMMA); one elected lane issues -- see cnet_fused_sm100.cu
+    {
       const uint32_t idesc = make_idesc(block_n, 1, 1);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -619,16 +628,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           // MN-major: 64-element M/N blocks are 8192 B apart (LBO); 8-k groups 1024 B apart (SBO)
           const uint64_t adesc = make_smem_desc(sa, 8192, 1024);
           const uint64_t bdesc = make_smem_desc(sa + a_bytes, 8192, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 k-rows = 2048 bytes (>>4 => +128)
-            tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
-                             (kb > kb0) || (k != 0));
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advance 16 k-rows = 2048 bytes (>>4 => +128)
+              tcgen05_mma_bf16(d_tmem, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc,
+                               (kb > kb0) || (k != 0));
+            }
+            tcgen05_commit(&sh->empty_bar[stage]);
           }
-          tcgen05_commit(&sh->empty_bar[stage]);
+          __syncwarp();
           if (++stage == num_stages) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&sh->tmem_full_bar[acc]);
+        if (elect_one_sync()) tcgen05_commit(&sh->tmem_full_bar[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
