@@ -176,6 +176,8 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp: provably uniform
   const int num_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int upt = NCHUNK / p.nhb;                                  // uses of one chunk buffer per tile
+  // accumulator buffer uses per tile: GEMM1 alternates the two buffers; GEMM2 stays on buffer 0 unless GEMM3 is deferred
+  const uint32_t uses0 = p.deferred ? 4u : 6u, uses1 = p.deferred ? 4u : 2u;
 
   if ((smem_u32(smem) & 1023u) != 0) { if (threadIdx.x == 0) printf("glowk: dynamic smem not 1024-aligned\n"); __trap(); }
   if (warp == 0 && lane == 0) {
@@ -318,7 +320,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       CNET_TS(tl, 1);
       for (int c = 0; c < NCHUNK; ++c) {
         const int buf = c & 1;
-        const uint32_t idx = buf ? tcount * 2u + (uint32_t)(c >> 1) : tcount * 6u + (uint32_t)(c >> 1);
+        const uint32_t idx = tcount * (buf ? uses1 : uses0) + (uint32_t)(c >> 1);
         wait_t(&sh->acc_empty[buf], (idx & 1) ^ 1, tr, w1);
         if (c == 1 && !p.deferred) wait_t(&sh->c3_empty, (tcount & 1) ^ 1, tr, w1);   // [384,512) was GEMM3's accumulator
         CNET_TS(tl, 2 + 2 * c);
@@ -354,10 +356,12 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       wait_t(&sh->h1_full, tcount & 1, tr, w3);
       CNET_TS(tl, 10);
       for (int c = 0; c < NCHUNK; ++c) {
-        const uint32_t idx = tcount * 6u + 2u + (uint32_t)c;
-        wait_t(&sh->acc_empty[0], (idx & 1) ^ 1, tr, w4);
+        // deferred layout: [384,512) is free while GEMM2 runs -> ping-pong, EPI2 of chunk c overlaps GEMM2 of chunk c+1
+        const int buf2 = p.deferred ? (c & 1) : 0;
+        const uint32_t idx = tcount * (buf2 ? uses1 : uses0) + 2u + (uint32_t)(p.deferred ? (c >> 1) : c);
+        wait_t(&sh->acc_empty[buf2], (idx & 1) ^ 1, tr, w4);
         CNET_TS(tl, 11 + 3 * c);
-        const uint32_t d = tmem_base + (uint32_t)COL_ACC0;
+        const uint32_t d = tmem_base + (uint32_t)(buf2 ? COL_ACC1 : COL_ACC0);
 #pragma unroll
         for (int kb = 0; kb < HID / BLOCK_K; kb += BPS) {
           acquire(w5);
@@ -377,7 +381,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           }
           advance();
         }
-        if (elect_one_sync()) tcgen05_commit(&sh->acc_full[0]);
+        if (elect_one_sync()) tcgen05_commit(&sh->acc_full[buf2]);
         __syncwarp();
         CNET_TS(tl, 12 + 3 * c);
         if (!p.deferred && c >= 1) { gemm3_partial(c - 1); CNET_TS(tl, 13 + 3 * c); }
@@ -547,7 +551,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       // ---- EPI1: chunk accumulators -> bf16 -> TMEM (A operand of GEMM2)
       for (int c = 0; c < NCHUNK; ++c) {
         const int buf = c & 1;
-        const uint32_t idx = buf ? tcount * 2u + (uint32_t)(c >> 1) : tcount * 6u + (uint32_t)(c >> 1);
+        const uint32_t idx = tcount * (buf ? uses1 : uses0) + (uint32_t)(c >> 1);
         if (BWD) {                                                 // next mask box -> the other slice
           if (lane == 0) tma_store_wait_read<0>();                 // (my TMA store that last read it has retired)
           __syncwarp();
@@ -583,12 +587,13 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       }
       // ---- EPI2: chunk accumulators -> bf16 -> shared-memory chunk (A operand of GEMM3)
       for (int c = 0; c < NCHUNK; ++c) {
-        const uint32_t idx = tcount * 6u + 2u + (uint32_t)c;
-        wait_t(&sh->acc_full[0], idx & 1, tr, e2);
+        const int buf2 = p.deferred ? (c & 1) : 0;
+        const uint32_t idx = tcount * (buf2 ? uses1 : uses0) + 2u + (uint32_t)(p.deferred ? (c >> 1) : c);
+        wait_t(&sh->acc_full[buf2], idx & 1, tr, e2);
         CNET_TS(tl, 44 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 1, COL_ACC0, &sh->acc_empty[0], pk, tl ? 45 + 3 * c : -1, tcount);
+        epilogue_chunk(c, 1, buf2 ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf2], pk, tl ? 45 + 3 * c : -1, tcount);
         CNET_TS(tl && c == 1, 60);
         const int b = c % p.nhb;
         const uint32_t hidx = tcount * (uint32_t)upt + (uint32_t)(c / p.nhb);
@@ -724,7 +729,9 @@ struct Variant { int NH, N3, nhb, c3_col, deferred, nstages, bps; size_t smem; }
 static bool pick_variant(int mode, int64_t K1, int64_t n3tot, Variant* v) {
   if (K1 <= 0 || K1 % 64 != 0 || n3tot <= 0 || n3tot % 16 != 0) return false;
   if (mode == MODE_BWD && n3tot > 128) return false;           // the in-place mask boxes assume two chunk buffers
-  if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
+  const char* fd = getenv("GLOWK_CNET_DEFERRED");                 // experiments: deferred-GEMM3 layout for narrow N3 too
+  if (n3tot <= 128 && mode == MODE_FWD && fd && fd[0] == '1') { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 4; v->c3_col = COL_H; v->deferred = 1; }
+  else if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
   else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 4; v->c3_col = COL_H; v->deferred = 1; }
   else return false;
   const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES + 
