@@ -306,6 +306,15 @@ int glowk_rows_coupling(const float* P3, int64_t ldp, const float* bias3, const 
                         const float* ld_in, float* ld_out, const float* an_logs, float an_logscale_factor,
                         const float* logabsdet, float sign, float* partials, void* tickets, void* stream);
 
+/* Reverse pass of a FlowStep behind the coupling network in one launch (model.py:131-152): inverse coupling
+ * (glowk_rows_coupling, reverse = 1, no logdet) applied to the rows x while they are staged in shared memory, then
+ * glowk_rows_actnorm_mix(reverse = 1) with w = W^-1 (or idx = inverse permutation); x is NOT modified, the result
+ * goes to z.  Bit-identical to the two calls; C a multiple of 4, <= glowk_rows_max_channels(). */
+int glowk_rows_coupling_rev_mix(const float* P3, int64_t ldp, const float* bias3, const float* logs3,
+                                float logscale_factor3, const float* x, float* z, const float* w, const int64_t* idx,
+                                const float* bias, const float* logs, float logscale_factor, int64_t N, int64_t C,
+                                int64_t H, int64_t W, int affine, void* stream);
+
 /* glowk_coupling_bwd on rows: y, dy, dz: [P][C]; hrows, du: [P][Cout]. */
 int glowk_rows_coupling_bwd(const float* y, const float* hrows, const float* dy, const float* dld, const float* logs3,
                             float logscale_factor, float* dz, float* du, float* dlogs3, float* dbias3, int64_t N,

@@ -71,6 +71,7 @@ SIGNATURES = {
     "glowk_rows_coupling_nblk": [_i64, _i64],
     "glowk_rows_coupling": [_p, _i64, _p, _p, _f32, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _p, _p, _f32,
                             _p, _f32, _p, _p, _p],
+    "glowk_rows_coupling_rev_mix": [_p, _i64, _p, _p, _f32, _p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i64, _i64, _i32, _p],
     "glowk_rows_coupling_bwd": [_p, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _i64, _i64, _i64, _i32, _p],
     "glowk_rows_actnorm_mix_bwd": [_p, _p, _p, _i64, _i64, _p, _p, _p, _p, _f32, _p, _p, _p, _p, _i64, _i64, _i64,
                                    _i64, _p, _p, _p],

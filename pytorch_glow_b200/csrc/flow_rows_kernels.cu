@@ -155,6 +155,170 @@ rows_mix_kernel(const float* __restrict__ x, float* __restrict__ z, const float*
 }
 
 // ------------------------------------------------------------------------------------------
+// Reverse pass of a whole FlowStep behind the coupling network (model.py:131-152) in ONE kernel:
+//   coupling^-1 (tap gather-sum of P3, Conv2dZeros scale, z2 = z2/scale - shift | z2 - h)  ->  W^-1 mix | perm^-1
+//   ->  ActNorm^-1.
+// rows_mix_kernel stages the pixel rows of a pass in shared memory anyway; here the staged rows are transformed in
+// place by the inverse coupling before the mix reads them, so the sampling pass launches one flow kernel per step
+// instead of two (the two were ~16 us each at every level: launch / latency bound) and the coupled rows make no
+// HBM round trip.  Arithmetic (operation order included) is that of rows_coupling_kernel followed by
+// rows_mix_kernel: results are bit-identical to the two-launch path.
+// ------------------------------------------------------------------------------------------
+template <bool PERM, int CT>
+__global__ void __launch_bounds__(256, 4)
+rows_coupling_rev_mix_kernel(const float* __restrict__ P3, int ldp, const float* __restrict__ bias3,
+                             const float* __restrict__ logs3, float f3, int affine, int H, int W, FastDiv divW,
+                             FastDiv divHW, FastDiv divCh, const float* __restrict__ x, float* __restrict__ z,
+                             const float* __restrict__ w, const int64_t* __restrict__ idx,
+                             const float* __restrict__ bias, const float* __restrict__ logs, float f, int P, int C_rt,
+                             int iters) {
+  pdl_trigger();
+  pdl_wait();
+  const int C = CT ? CT : C_rt;
+  const int Ch = C >> 1, Cout = affine ? C : Ch, HW = H * W;
+  extern __shared__ __align__(16) float smem[];
+  float* wt = smem;                               // [C][C]: wt[i*C + o] = W^-1[o][i]   (mix only)
+  float* sc = wt + (PERM ? 0 : C * C);            // [C] exp(-f*logs)
+  float* bs = sc + C;                             // [C] bias
+  float* s_b3 = bs + C;                           // [C] Conv2dZeros bias
+  float* s_e3 = s_b3 + C;                         // [C] exp(f3*logs3)
+  int* sidx = reinterpret_cast<int*>(s_e3 + C);   // [C] (perm only)
+  const int og = threadIdx.x, slot = threadIdx.y;
+  const int nthr = blockDim.x * blockDim.y;
+  const int tid = slot * blockDim.x + og;
+  const int ppp = 2 * blockDim.y;                 // pixels per pass
+  float* xbuf = reinterpret_cast<float*>(sidx + C);   // [2][ppp][C]
+  const int64_t total4 = (int64_t)P * C / 4;
+  auto stage_pass = [&](int it_) {
+    const int64_t base4 = (int64_t)(blockIdx.x * iters + it_) * ppp * C / 4;
+    float* dst = xbuf + (it_ & 1) * ppp * C;
+    const int n4 = ppp * C / 4;
+    for (int i = tid; i < n4; i += nthr)
+      if (base4 + i < total4) cp_async16(dst + 4 * i, x + 4 * (base4 + i));
+    cp_async_commit();
+  };
+  stage_pass(0);
+  const bool has_an = bias != nullptr;
+  for (int c = tid; c < C; c += nthr) {
+    const float l = has_an ? logs[c] * f : 0.f;
+    sc[c] = has_an ? expf(-l) : 1.f;
+    bs[c] = has_an ? bias[c] : 0.f;
+    if (c < Cout) { s_b3[c] = bias3[c]; s_e3[c] = expf(logs3[c] * f3); }
+    if (PERM) sidx[c] = (int)idx[c];
+  }
+  if (!PERM)
+    for (int o = slot; o < C; o += blockDim.y)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) wt[(og * 4 + u) * C + o] = w[o * C + og * 4 + u];
+  __syncthreads();
+  for (int it = 0; it < iters; ++it) {
+    const int pix0 = (blockIdx.x * iters + it) * ppp;
+    if (pix0 >= P) break;                                           // (CTA-uniform)
+    if (it + 1 < iters) { stage_pass(it + 1); cp_async_wait_group<1>(); } else cp_async_wait_group<0>();
+    __syncthreads();
+    float* xb_ = xbuf + (it & 1) * ppp * C;
+    // ---- inverse coupling on the staged rows: item = (pixel of the pass, channel pair | channel)
+    for (int i = tid; i < ppp * Ch; i += nthr) {
+      const int pl = fdiv(i, divCh), j = i - pl * Ch;
+      const int pixg = pix0 + pl;
+      if (pixg >= P) break;
+      const int n = fdiv(pixg, divHW), pix = pixg - n * HW;
+      const int yy = fdiv(pix, divW), xx = pix - yy * W;
+      const bool up = yy > 0, dn = yy < H - 1, lf = xx > 0, rt = xx < W - 1;
+      float* zp = xb_ + pl * C + Ch + j;
+      if (affine) {
+        const float* Pp = P3 + (int64_t)pixg * ldp + 2 * j;
+        float u0 = 0.f, u1 = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+          if (ok) {
+            const float2 v = *reinterpret_cast<const float2*>(Pp + (dy * W + dx) * ldp + t * Cout);
+            u0 += v.x; u1 += v.y;
+          }
+        }
+        // __fmul_rn: no FMA contraction with the consumers below -- rows_coupling_kernel materialises shift / hsc
+        // (it can store them for the backward pass), and the two paths must agree bit for bit
+        const float shift = __fmul_rn(u0 + s_b3[2 * j], s_e3[2 * j]);
+        const float hsc = __fmul_rn(u1 + s_b3[2 * j + 1], s_e3[2 * j + 1]);
+        const float scale = 1.f / (1.f + expf(-(hsc + 2.f)));   // F.sigmoid(scale + 2.)
+        float v = *zp;
+        v = v / scale - shift;
+        *zp = v;
+      } else {
+        const float* Pp = P3 + (int64_t)pixg * ldp + j;
+        float u = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const int dy = t / 3 - 1, dx = t % 3 - 1;
+          const bool ok = (dy < 0 ? up : (dy > 0 ? dn : true)) && (dx < 0 ? lf : (dx > 0 ? rt : true));
+          if (ok) u += Pp[(dy * W + dx) * ldp + t * Cout];
+        }
+        const float h = __fmul_rn(u + s_b3[j], s_e3[j]);
+        *zp = *zp - h;
+      }
+    }
+    __syncthreads();
+    // ---- W^-1 mix / inverse permutation + ActNorm^-1 (rows_mix_kernel, reverse)
+    const int pixA = pix0 + slot;
+    const int pixB = pixA + blockDim.y;
+    const bool hasA = pixA < P, hasB = pixB < P;
+    const float* xrA = xb_ + (hasA ? slot : 0) * C;
+    const float* xrB = xb_ + (hasB ? slot + (int)blockDim.y : (hasA ? slot : 0)) * C;
+    float accA[4], accB[4];
+    if (PERM) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int o = og * 4 + a, sx = sidx[o];
+        float tA = xrA[sx], tB = xrB[sx];
+        if (has_an) { tA = tA * sc[o] - bs[o]; tB = tB * sc[o] - bs[o]; }
+        accA[a] = tA; accB[a] = tB;
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) { accA[a] = 0.f; accB[a] = 0.f; }
+#pragma unroll
+      for (int i0 = 0; i0 < C; i0 += 12) {
+        float4 xa4[3], xb4[3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const bool in = i0 + 4 * b < C;
+          xa4[b] = in ? *reinterpret_cast<const float4*>(xrA + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
+          xb4[b] = in ? *reinterpret_cast<const float4*>(xrB + i0 + 4 * b) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+          const int i = i0 + 4 * b;
+          if (i < C) {
+            const float xa[4] = {xa4[b].x, xa4[b].y, xa4[b].z, xa4[b].w};
+            const float xb[4] = {xb4[b].x, xb4[b].y, xb4[b].z, xb4[b].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 wv = *reinterpret_cast<const float4*>(wt + (i + u) * C + og * 4);
+              accA[0] = fmaf(wv.x, xa[u], accA[0]); accA[1] = fmaf(wv.y, xa[u], accA[1]);
+              accA[2] = fmaf(wv.z, xa[u], accA[2]); accA[3] = fmaf(wv.w, xa[u], accA[3]);
+              accB[0] = fmaf(wv.x, xb[u], accB[0]); accB[1] = fmaf(wv.y, xb[u], accB[1]);
+              accB[2] = fmaf(wv.z, xb[u], accB[2]); accB[3] = fmaf(wv.w, xb[u], accB[3]);
+            }
+          }
+        }
+      }
+      if (has_an) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          accA[a] = accA[a] * sc[og * 4 + a] - bs[og * 4 + a];
+          accB[a] = accB[a] * sc[og * 4 + a] - bs[og * 4 + a];
+        }
+      }
+    }
+    if (hasA) *reinterpret_cast<float4*>(z + (int64_t)pixA * C + og * 4) = make_float4(accA[0], accA[1], accA[2], accA[3]);
+    if (hasB) *reinterpret_cast<float4*>(z + (int64_t)pixB * C + og * 4) = make_float4(accB[0], accB[1], accB[2], accB[3]);
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Tap gather-sum (second half of Conv2dZeros as nine pointwise GEMMs, module.py:295-296) + coupling
 // (model.py:105-115 fwd, 131-140 rev) + this step's logdet (module.py:77-82, 357-367; model.py:114,140).
 // grid = (nblk, N), block = (Ch, PPB): thread (j, slot) owns channel pair j of one pixel; the Ch lanes of a
@@ -1367,6 +1531,52 @@ extern "C" int glowk_rows_actnorm_mix(const float* x, float* z, const float* w, 
   }
 #undef GLOWK_MIX_LAUNCH
   GLOWK_CHECK_LAUNCH("glowk_rows_actnorm_mix");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_coupling_rev_mix(const float* P3, int64_t ldp, const float* bias3, const float* logs3,
+                                           float logscale_factor3, const float* x, float* z, const float* w,
+                                           const int64_t* idx, const float* bias, const float* logs,
+                                           float logscale_factor, int64_t N, int64_t C, int64_t H, int64_t W, int affine,
+                                           void* stream) {
+  const int64_t P = N * H * W;
+  if (P == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(P3 && bias3 && logs3 && x && z && x != z, "glowk_rows_coupling_rev_mix: bad pointers");
+  GLOWK_CHECK_ARG((w != nullptr) != (idx != nullptr), "glowk_rows_coupling_rev_mix: exactly one of w / idx");
+  GLOWK_CHECK_ARG((bias != nullptr) == (logs != nullptr), "glowk_rows_coupling_rev_mix: bias and logs go together");
+  GLOWK_CHECK_ARG(C > 0 && C % 4 == 0 && C <= ROWS_MAX_C, "glowk_rows_coupling_rev_mix: C=%lld must be a multiple of 4, <= %d", (long long)C, ROWS_MAX_C);
+  const int64_t Cout = affine ? C : C / 2;
+  GLOWK_CHECK_ARG(ldp >= 9 * Cout && ldp % 2 == 0, "glowk_rows_coupling_rev_mix: ldp=%lld too small for 9*Cout=%lld", (long long)ldp, (long long)(9 * Cout));
+  GLOWK_CHECK_ARG((((uintptr_t)x | (uintptr_t)z) & 15) == 0 && (((uintptr_t)P3) & 7) == 0, "glowk_rows_coupling_rev_mix: rows must be 16-byte aligned");
+  GLOWK_CHECK_ARG(P * C < (1ll << 31) && P * ldp < (1ll << 31), "glowk_rows_coupling_rev_mix: tensor too large for 32-bit indexing");
+  const int G = (int)C / 4, ppb = 256 / G;
+  const dim3 block((unsigned)G, (unsigned)ppb);
+  cudaStream_t st = (cudaStream_t)stream;
+  const FastDiv dW = make_fastdiv(W), dHW = make_fastdiv(H * W), dCh = make_fastdiv(C / 2);
+#define GLOWK_CRM_LAUNCH(PERM_, CT_, SMEM_)                                                                          \
+  do {                                                                                                               \
+    auto kern = rows_coupling_rev_mix_kernel<PERM_, CT_>;                                                            \
+    if (SMEM_ > 40 * 1024) GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); \
+    const int64_t passes = ceil_div(P, 2 * ppb);                                                                     \
+    int iters = (int)ceil_div(passes, resident_ctas((const void*)kern, G * ppb, SMEM_));                             \
+    iters = iters < 1 ? 1 : (iters > 32 ? 32 : iters);                                                               \
+    const unsigned grid = (unsigned)ceil_div(passes, iters);                                                         \
+    GLOWK_CUDA(launch_pdl(kern, grid, block, SMEM_, st, P3, (int)ldp, bias3, logs3, logscale_factor3, affine, (int)H, \
+                          (int)W, dW, dHW, dCh, x, z, w, idx, bias, logs, logscale_factor, (int)P, (int)C, iters));  \
+  } while (0)
+  const size_t xbuf_bytes = sizeof(float) * 2 * (size_t)(2 * ppb) * C;
+  if (w) {
+    const size_t smem = sizeof(float) * ((size_t)C * C + 5 * C) + xbuf_bytes;
+    if (C == 12) GLOWK_CRM_LAUNCH(false, 12, smem);
+    else if (C == 24) GLOWK_CRM_LAUNCH(false, 24, smem);
+    else if (C == 48) GLOWK_CRM_LAUNCH(false, 48, smem);
+    else GLOWK_CRM_LAUNCH(false, 0, smem);
+  } else {
+    const size_t smem = sizeof(float) * (5 * (size_t)C) + xbuf_bytes;
+    GLOWK_CRM_LAUNCH(true, 0, smem);
+  }
+#undef GLOWK_CRM_LAUNCH
+  GLOWK_CHECK_LAUNCH("glowk_rows_coupling_rev_mix");
   return GLOWK_OK;
 }
 

@@ -437,6 +437,18 @@ def rows_actnorm_mix(x, weight=None, indices=None, bias=None, logs=None, logscal
     return z
 
 
+def rows_coupling_rev_mix(p_rows, bias3, logs3, x, n, h, w, affine, logscale_factor3, weight=None, indices=None,
+                          bias=None, logs=None, logscale_factor=3.0):
+    """Reverse FlowStep behind the coupling net in one launch: inverse coupling (from the tap-GEMM output p_rows) +
+    W^-1 mix / inverse permutation + ActNorm^-1 on the rows x (left untouched); returns the new rows."""
+    check_cuda(p_rows, bias3, logs3, x, weight, indices, bias, logs)
+    z = torch.empty_like(x)
+    call("glowk_rows_coupling_rev_mix", ptr(p_rows), p_rows.shape[1], ptr(bias3), ptr(logs3), float(logscale_factor3),
+         ptr(x), ptr(z), ptr(weight), ptr(indices), ptr(bias), ptr(logs), float(logscale_factor), n, x.shape[1], h, w,
+         int(bool(affine)))
+    return z
+
+
 def rows_coupling_nblk(hw, c):
     return int(_C.lib().glowk_rows_coupling_nblk(hw, c))
 

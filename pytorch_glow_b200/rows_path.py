@@ -10,6 +10,8 @@ launch each (`PackPlan`, `GradPlan`).
 The per-layer modules (module.py / model.py) keep the reference's NCHW call conventions and kernels;
 this file is what FlowModel uses when the whole model fits the rows kernels (`supported`).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -396,9 +398,14 @@ def _step_reverse(step, x, n, c, h, w, ws):
     dt = net.dtype(step.conv_dtype)
     p3 = net.tap_rows_from_rows(x, n, h, w, dt)
     c3 = net[4]
+    wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
+    if not _is_wide(c) and os.environ.get("GLOWK_REV_FUSED", "1") != "0":
+        # inverse coupling + W^-1 mix + ActNorm^-1 in ONE launch (the coupled rows never leave shared memory)
+        return K.rows_coupling_rev_mix(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w,
+                                       step.coupling == 'affine', c3.logscale_factor, wm, idx,
+                                       an.bias.detach().reshape(-1), an.logs.detach().reshape(-1), an.logscale_factor)
     K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
                     c3.logscale_factor)
-    wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
     if _is_wide(c):
         return _mix_wide_forward(x, wm, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
                                  an.logscale_factor, True)

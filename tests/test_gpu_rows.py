@@ -485,3 +485,33 @@ def test_alternate_kernels_behind_ab_switches():
                               "flowmodel_rows_equals_nchw_path or flowmodel_rows_gradients_equal_nchw_path"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("c,h,w,affine,perm", [(12, 32, 32, True, False), (24, 16, 16, True, False), (48, 8, 8, True, False),
+                                               (12, 10, 6, False, False), (24, 5, 7, True, True), (96, 4, 4, False, False)])
+def test_rows_coupling_rev_mix_matches_two_launches(c, h, w, affine, perm):
+    """One-launch reverse FlowStep tail (inverse coupling + W^-1 mix + ActNorm^-1, model.py:131-152) == glowk_rows_coupling
+    (reverse) followed by glowk_rows_actnorm_mix (reverse), bit for bit."""
+    n = 3
+    g = torch.Generator().manual_seed(c * 100 + h)
+    cout = c if affine else c // 2
+    ldp = K.round_up(9 * cout, 16)
+    x = torch.randn(n * h * w, c, generator=g).cuda()
+    p3 = (torch.randn(n * h * w, ldp, generator=g) * 0.1).cuda()
+    b3 = (torch.randn(cout, generator=g) * 0.1).cuda()
+    l3 = (torch.randn(cout, generator=g) * 0.1).cuda()
+    bias = (torch.randn(c, generator=g) * 0.2).cuda()
+    logs = (torch.randn(c, generator=g) * 0.1).cuda()
+    wm = idx = None
+    if perm:
+        idx = torch.randperm(c, generator=g).cuda()
+    else:
+        wm = (torch.eye(c) + 0.05 * torch.randn(c, c, generator=g)).cuda()
+    ref = x.clone()
+    K.rows_coupling(p3, b3, l3, ref, n, h, w, affine, True, 3.0)
+    ref = K.rows_actnorm_mix(ref, wm, idx, bias, logs, 3.0, reverse=True)
+    x0 = x.clone()
+    got = K.rows_coupling_rev_mix(p3, b3, l3, x, n, h, w, affine, 3.0, wm, idx, bias, logs, 3.0)
+    torch.cuda.synchronize()
+    assert torch.equal(x, x0)                       # the input rows are not modified
+    assert torch.equal(got, ref), (got - ref).abs().max().item()
