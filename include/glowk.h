@@ -201,6 +201,16 @@ int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* w3t, int64_
                         const void* h1, void* d2, void* d1, int64_t ldh, void* da1, int64_t ldda1, float* dbias2,
                         float* dbias1, void* stream);
 
+/* glowk_cnet_backward with dgrad3's operand gathered in-kernel: d3col = flipped 3x3 im2col of du ([N*H*W][ldu] fp32,
+ * the gradient of Conv2dZeros' output from glowk_rows_coupling_bwd) -- exactly glowk_im2col_rows(flip = 1).  The tile is
+ * also stored to d3col_save ([M][ldd3] bf16): the conv3 weight-gradient GEMM reads it. */
+int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
+                                 void* d3col_save, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
+                                 int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t K3, int64_t hidden, int64_t K1p,
+                                 const float* logs2, float f2, const float* logs1, float f1, const void* h2,
+                                 const void* h1, void* d2, void* d1, int64_t ldh, void* da1, int64_t ldda1,
+                                 float* dbias2, float* dbias1, void* stream);
+
 /* ---- Coupling: model.py:105-115 (fwd) / 131-140 (rev) --------------------------------------
  * h[n,co,y,x] = (u + bias3[co]) * exp(f*logs3[co]),  u = 3x3 tap gather-sum of P (ldp floats/row,
  * column tap*Cout+co), i.e. Conv2dZeros (module.py:295-296).

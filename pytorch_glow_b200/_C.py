@@ -52,6 +52,8 @@ SIGNATURES = {
                                     _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p],
     "glowk_cnet_backward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _f32, _p, _f32, _p, _p,
                             _p, _p, _i64, _p, _i64, _p, _p, _p],
+    "glowk_cnet_backward_implicit": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
+                                     _i64, _p, _f32, _p, _f32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p],
     "glowk_coupling_nblk": [_i64],
     "glowk_coupling": [_p, _i64, _p, _p, _f32, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_logdet_finish": [_p, _p, _p, _i64, _f32, _p, _p, _i64, _i64, _f32, _i64, _p],

@@ -68,7 +68,7 @@ struct Params {
   // implicit conv1 (forward): the A tile is gathered in-kernel from the pixel-major flow state z [P][ld_z] fp32,
   // channels c0 .. c0+Cin-1, 3x3 taps with zero padding, k = tap*Cin + ci (glowk_im2col_rows); gather = 0: TMA load
   const float* z;
-  int gather, ld_z, c0, Cin, H, W, ones_col, save_a;
+  int gather, ld_z, c0, Cin, H, W, ones_col, save_a, flip;
 };
 
 // Profiling aid (GLOWK_CNET_DEBUG=1): wait cycles of CTA 0's roles, read back by glowk_debug_cnet_trace.
@@ -404,7 +404,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // state, rounds to bf16 and writes the K-major, 128B-swizzled A tile the MMA warp reads -- the job of
     // glowk_im2col_rows, without the HBM round trip of its output.  Training keeps the tile for the weight gradient
     // of conv1 (TMA store to a1_save) and sets the ones column (bias gradient through the wgrad GEMM).
-    if (!BWD && p.gather) {
+    if (p.gather) {
       const int gt = (int)threadIdx.x - 32 * (2 + EPI_WARPS);      // 0 .. 63
       const int HW = p.H * p.W, K = 9 * p.Cin, K1 = p.K1B * BLOCK_K;
       uint32_t tcount = 0;
@@ -424,7 +424,8 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const uint32_t sw = (uint32_t)(r & 7);
           int k = 0;
           for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+            const int tt = p.flip ? 8 - tap : tap;                 // flip: the adjoint's mirrored taps (dgrad of conv3)
+            const int dy = tt / 3 - 1, dx = tt - (tt / 3) * 3 - 1;
             const bool ok = row_ok && (unsigned)(yy + dy) < (unsigned)p.H && (unsigned)(xx + dx) < (unsigned)p.W;
             const float* src = p.z + (int64_t)(pix + dy * p.W + dx) * p.ld_z + p.c0;
             for (int ci = 0; ci < p.Cin; ci += 2, k += 2) {
@@ -766,7 +767,7 @@ static int launch_chain(const CUtensorMap* tm, const Params& p, size_t smem, cud
 
 // A: [M][K1] (lda), W1: [512][K1], W2: [512][512], W3: [n3tot][512]; o1/o2/y1/y2: [M][512] bf16 (ldh);
 // o3: forward fp32 [M][n3tot] (ldo3), backward bf16 [M][n3tot] (ldo3).
-struct Gather { const float* z; int64_t ld_z, c0, Cin, H, W, ones_col; };
+struct Gather { const float* z; int64_t ld_z, c0, Cin, H, W, ones_col; int flip; };
 
 int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, const void* W1, int64_t ldw1, const void* W2, int64_t ldw2,
                  const void* W3, int64_t ldw3, int64_t M, int64_t K1, int64_t n3tot, const float* bias1,
@@ -782,7 +783,7 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
   int gth_save_a = 0;
   if (gth) {
     gth_save_a = A != nullptr;
-    GLOWK_CHECK_ARG(!backward && gth->z && gth->Cin > 0 && gth->Cin % 2 == 0 && gth->c0 % 2 == 0 && gth->ld_z % 2 == 0 &&
+    GLOWK_CHECK_ARG(gth->z && gth->Cin > 0 && gth->Cin % 2 == 0 && gth->c0 % 2 == 0 && gth->ld_z % 2 == 0 &&
                     ((uintptr_t)gth->z) % 8 == 0 && 9 * gth->Cin <= K1 && gth->H > 0 && gth->W > 0 && M % (gth->H * gth->W) == 0 &&
                     (gth->ones_col < 0 || (gth->ones_col >= 9 * gth->Cin && gth->ones_col < K1)),
                     "glowk_cnet_forward_implicit: bad gather arguments");
@@ -820,8 +821,8 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
   p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
   p.dbias1 = dbias1; p.dbias2 = dbias2;
   p.z = gth ? gth->z : nullptr; p.gather = gth ? 1 : 0;
-  if (gth) { p.ld_z = (int)gth->ld_z; p.c0 = (int)gth->c0; p.Cin = (int)gth->Cin; p.H = (int)gth->H; p.W = (int)gth->W; p.ones_col = (int)gth->ones_col; }
-  else { p.ld_z = p.c0 = p.Cin = p.H = p.W = 0; p.ones_col = -1; }
+  if (gth) { p.ld_z = (int)gth->ld_z; p.c0 = (int)gth->c0; p.Cin = (int)gth->Cin; p.H = (int)gth->H; p.W = (int)gth->W; p.ones_col = (int)gth->ones_col; p.flip = gth->flip; }
+  else { p.ld_z = p.c0 = p.Cin = p.H = p.W = 0; p.ones_col = -1; p.flip = 0; }
   p.save_a = gth_save_a;
   if (v.bps == 2) return backward ? launch_chain<MODE_BWD, 2>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 2>(tm, p, v.smem, st);
   return backward ? launch_chain<MODE_BWD, 1>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 1>(tm, p, v.smem, st);
@@ -878,7 +879,7 @@ extern "C" int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t
   GLOWK_CHECK_ARG(ld_z >= c0 + Cin && ldw1 >= K1 && ldw2 >= hidden && ldw3 >= hidden && ldp3 >= N3 && (!a1_save || lda >= K1),
                   "glowk_cnet_forward_implicit: leading dimensions too small");
   GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward_implicit: ldh too small");
-  cnet::Gather g{z, ld_z, c0, Cin, H, W, ones_col};
+  cnet::Gather g{z, ld_z, c0, Cin, H, W, ones_col, 0};
   return cnet::chain_launch(0, &g, a1_save, a1_save ? lda : K1, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1,
                             bias2, logs2, f2, h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr,
                             nullptr, (cudaStream_t)stream);
@@ -897,4 +898,22 @@ extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* 
   // chain order: GEMM1 uses (w3t, logs2 / h2 mask), GEMM2 (w2t, logs1 / h1 mask), GEMM3 w1t
   return cnet::chain_launch(1, nullptr, d3col, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2, nullptr,
                             logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
+                                            void* d3col_save, int64_t ldd3, const void* w3t, int64_t ldw3t,
+                                            const void* w2t, int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t K3,
+                                            int64_t hidden, int64_t K1p, const float* logs2, float f2, const float* logs1,
+                                            float f1, const void* h2, const void* h1, void* d2, void* d1, int64_t ldh,
+                                            void* da1, int64_t ldda1, float* dbias2, float* dbias1, void* stream) {
+  const int64_t M = N * H * W;
+  if (M == 0) return GLOWK_OK;
+  GLOWK_CHECK_ARG(du && d3col_save && w3t && w2t && w1t && logs2 && logs1 && h2 && h1 && d2 && d1 && da1,
+                  "glowk_cnet_backward_implicit: null pointer");
+  GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_backward_implicit: hidden must be %d", cnet::HID);
+  GLOWK_CHECK_ARG(ldu >= Cout && ldd3 >= K3 && ldw3t >= K3 && ldw2t >= hidden && ldw1t >= hidden && ldh >= hidden && ldda1 >= K1p,
+                  "glowk_cnet_backward_implicit: leading dimensions too small");
+  cnet::Gather g{du, ldu, 0, Cout, H, W, -1, 1};
+  return cnet::chain_launch(1, &g, d3col_save, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2,
+                            nullptr, logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
 }

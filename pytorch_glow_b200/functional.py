@@ -269,6 +269,26 @@ def cnet_backward(d3col, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h
     return d2, d1, da1
 
 
+def cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h1, dbias2=None,
+                           dbias1=None):
+    """glowk_cnet_backward_implicit: the dgrad chain with its first operand (flipped im2col of du) gathered in-kernel.
+    Returns (d3col [M][k3p] bf16 -- the conv3 wgrad operand --, d2, d1 [M][ldh] bf16, da1 [M][k1p] bf16)."""
+    check_cuda(du, w3t, w2t, w1t, h2, h1)
+    assert du.dtype == torch.float32 and du.dim() == 2
+    m = n * h * w
+    assert du.shape[0] == m
+    ldh = h1.shape[1]
+    dev = du.device
+    d3col = torch.empty(m, k3p, device=dev, dtype=torch.bfloat16)
+    d2 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16)
+    d1 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16)
+    da1 = torch.empty(m, k1p, device=dev, dtype=torch.bfloat16)
+    call("glowk_cnet_backward_implicit", ptr(du), du.shape[1], cout, n, h, w, ptr(d3col), k3p, ptr(w3t), w3t.shape[1],
+         ptr(w2t), w2t.shape[1], ptr(w1t), w1t.shape[1], k3p, hidden, k1p, ptr(logs2), float(f2), ptr(logs1), float(f1),
+         ptr(h2), ptr(h1), ptr(d2), ptr(d1), ldh, ptr(da1), k1p, ptr(dbias2), ptr(dbias1))
+    return d3col, d2, d1, da1
+
+
 # ------------------------------------------------------------------ coupling / logdet / prior
 def coupling(p_rows, bias3, logs3, z, affine, reverse, logscale_factor=3.0, save_h=False):
     """In-place coupling on z[:, C/2:] from the tap-GEMM output p_rows.  model.py:105-115 / 131-140.

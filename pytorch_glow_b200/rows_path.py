@@ -430,8 +430,13 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
                                  _gbuf(c3.logs), _gbuf(c3.bias), c3.logscale_factor)
     # (2) conv3 (tap form): dP3 = flipped im2col of du
     k3p = round_up(9 * cout, 64)
-    d3col = K.im2col_rows(du, n, h, w, 0, cout, 3, dt, k3p, flip=True)
-    K.gemm_wgrad(d3col, h2, k3p, hid, plan.view(step, "w3"))
+    k1p = net.k1p
+    wide = _is_wide(c)
+    fused = dt == _C.BF16 and not wide and net.fused(True)
+    implicit = fused and cout % 2 == 0 and os.environ.get("GLOWK_CNET_IMPLICIT", "1") != "0"
+    if not implicit:
+        d3col = K.im2col_rows(du, n, h, w, 0, cout, 3, dt, k3p, flip=True)
+        K.gemm_wgrad(d3col, h2, k3p, hid, plan.view(step, "w3"))
     # bf16 (tcgen05) path: the ReLU-backward epilogue only reduces this pass's bias gradient into scratch; dlogs of
     # the two hidden ActNorms come from W, dW and db in GradPlan.finish (see glowk_conv_actnorm_finish_batched)
     defer = dt == _C.BF16
@@ -440,12 +445,15 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     ones = _ones_col(net, dt) if defer else -1        # a1 carries a ones column: dbias of an1 = that column of dW1
     if ones >= 0:
         db1 = None
-    k1p = net.k1p
-    wide = _is_wide(c)
-    fused = defer and not wide and net.fused(True)
-    if fused:
-        # dgrad3 -> ReLU' / ActNorm scale -> dgrad2 -> ReLU' / ActNorm scale -> dgrad1 in ONE kernel: d2 feeds dgrad2
-        # from tensor memory, d1 feeds dgrad1 from shared memory; both are stored once for the wgrad GEMMs
+    if implicit:
+        # dgrad3 -> ReLU' / ActNorm scale -> dgrad2 -> ReLU' / ActNorm scale -> dgrad1 in ONE kernel, dgrad3's operand
+        # (flipped im2col of du) gathered in-kernel; d3col / d2 / d1 are stored once for the wgrad GEMMs
+        d3col, d2, d1, da1 = K.cnet_backward_implicit(
+            du, n, h, w, cout, k3p, net.packed("w3t", dt), net.packed("w2t", dt), net.packed("w1t", dt), hid, k1p,
+            an2.logs.detach().reshape(-1), an2.logscale_factor, an1.logs.detach().reshape(-1), an1.logscale_factor,
+            h2, h1, dbias2=db2, dbias1=db1)
+        K.gemm_wgrad(d3col, h2, k3p, hid, plan.view(step, "w3"))
+    elif fused:
         d2, d1, da1 = K.cnet_backward(d3col, net.packed("w3t", dt), net.packed("w2t", dt), net.packed("w1t", dt), hid,
                                       k1p, an2.logs.detach().reshape(-1), an2.logscale_factor,
                                       an1.logs.detach().reshape(-1), an1.logscale_factor, h2, h1, dbias2=db2, dbias1=db1)

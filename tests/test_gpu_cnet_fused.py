@@ -134,3 +134,28 @@ def test_cnet_forward_implicit_matches_explicit_im2col(n, h, w, c, ones, save):
         assert torch.equal(a1, a1r) and torch.equal(h1, h1r) and torch.equal(h2, h2r)
     else:
         assert a1 is None and h1 is None and h2 is None
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 32, 32, 12), (3, 16, 16, 24), (1, 10, 6, 12)])
+def test_cnet_backward_implicit_matches_explicit_im2col(n, h, w, c):
+    """dgrad3's operand gathered in-kernel (flipped 3x3 im2col of du) == glowk_im2col_rows(flip=1) + the explicit chain."""
+    if not _C.has_tcgen05():
+        pytest.skip("needs sm_100")
+    cout, cin = c, c // 2
+    k3p, k1p = K.round_up(9 * cout, 64), K.round_up(9 * cin, 64)
+    if not K.cnet_fused_supported(True, k3p, HID, k1p):
+        pytest.skip("shape not served by the fused kernel")
+    m = n * h * w
+    g = torch.Generator().manual_seed(n * 77 + h)
+    du = (torch.randn(m, cout, generator=g) * 0.5).cuda()
+    _, w3t, w2t, w1t, h2, h1, l2, l1 = _mk_bwd(m, k3p, k1p, 5)
+    w3t[:, 9 * cout:] = 0
+    d3r = K.im2col_rows(du, n, h, w, 0, cout, 3, _C.BF16, k3p, flip=True)
+    db2r = torch.zeros(HID, device="cuda")
+    d2r, d1r, da1r = K.cnet_backward(d3r, w3t, w2t, w1t, HID, k1p, l2, 3.0, l1, 3.0, h2, h1, dbias2=db2r)
+    db2 = torch.zeros(HID, device="cuda")
+    d3, d2, d1, da1 = K.cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, HID, k1p, l2, 3.0, l1, 3.0, h2, h1,
+                                               dbias2=db2)
+    torch.cuda.synchronize()
+    assert torch.equal(d3, d3r) and torch.equal(d2, d2r) and torch.equal(d1, d1r) and torch.equal(da1, da1r)
+    assert torch.allclose(db2, db2r, rtol=1e-4, atol=1e-4)
