@@ -114,3 +114,44 @@ def test_inferer_batched_paths_match_per_sample_loops():
     one = inf.apply_attribute_delta(imgs[0], delta, [0.5, 0.0, -0.5])
     assert one.shape == (3, 16, 16)
     assert inf.sample(eps_std=0.7).shape == (4, 3, 16, 16)
+
+
+@pytest.mark.gpu
+def test_inferer_matches_reference_inferer_fixture():
+    """encode / decode / compute_attribute_delta (with the reference's len(batch) quirk) / apply_attribute_delta against
+    outputs of the reference's own Inferer (network/inferer.py:62-188), generated by tests/golden/make_golden_inferer.py
+    from the real reference on CPU.  L=1 model: decode is deterministic."""
+    import os
+    import pytorch_glow_b200 as G
+    from pytorch_glow_b200.hps import make_hps
+    from parity_util import adopt, GOLDEN
+    z = np.load(os.path.join(GOLDEN, "inferer.npz"))
+    dev = "cuda:0"
+    ncls, B = 5, 4
+    hps = make_hps((16, 16, 3), K=2, L=1, hidden_channels=16, coupling="affine", permutation="invconv", batch=B)
+    hps.dataset.num_classes = ncls
+    np.random.seed(0)
+    glow = G.Glow(hps)
+    adopt(glow, {k[3:]: torch.from_numpy(np.array(z[k])) for k in z.files if k.startswith("sd/")})
+    glow = glow.to(dev).eval()
+    glow.flow.set_conv_dtype("fp32")
+    inf = Inferer(hps, glow, devices=[dev], data_device=dev)
+    orig = torch.nn.init.uniform_
+    torch.nn.init.uniform_ = lambda t, a=0., b=1.: t.fill_((a + b) / 2)      # the fixture's deterministic dequantisation
+    try:
+        img = torch.from_numpy(z["img"])
+        zz = inf.encode(img)
+        assert float((zz.cpu() - torch.from_numpy(z["z"])).abs().max()) < 1e-4 * float(np.abs(z["z"]).max())
+        rec = inf.decode(torch.from_numpy(z["z"]))
+        assert float((rec.cpu() - torch.from_numpy(z["rec"])).abs().max()) < 1e-4 * max(1.0, float(np.abs(z["rec"]).max()))
+        batches = [{"x": torch.from_numpy(z["batch%d/x" % i]), "y_onehot": torch.from_numpy(z["batch%d/y_onehot" % i])}
+                   for i in range(3)]
+        delta = inf.compute_attribute_delta(batches, reference_quirk=True)
+        assert np.abs(delta - z["deltaz"]).max() < 1e-4 * max(1.0, np.abs(z["deltaz"]).max())
+        out = inf.apply_attribute_delta(img, z["deltaz"].astype(np.float32), z["alpha"])
+        assert float((out.cpu() - torch.from_numpy(z["interp"])).abs().max()) < 2e-4 * max(1.0, float(np.abs(z["interp"]).max()))
+        # the batched sweep gives the same image for the same interpolation vector
+        sweep = inf.interpolate_batch(img, z["deltaz"].astype(np.float32), np.stack([z["alpha"], 0 * z["alpha"]]))
+        assert float((sweep[0] - out).abs().max()) < 1e-5 * max(1.0, float(out.abs().max()))
+    finally:
+        torch.nn.init.uniform_ = orig
