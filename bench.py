@@ -326,7 +326,7 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
     w1 = (rnd(hidden, k1p) * 0.05).to(bf); w1[:, 9 * cin:] = 0
     w3 = (rnd(n3p, hidden) * 0.05).to(bf)
     w3t = (rnd(hidden, k3p) * 0.05).to(bf); w2t = (rnd(hidden, hidden) * 0.05).to(bf); w1t = (rnd(k1p, hidden) * 0.05).to(bf)
-    d3 = [(rnd(M, k3p) * 0.5).to(bf) for _ in range(2)]
+    dus = [rnd(M, C) * 0.5 for _ in range(2)]                        # gradient of Conv2dZeros' output (affine: C_out = C)
     fwd_flops = 2.0 * M * (9 * cin * hidden + hidden * hidden + hidden * 9 * C)
     bwd_flops = 2.0 * M * (k3p * hidden + hidden * hidden + hidden * k1p)
     fused = KF.cnet_fused_supported(False, k1p, hidden, n3p) and KF.cnet_fused_supported(True, k3p, hidden, k1p)
@@ -335,9 +335,10 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
     if fused:
         cases += [
             ("cnet_bwd", "cnet_chain_kernel<BWD>: dgrad3 -> ReLU'/ActNorm -> dgrad2 -> ReLU'/ActNorm -> dgrad1 fused (M=%d, "
-             "K3=%d, hidden=%d, K1p=%d); reads dP3 + the two saved activations (masks), writes d2, d1, dA1" % (M, k3p, hidden, k1p),
-             lambda i: KF.cnet_backward(d3[i % 2], w3t, w2t, w1t, hidden, k1p, logs, 3.0, logs, 3.0, hs[i], hs[(i + 1) % R], dbias2=dbias),
-             2.0 * M * (k3p + 4 * hidden + k1p), bwd_flops),
+             "K3=%d, hidden=%d, K1p=%d); reads du (in-kernel flipped im2col) + the two saved activations (masks), writes d3col, d2, d1, dA1" % (M, k3p, hidden, k1p),
+             lambda i: KF.cnet_backward_implicit(dus[i % 2], B, H, W, C, k3p, w3t, w2t, w1t, hidden, k1p, logs, 3.0, logs, 3.0,
+                                                 hs[i], hs[(i + 1) % R], dbias2=dbias),
+             4.0 * M * C + 2.0 * M * (k3p + 4 * hidden + k1p), bwd_flops),
             ("cnet_fwd_train", "cnet_chain_kernel<FWD>, training: implicit conv1 -> conv2 -> conv3 fused, a1 / h1 / h2 stored "
              "once for the backward pass (M=%d)" % M,
              lambda i: KF.cnet_forward_implicit(zs[i], B, H, W, 0, cin, k1p, w1, w2, w3, hidden, n3p, bias, logs, 3.0, bias, logs,
