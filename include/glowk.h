@@ -82,6 +82,11 @@ int glowk_invconv_prepare_batched(const float* w, int64_t batch, int64_t C, floa
 int glowk_invconv_lu_assemble(const float* p, const float* l, const float* u, const float* sign_s,
                               const float* log_s, int64_t C, float* w_out, float* winv_out,
                               float* logabsdet_out, void* stream);
+/* Gradient chain of that parameterisation (autograd of W = P Lf Uf): from dW ([C][C], the gradient wrt the assembled
+ * weight, logdet term included) accumulate dl += tril(P^T dW Uf^T, -1), du += triu(Lf^T P^T dW, 1),
+ * dlog_s += diag(Lf^T P^T dW) * sign_s * exp(log_s).  One small kernel per FlowStep. */
+int glowk_invconv_lu_grads(const float* dw, const float* p, const float* l, const float* u, const float* sign_s,
+                           const float* log_s, int64_t C, float* dl, float* du, float* dlog_s, void* stream);
 
 /* ---- Fused ActNorm + channel mix: model.py:94-103 (fwd) / 142-152 (rev) ------------------
  * fwd: z[n,o,p] = sum_i W[o,i] * ((x[n,i,p] + bias[i]) * exp(f*logs[i]))          (mix)
@@ -286,6 +291,10 @@ int glowk_optim_clip_norm(float* grads, int64_t n, float clip_value, float max_n
 int glowk_optim_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                      const float* norm_coef, const float* sched_dev, float lr, float beta1, float beta2,
                      float eps, int64_t step, void* stream);
+/* torch.optim.Adamax (network/builder.py:10-13, the reference's `optimizer: "adamax"` choice) over the same arenas:
+ * grads *= norm_coef[1]; m = beta1*m + (1-beta1)*g; u = max(beta2*u, |g| + eps); p -= lr/(1-beta1^step) * m/u. */
+int glowk_optim_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n, const float* norm_coef,
+                       const float* sched_dev, float lr, float beta1, float beta2, float eps, int64_t step, void* stream);
 /* Fills sched_dev = [noam_lr(step), 1-beta1^(step+1), sqrt(1-beta2^(step+1))] from the DEVICE counter *step_dev
  * (int64, completed iterations) and increments it: misc/lr_scheduler.py:18-37 (noam_decay; warmup_steps = 0 gives
  * the constant base_lr, min_lr < 0 = none) + the bias corrections of torch.optim.Adam, inside a captured graph. */

@@ -30,6 +30,7 @@ SIGNATURES = {
     "glowk_invconv_prepare": [_p, _i64, _p, _p, _p],
     "glowk_invconv_prepare_batched": [_p, _i64, _i64, _p, _p, _p],
     "glowk_invconv_lu_assemble": [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
+    "glowk_invconv_lu_grads": [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     "glowk_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i64, _i32, _p],
     "glowk_squeeze2d": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_im2col": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p],
@@ -67,6 +68,7 @@ SIGNATURES = {
     "glowk_optim_workspace_floats": [],
     "glowk_optim_clip_norm": [_p, _i64, _f32, _f32, _p, _p],
     "glowk_optim_adam": [_p, _p, _p, _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _i64, _p],
+    "glowk_optim_adamax": [_p, _p, _p, _p, _i64, _p, _p, _f32, _f32, _f32, _f32, _i64, _p],
     "glowk_optim_schedule": [_p, _p, _f32, _i64, _f32, _f32, _f32, _p],
     "glowk_rows_max_channels": [],
     "glowk_rows_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i32, _p],

@@ -374,6 +374,27 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ g, float*
   }
 }
 
+// torch.optim.Adamax (the reference's other optimizer choice, network/builder.py:10-13):
+//   m = beta1*m + (1-beta1)*g;  u = max(beta2*u, |g| + eps);  p -= lr/(1-beta1^t) * m/u
+__global__ void adamax_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                              float* __restrict__ u, int64_t n, const float* __restrict__ norm_coef,
+                              const float* __restrict__ sched, float lr_scalar, float beta1, float beta2, float eps,
+                              float bc1_h) {
+  const float coef = norm_coef ? norm_coef[1] : 1.f;
+  const float lr = sched ? sched[0] : lr_scalar;
+  const float bc1 = sched ? sched[1] : bc1_h;
+  const float clr = lr / bc1;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * coef;
+    g[i] = gi;
+    const float mi = m[i] * beta1 + (1.f - beta1) * gi;
+    const float ui = fmaxf(u[i] * beta2, fabsf(gi) + eps);
+    m[i] = mi; u[i] = ui;
+    p[i] = p[i] - clr * (mi / ui);
+  }
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -486,6 +507,20 @@ extern "C" int glowk_optim_adam(float* params, float* grads, float* exp_avg, flo
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, norm_coef, sched_dev, lr,
                                                         beta1, beta2, eps, (float)bc1, (float)sqrt(bc2));
   GLOWK_CHECK_LAUNCH("glowk_optim_adam");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_optim_adamax(float* params, float* grads, float* exp_avg, float* exp_inf, int64_t n,
+                                  const float* norm_coef, const float* sched_dev, float lr, float beta1, float beta2,
+                                  float eps, int64_t step, void* stream) {
+  GLOWK_CHECK_ARG(params && grads && exp_avg && exp_inf && n > 0 && step >= 1, "glowk_optim_adamax: bad arguments");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  int blocks = (int)ceil_div(n, 256 * 4);
+  const int cap = 8 * sm_count();
+  if (blocks > cap) blocks = cap;
+  adamax_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_inf, n, norm_coef, sched_dev, lr,
+                                                          beta1, beta2, eps, (float)bc1);
+  GLOWK_CHECK_LAUNCH("glowk_optim_adamax");
   return GLOWK_OK;
 }
 

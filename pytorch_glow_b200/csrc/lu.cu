@@ -303,6 +303,48 @@ __global__ void lu_assemble_kernel(const float* __restrict__ p, const float* __r
   }
 }
 
+
+// Chain rule of the LU parameterisation W = P Lf Uf (Lf = tril(l,-1) + I, Uf = triu(u,1) + diag(sign_s e^{log_s})):
+// with G = P^T dW,  dLf = G Uf^T,  dUf = Lf^T G:
+//   dl += tril(dLf, -1);  du += triu(dUf, 1);  dlog_s += diag(dUf) * sign_s e^{log_s}.
+// One CTA; P^T dW is a row gather (row r of G = row i of dW with P[i][r] = 1).  Replaces five cuBLAS matmuls +
+// torch.eye / tril / triu per FlowStep and backward pass on the LU path.
+__global__ void lu_grads_kernel(const float* __restrict__ dw, const float* __restrict__ p, const float* __restrict__ l,
+                                const float* __restrict__ u, const float* __restrict__ sign_s,
+                                const float* __restrict__ log_s, int C, float* __restrict__ dl, float* __restrict__ du,
+                                float* __restrict__ dlog_s, int* __restrict__ rowsrc) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  // rowsrc[r] = i with P[i][r] = 1  (G[r][:] = dW[i][:])
+  for (int r = tid; r < C; r += nthr) {
+    int src = 0;
+    for (int i = 0; i < C; ++i) if (p[i * C + r] != 0.f) src = i;
+    rowsrc[r] = src;
+  }
+  __syncthreads();
+  for (int e = tid; e < C * C; e += nthr) {
+    const int i = e / C, j = e - i * C;
+    if (i > j) {
+      // dLf[i][j] = sum_k G[i][k] Uf[j][k]   (Uf[j][k] != 0 for k >= j)
+      const float* g = dw + (size_t)rowsrc[i] * C;
+      double s = 0.0;
+      for (int k = j; k < C; ++k) {
+        const double uv = (k == j) ? (double)sign_s[j] * exp((double)log_s[j]) : (double)u[j * C + k];
+        s += (double)g[k] * uv;
+      }
+      dl[e] += (float)s;
+    } else {
+      // dUf[i][j] = sum_k Lf[k][i] G[k][j]   (Lf[k][i] != 0 for k >= i)
+      double s = 0.0;
+      for (int k = i; k < C; ++k) {
+        const double lv = (k == i) ? 1.0 : (double)l[k * C + i];
+        s += lv * (double)dw[(size_t)rowsrc[k] * C + j];
+      }
+      if (i < j) du[e] += (float)s;
+      else dlog_s[i] += (float)(s * (double)sign_s[i] * exp((double)log_s[i]));
+    }
+  }
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -373,5 +415,21 @@ extern "C" int glowk_invconv_lu_assemble(const float* p, const float* l, const f
   cudaError_t e = cudaGetLastError();
   if (X) cudaFreeAsync(X, st);
   if (e != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_invconv_lu_assemble: %s", cudaGetErrorString(e));
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_invconv_lu_grads(const float* dw, const float* p, const float* l, const float* u,
+                                      const float* sign_s, const float* log_s, int64_t C, float* dl, float* du,
+                                      float* dlog_s, void* stream) {
+  GLOWK_CHECK_ARG(dw && p && l && u && sign_s && log_s && dl && du && dlog_s, "glowk_invconv_lu_grads: null pointer");
+  GLOWK_CHECK_ARG(C > 0 && C <= 1024, "glowk_invconv_lu_grads: C out of range");
+  cudaStream_t st = (cudaStream_t)stream;
+  int* rowsrc = nullptr;
+  GLOWK_CUDA(cudaMallocAsync((void**)&rowsrc, (size_t)C * sizeof(int), st));
+  const int threads = C <= 16 ? 64 : (C <= 48 ? 256 : 1024);
+  lu_grads_kernel<<<1, threads, 0, st>>>(dw, p, l, u, sign_s, log_s, (int)C, dl, du, dlog_s, rowsrc);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(rowsrc, st);
+  if (e != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_invconv_lu_grads: %s", cudaGetErrorString(e));
   return GLOWK_OK;
 }

@@ -210,6 +210,13 @@ def gemm_wgrad(a, b, mo, no, dw):
     return dw
 
 
+def invconv_lu_grads(dw, p, l, u, sign_s, log_s, dl, du, dlog_s):
+    """Accumulate the gradients of the LU parameters from dW (glowk_invconv_lu_grads)."""
+    check_cuda(dw, p, l, u, sign_s, log_s, dl, du, dlog_s)
+    call("glowk_invconv_lu_grads", ptr(dw), ptr(p), ptr(l), ptr(u), ptr(sign_s), ptr(log_s), l.shape[0], ptr(dl), ptr(du),
+         ptr(dlog_s))
+
+
 def cnet_fused_supported(backward, k1, hidden, n3):
     """True iff glowk_cnet_forward / glowk_cnet_backward serve this shape on the current device."""
     return bool(_C.lib().glowk_cnet_fused_supported(int(bool(backward)), int(k1), int(hidden), int(n3)))
@@ -409,6 +416,11 @@ def optim_clip_norm(grads, clip_value, max_norm, workspace):
 
 def optim_adam(params, grads, exp_avg, exp_avg_sq, workspace, step, lr, beta1, beta2, eps, sched=None):
     call("glowk_optim_adam", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), params.numel(), ptr(workspace),
+         ptr(sched), float(lr), float(beta1), float(beta2), float(eps), int(step))
+
+
+def optim_adamax(params, grads, exp_avg, exp_inf, workspace, step, lr, beta1, beta2, eps, sched=None):
+    call("glowk_optim_adamax", ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_inf), params.numel(), ptr(workspace),
          ptr(sched), float(lr), float(beta1), float(beta2), float(eps), int(step))
 
 

@@ -484,21 +484,12 @@ class Invertible1x1Conv(nn.Module):
         return self.prepared(False)[0]
 
     def accumulate_lu_grads(self, dw):
-        """Chain dL/dW (CxC, includes the logdet term) into the LU parameters: W = P Lf Uf."""
-        with torch.no_grad():
-            c = self.num_channels
-            eye = torch.eye(c, device=dw.device)
-            lf = torch.tril(self.l, -1) + eye
-            s = self.sign_s * torch.exp(self.log_s)
-            uf = torch.triu(self.u, 1) + torch.diag(s)
-            ptdw = self.p.t() @ dw
-            dlf = ptdw @ uf.t()
-            duf = lf.t() @ ptdw
-            for prm, g in ((self.l, torch.tril(dlf, -1)), (self.u, torch.triu(duf, 1)),
-                           (self.log_s, torch.diagonal(duf) * s)):
-                if prm.grad is None:
-                    prm.grad = torch.zeros_like(prm)
-                prm.grad.add_(g)
+        """Chain dL/dW (CxC, includes the logdet term) into the LU parameters: W = P Lf Uf (one kernel)."""
+        for prm in (self.l, self.u, self.log_s):
+            if prm.grad is None:
+                prm.grad = torch.zeros_like(prm)
+        K.invconv_lu_grads(dw.contiguous(), self.p, self.l.detach(), self.u.detach(), self.sign_s, self.log_s.detach(),
+                           self.l.grad, self.u.grad, self.log_s.grad)
 
     def forward(self, x, logdet=None, reverse=False):
         _C.check_cuda(x)

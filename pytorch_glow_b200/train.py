@@ -129,8 +129,12 @@ class FusedTrainStep:
     """
 
     def __init__(self, glow, lr=1e-3, betas=(0.9, 0.9999), eps=1e-8, max_grad_clip=5.0, max_grad_norm=100.0,
-                 warmup_steps=4000, min_lr=1e-4, use_graphs=False, process_group=None, world_size=1, overlap=None):
+                 warmup_steps=4000, min_lr=1e-4, use_graphs=False, process_group=None, world_size=1, overlap=None,
+                 optimizer="adam"):
         self.glow = glow
+        if optimizer not in ("adam", "adamax"):            # network/builder.py:10-13
+            raise ValueError("optimizer must be 'adam' or 'adamax'")
+        self.optimizer = optimizer
         self.base_lr, self.betas, self.eps = lr, betas, eps
         self.max_grad_clip, self.max_grad_norm = max_grad_clip, max_grad_norm
         self.warmup_steps, self.min_lr = warmup_steps, min_lr
@@ -193,12 +197,13 @@ class FusedTrainStep:
         """Adam state in torch.optim.Adam's layout, parameter indices in `glow.parameters()` order."""
         index = {id(p): i for i, p in enumerate(self.glow.parameters())}
         state = {}
+        second = "exp_avg_sq" if self.optimizer == "adam" else "exp_inf"      # torch.optim.Adamax' key
         step_t = float(self.global_step)
         for p, o in zip(self.arena.params, self.arena.offsets):
             n = p.numel()
             state[index[id(p)]] = {"step": torch.tensor(step_t),
                                    "exp_avg": self.exp_avg[o:o + n].view(p.shape).clone(),
-                                   "exp_avg_sq": self.exp_avg_sq[o:o + n].view(p.shape).clone()}
+                                   second: self.exp_avg_sq[o:o + n].view(p.shape).clone()}
         group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": 0, "amsgrad": False,
                  "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
                  "decoupled_weight_decay": False, "params": list(range(len(index)))}
@@ -219,7 +224,7 @@ class FusedTrainStep:
                 self.exp_avg[o:o + n].zero_(); self.exp_avg_sq[o:o + n].zero_()
                 continue
             self.exp_avg[o:o + n].copy_(e["exp_avg"].reshape(-1))
-            self.exp_avg_sq[o:o + n].copy_(e["exp_avg_sq"].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(e["exp_avg_sq" if "exp_avg_sq" in e else "exp_inf"].reshape(-1))
             steps.append(int(float(e["step"])))
         if steps:
             self.set_global_step(max(steps))
@@ -268,8 +273,9 @@ class FusedTrainStep:
         K.optim_schedule(self.step_dev, self.sched_dev, self.base_lr, self.warmup_steps, self.min_lr, self.betas[0],
                          self.betas[1])
         K.optim_clip_norm(self.arena.grad, self.max_grad_clip, self.max_grad_norm, self.ws)
-        K.optim_adam(self.arena.flat, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.ws, self.global_step + 1,
-                     0.0, self.betas[0], self.betas[1], self.eps, sched=self.sched_dev)
+        step_fn = K.optim_adam if self.optimizer == "adam" else K.optim_adamax     # exp_avg_sq doubles as Adamax' exp_inf
+        step_fn(self.arena.flat, self.arena.grad, self.exp_avg, self.exp_avg_sq, self.ws, self.global_step + 1,
+                0.0, self.betas[0], self.betas[1], self.eps, sched=self.sched_dev)
 
     def _allreduce(self):
         if self.world_size > 1 and not self.overlap:

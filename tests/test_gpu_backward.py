@@ -219,6 +219,38 @@ def test_fused_optimizer_matches_torch():
         assert_close(flat, ref.data, 1e-5, 1e-6, "params after step %d" % t)
 
 
+def test_fused_adamax_and_device_schedule_match_torch():
+    """glowk_optim_adamax against torch.optim.Adamax (the reference's other optimizer, network/builder.py:10-13) with
+    the reference's two clipping calls, and glowk_optim_schedule (device-side Noam LR + bias corrections,
+    misc/lr_scheduler.py:18-37) against the host formulas."""
+    torch.manual_seed(1)
+    n = 50001
+    p0 = torch.randn(n)
+    grads = [torch.randn(n) * s for s in (10.0, 0.5, 3.0)]
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adamax([ref], lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    flat, m, u = cu(p0.clone()), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    ws = K.optim_workspace(DEV)
+    step_dev = torch.zeros(1, dtype=torch.int64, device=DEV)
+    sched = torch.zeros(4, device=DEV)
+    for t, g in enumerate(grads):
+        lr = noam_lr(2e-3, t, 4000, 1e-4)
+        ref.grad = g.clone()
+        torch.nn.utils.clip_grad_value_([ref], 5)
+        torch.nn.utils.clip_grad_norm_([ref], 100)
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        opt.step()
+        K.optim_schedule(step_dev, sched, 2e-3, 4000, 1e-4, 0.9, 0.999)
+        assert int(step_dev) == t + 1
+        assert abs(float(sched[0]) - lr) <= 1e-6 * lr
+        assert abs(float(sched[1]) - (1 - 0.9 ** (t + 1))) < 1e-6 and abs(float(sched[2]) - (1 - 0.999 ** (t + 1)) ** 0.5) < 1e-6
+        gg = cu(g.clone())
+        K.optim_clip_norm(gg, 5.0, 100.0, ws)
+        K.optim_adamax(flat, gg, m, u, ws, t + 1, 0.0, 0.9, 0.999, 1e-8, sched=sched)
+        assert_close(flat, ref.data, 1e-5, 1e-6, "Adamax params after step %d" % t)
+
+
 @pytest.mark.parametrize("use_graphs", [False, True])
 def test_train_steps_follow_oracle(golden_glow, use_graphs):
     """Three full iterations (fwd + bwd + clip + Adam, Noam LR) vs the same iterations through the oracle."""
