@@ -243,6 +243,19 @@ int glowk_logdet_finish(const float* logdet_in, float* logdet_out, const float* 
  * h == null => mean = logs = 0 over all C channels of x (the Glow top prior, model.py:435-438). */
 int glowk_gaussian_logp(const float* h, int64_t ldh, const float* x, int64_t N, int64_t C, int64_t HW,
                         int64_t c0, int64_t Cz, const float* logdet_in, float* logdet_out, void* stream);
+/* Loss head (network/model.py:425-427, 435-450, 496-498; plain N(0, I) top prior): z [N][D] is the top latent, ld [N]
+ * the flow's accumulated logdet started from ZERO (null = 0); per sample
+ *   objective = ld[n] + c0 + sum log N(z[n]; 0, I)     (c0 = -log(n_bins) * D_x: the objective's initial value)
+ *   nll[n]    = -objective / denom                     (denom = ln 2 * D_x: bits per dimension)
+ * and, if loss != null, loss[0] = mean_n nll[n] (Glow.generative_loss), summed in index order by the last CTA;
+ * ticket: one zero-initialised uint32 that the kernel leaves at zero. */
+int glowk_nll_head(const float* z, const float* ld, float c0, float denom, int64_t N, int64_t D, float* nll,
+                   float* loss, void* ticket, void* stream);
+/* Adjoint of glowk_nll_head.  g_loss = dL/dloss (device scalar), g_nll = dL/dnll [N], dz_in = dL/dz [N][D]; each may be
+ * null (both g's null: the loss gradient is 1).  coef_n = (g_loss / N + g_nll[n]) / denom;
+ * dz = dz_in + z * coef_n, dld[n] = -coef_n (the gradient of the flow's logdet output). */
+int glowk_nll_head_bwd(const float* z, const float* g_loss, const float* g_nll, const float* dz_in, float denom,
+                       int64_t N, int64_t D, float* dz, float* dld, void* stream);
 /* Reverse: out[:, :C/2] = z1, out[:, C/2:] = mean + exp(logs) * eps   (eps already scaled by eps_std). */
 int glowk_split2d_sample(const float* h, int64_t ldh, const float* z1, const float* eps, float* out,
                          int64_t N, int64_t Chalf, int64_t HW, void* stream);
@@ -390,6 +403,11 @@ int glowk_rows_tapsum(const float* P, int64_t ldp, float* dst, int64_t ld_dst, i
  * pure layout change. */
 int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* dst, int dst_layout, int64_t dst_ld,
                        int64_t N, int64_t C, int64_t H, int64_t W, int factor, int reverse, void* stream);
+/* The entry squeeze of Glow.normal_flow with the dequantisation folded in (network/model.py:419-423 + the first
+ * Squeeze2d): dst = squeeze(src + add); `add` is the U(0, 1/n_bins) noise, laid out like src. */
+int glowk_rows_squeeze_add(const float* src, const float* add, int src_layout, int64_t src_ld, float* dst,
+                           int dst_layout, int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W, int factor,
+                           void* stream);
 
 /* One launch for many glowk_pack_conv_weight / glowk_unpack_weight_grad calls.  jobs: device array of
  *   struct { const float* w; void* packed; int32 O, I, ks, layout, rows, ld; int64 block0; }   (48 bytes)

@@ -87,6 +87,9 @@ SIGNATURES = {
     "glowk_rows_split2d_sample": [_p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _p],
     "glowk_rows_split2d_bwd": [_p, _p, _i64, _p, _p, _f32, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _p],
     "glowk_rows_tapsum": [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
+    "glowk_rows_squeeze_add": [_p, _p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _p],
+    "glowk_nll_head": [_p, _p, _f32, _f32, _i64, _i64, _p, _p, _p, _p],
+    "glowk_nll_head_bwd": [_p, _p, _p, _p, _f32, _i64, _i64, _p, _p, _p],
     "glowk_rows_squeeze": [_p, _i32, _i64, _p, _i32, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_pack_conv_weights_batched": [_p, _i64, _i64, _i32, _p],
     "glowk_unpack_weight_grads_batched": [_p, _i64, _i64, _p],

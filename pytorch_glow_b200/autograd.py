@@ -250,6 +250,44 @@ class TopPriorFunction(torch.autograd.Function):
         return -z * g.view(-1, 1, 1, 1), g
 
 
+class GlowNLLFunction(torch.autograd.Function):
+    """Glow.normal_flow + Glow.generative_loss with the plain N(0, I) top prior as ONE autograd node
+    (network/model.py:409-452, 496-498): dequantisation add inside the entry squeeze, the flow on the pixel-major
+    kernels with its logdet started at zero, and the loss head (objective start value, top prior, bits/dim scaling,
+    batch mean) in one kernel.  Returns (z, nll [N], loss); parameter gradients are accumulated into .grad."""
+
+    @staticmethod
+    def forward(ctx, flow, n_bins, x, noise, *params):
+        from . import rows_path
+        import math
+        x = x.detach().contiguous()
+        d_x = x[0].numel()
+        tape = []
+        z, ld = rows_path.encode(flow, x, None, tape, add=None if noise is None else noise.detach().contiguous(),
+                                 want_ld=True)
+        ctx.denom = math.log(2.) * d_x
+        nll, loss = K.nll_head(z, ld, -math.log(n_bins) * d_x, ctx.denom)
+        ctx.flow, ctx.tape, ctx.z = flow, tape, z
+        ctx.set_materialize_grads(False)
+        return z, nll, loss
+
+    @staticmethod
+    def backward(ctx, dz, dnll, dloss):
+        from . import rows_path
+        if dz is None and dnll is None and dloss is None:
+            return (None,) * len(ctx.needs_input_grad)
+        f = lambda t: None if t is None else t.contiguous().float()
+        dz_top, dld = K.nll_head_bwd(ctx.z, ctx.denom, g_loss=f(dloss), g_nll=f(dnll), dz_in=f(dz))
+        if dloss is None and dnll is None:
+            dld.zero_()                                     # only z took part in the loss
+            dz_top = f(dz)
+        dx = rows_path.backward(ctx.flow, ctx.tape, dz_top, dld)
+        ctx.tape = None
+        # the dequantised input is x + noise: both receive the same gradient
+        return (None, None, dx if ctx.needs_input_grad[2] else None, dx if ctx.needs_input_grad[3] else None) + \
+            (None,) * (len(ctx.needs_input_grad) - 4)
+
+
 # ------------------------------------------------------------------ stand-alone layer nodes
 class _StepFunction(torch.autograd.Function):
     @staticmethod

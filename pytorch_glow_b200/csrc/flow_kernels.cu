@@ -622,6 +622,61 @@ __global__ void split2d_sample_kernel(const float* __restrict__ h, int64_t ldh, 
   out[e] = v;
 }
 
+
+// Loss head of Glow.normal_flow + Glow.generative_loss (network/model.py:425-427, 435-450, 496-498) with the plain
+// N(0, I) top prior: per sample  objective = ld[n] + c0 + sum log N(z[n]; 0, I)  (c0 = -log(n_bins) * D_x),
+// nll[n] = -objective / denom  (denom = ln2 * D_x), and loss = mean_n nll[n], summed in index order by the last CTA
+// to finish (the ticket resets itself).  Summation order of the prior term is that of gaussian_logp_kernel.
+__global__ void nll_head_kernel(const float* __restrict__ z, int64_t D, const float* __restrict__ ld, float c0,
+                                float denom, int N, float* __restrict__ nll, float* __restrict__ loss,
+                                unsigned* __restrict__ ticket) {
+  __shared__ float red[32];
+  __shared__ bool s_last;
+  const int64_t n = blockIdx.x;
+  const float log2pi = 1.8378770664093453f;
+  float acc = 0.f;
+  for (int64_t e = threadIdx.x; e < D; e += blockDim.x) {
+    const float v = z[n * D + e];
+    acc += -0.5f * (log2pi + v * v);
+  }
+  const float tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    const float objective = tot + (ld ? ld[n] : 0.f) + c0;
+    nll[n] = (-objective) / denom;
+    s_last = false;
+    if (loss) {
+      __threadfence();
+      s_last = atomicAdd(ticket, 1u) == (unsigned)(N - 1);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float part = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) part += __ldcg(nll + i);
+  const float sum = block_sum(part, red);
+  if (threadIdx.x == 0) { loss[0] = sum / (float)N; *ticket = 0u; }
+}
+
+// Its adjoint.  g_loss = dL/dloss (device scalar), g_nll = dL/dnll [N], dz_in = dL/dz [N][D] -- each may be null; with
+// both g's null the loss gradient is 1.  coef_n = (g_loss / N + g_nll[n]) / denom:
+//   dz = dz_in + z * coef_n,   dld[n] = -coef_n.
+__global__ void nll_head_bwd_kernel(const float* __restrict__ z, const float* __restrict__ g_loss,
+                                    const float* __restrict__ g_nll, const float* __restrict__ dz_in, float denom,
+                                    int N, int64_t D, float* __restrict__ dz, float* __restrict__ dld) {
+  const int n = blockIdx.y;
+  float g = (g_loss ? g_loss[0] : (g_nll ? 0.f : 1.f)) / (float)N;
+  if (g_nll) g += g_nll[n];
+  const float coef = g / denom;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < D) {
+    const int64_t i = (int64_t)n * D + e;
+    const float v = z[i] * coef;
+    dz[i] = dz_in ? dz_in[i] + v : v;
+  }
+  if (e == 0) dld[n] = -coef;
+}
+
 }  // namespace glowk
 
 using namespace glowk;
@@ -886,5 +941,26 @@ extern "C" int glowk_split2d_sample(const float* h, int64_t ldh, const float* z1
   if (total == 0) return GLOWK_OK;
   split2d_sample_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(h, ldh, z1, eps, out, total, Chalf, HW);
   GLOWK_CHECK_LAUNCH("glowk_split2d_sample");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_nll_head(const float* z, const float* ld, float c0, float denom, int64_t N, int64_t D, float* nll,
+                              float* loss, void* ticket, void* stream) {
+  GLOWK_CHECK_ARG(z && nll && (!loss || ticket), "glowk_nll_head: null pointer");
+  GLOWK_CHECK_ARG(denom > 0.f && N < (1ll << 31), "glowk_nll_head: bad arguments");
+  if (N == 0) return GLOWK_OK;
+  nll_head_kernel<<<(unsigned)N, 256, 0, (cudaStream_t)stream>>>(z, D, ld, c0, denom, (int)N, nll, loss, (unsigned*)ticket);
+  GLOWK_CHECK_LAUNCH("glowk_nll_head");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_nll_head_bwd(const float* z, const float* g_loss, const float* g_nll, const float* dz_in,
+                                  float denom, int64_t N, int64_t D, float* dz, float* dld, void* stream) {
+  GLOWK_CHECK_ARG(z && dz && dld, "glowk_nll_head_bwd: null pointer");
+  GLOWK_CHECK_ARG(denom > 0.f && N <= 65535 && D > 0, "glowk_nll_head_bwd: bad arguments");
+  if (N == 0) return GLOWK_OK;
+  const dim3 grid((unsigned)ceil_div(D, 256), (unsigned)N);
+  nll_head_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z, g_loss, g_nll, dz_in, denom, (int)N, D, dz, dld);
+  GLOWK_CHECK_LAUNCH("glowk_nll_head_bwd");
   return GLOWK_OK;
 }

@@ -1248,7 +1248,7 @@ __device__ __forceinline__ int64_t layout_off(int layout, int64_t ld, int64_t n,
 
 __global__ void rows_squeeze_kernel(const float* __restrict__ src, int src_layout, int64_t src_ld,
                                     float* __restrict__ dst, int dst_layout, int64_t dst_ld, int total,
-                                    int C, int H, int W, int f, int reverse) {
+                                    int C, int H, int W, int f, int reverse, const float* __restrict__ add) {
   pdl_wait();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
@@ -1272,7 +1272,7 @@ __global__ void rows_squeeze_kernel(const float* __restrict__ src, int src_layou
     so = layout_off(src_layout, src_ld, n, c * f * f + fh * f + fw, i, jx, Cs, Hs, Ws);
     dofs = layout_off(dst_layout, dst_ld, n, c, y, x, C, H, W);
   }
-  dst[dofs] = src[so];
+  dst[dofs] = add ? src[so] + add[so] : src[so];      // add: the dequantisation noise (network/model.py:421-423)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1825,9 +1825,10 @@ extern "C" int glowk_rows_split2d_bwd(const float* x, const float* hrows, int64_
   return GLOWK_OK;
 }
 
-extern "C" int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* dst, int dst_layout,
-                                  int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W, int factor, int reverse,
-                                  void* stream) {
+static int rows_squeeze_launch(const char* who, const float* src, const float* add, int src_layout, int64_t src_ld,
+                               float* dst, int dst_layout, int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W,
+                               int factor, int reverse, void* stream) {
+  (void)who;
   if (N == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(src && dst && src != dst, "glowk_rows_squeeze: bad pointers");
   GLOWK_CHECK_ARG(factor >= 1 && H % factor == 0 && W % factor == 0, "glowk_rows_squeeze: H,W not divisible by factor");   // module.py:588
@@ -1839,9 +1840,24 @@ extern "C" int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_
   if (total == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(total < (1ll << 31), "glowk_rows_squeeze: tensor too large for 32-bit indexing");
   rows_squeeze_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      src, src_layout, src_ld, dst, dst_layout, dst_ld, (int)total, (int)C, (int)H, (int)W, factor, reverse);
+      src, src_layout, src_ld, dst, dst_layout, dst_ld, (int)total, (int)C, (int)H, (int)W, factor, reverse, add);
   GLOWK_CHECK_LAUNCH("glowk_rows_squeeze");
   return GLOWK_OK;
+}
+
+extern "C" int glowk_rows_squeeze(const float* src, int src_layout, int64_t src_ld, float* dst, int dst_layout,
+                                  int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W, int factor, int reverse,
+                                  void* stream) {
+  return rows_squeeze_launch("glowk_rows_squeeze", src, nullptr, src_layout, src_ld, dst, dst_layout, dst_ld, N, C, H, W,
+                             factor, reverse, stream);
+}
+
+extern "C" int glowk_rows_squeeze_add(const float* src, const float* add, int src_layout, int64_t src_ld, float* dst,
+                                      int dst_layout, int64_t dst_ld, int64_t N, int64_t C, int64_t H, int64_t W,
+                                      int factor, void* stream) {
+  GLOWK_CHECK_ARG(add, "glowk_rows_squeeze_add: null pointer");
+  return rows_squeeze_launch("glowk_rows_squeeze_add", src, add, src_layout, src_ld, dst, dst_layout, dst_ld, N, C, H, W,
+                             factor, 0, stream);
 }
 
 extern "C" int glowk_pack_conv_weights_batched(const void* jobs, int64_t njobs, int64_t total_blocks, int act_dtype,

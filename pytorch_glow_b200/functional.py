@@ -337,6 +337,40 @@ def gaussian_logp(h_rows, x, c0, cz, logdet_in=None):
     return out
 
 
+_tickets = {}
+
+
+def _ticket(device):
+    t = _tickets.get(device)
+    if t is None:
+        t = _tickets[device] = torch.zeros(4, device=device, dtype=torch.int32)
+    return t
+
+
+def nll_head(z, ld, c0, denom, want_loss=True):
+    """Glow's loss head (model.py:425-450, 496-498; N(0, I) top prior): z [N, ...] top latent, ld [N] the flow's
+    logdet started from zero -> (nll [N] in bits/dim, mean loss as a 0-dim tensor or None)."""
+    check_cuda(z, ld)
+    assert z.dtype == torch.float32 and z.is_contiguous()
+    n = z.shape[0]
+    nll = torch.empty(n, device=z.device, dtype=torch.float32)
+    loss = torch.empty((), device=z.device, dtype=torch.float32) if want_loss else None
+    call("glowk_nll_head", ptr(z), ptr(ld), float(c0), float(denom), n, z[0].numel() if n else 0, ptr(nll), ptr(loss),
+         ptr(_ticket(z.device)) if want_loss else 0)
+    return nll, loss
+
+
+def nll_head_bwd(z, denom, g_loss=None, g_nll=None, dz_in=None):
+    """Adjoint of nll_head -> (dz, dld)."""
+    check_cuda(z, g_loss, g_nll, dz_in)
+    n = z.shape[0]
+    dz = torch.empty_like(z)
+    dld = torch.empty(n, device=z.device, dtype=torch.float32)
+    call("glowk_nll_head_bwd", ptr(z), ptr(g_loss), ptr(g_nll), ptr(dz_in), float(denom), n, z[0].numel() if n else 0,
+         ptr(dz), ptr(dld))
+    return dz, dld
+
+
 def split2d_sample(h_rows, z1, eps):
     """cat(z1, mean + exp(logs)*eps).  network/module.py:482-483, 532-536."""
     check_cuda(h_rows, z1, eps)
@@ -452,9 +486,15 @@ def rows_actnorm_bwd(da, x, bias, logs, dlogs, dbias, logscale_factor=3.0, out=N
     return out
 
 
-def rows_squeeze(src, src_layout, src_ld, dst, dst_layout, dst_ld, n, c, h, w, factor, reverse):
-    """Squeeze2d / unsqueeze between layouts (module.py:551-591); see glowk_rows_squeeze."""
-    check_cuda(src, dst)
+def rows_squeeze(src, src_layout, src_ld, dst, dst_layout, dst_ld, n, c, h, w, factor, reverse, add=None):
+    """Squeeze2d / unsqueeze between layouts (module.py:551-591); see glowk_rows_squeeze.
+    add: tensor laid out like src, added on the fly (the dequantisation noise, model.py:421-423; forward only)."""
+    check_cuda(src, dst, add)
+    if add is not None:
+        assert not reverse and add.shape == src.shape and add.dtype == torch.float32 and add.is_contiguous()
+        call("glowk_rows_squeeze_add", src.data_ptr(), add.data_ptr(), int(src_layout), int(src_ld), dst.data_ptr(),
+             int(dst_layout), int(dst_ld), n, c, h, w, int(factor))
+        return dst
     call("glowk_rows_squeeze", src.data_ptr(), int(src_layout), int(src_ld), dst.data_ptr(), int(dst_layout),
          int(dst_ld), n, c, h, w, int(factor), int(bool(reverse)))
     return dst

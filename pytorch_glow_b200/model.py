@@ -5,6 +5,8 @@
 arguments, call conventions, ``output_shapes`` and ``state_dict()`` keys follow the
 reference; every flow layer executes as fused sm_100a kernels from libglowk.so.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -291,11 +293,33 @@ class Glow(nn.Module):
             h = h + self.y_emb(y_onehot).view(-1, nc, 1, 1)
         return ops.split_channel(h, 'simple')
 
+    def _fused_head(self, x):
+        """The loss head runs as one node (autograd.GlowNLLFunction) when the top prior is the plain N(0, I) and the
+        whole flow is on the pixel-major kernels (GLOWK_FUSED_HEAD=0: the layer-by-layer composition below)."""
+        from . import rows_path
+        return (self._plain_top_prior and config.use_rows_path and os.environ.get("GLOWK_FUSED_HEAD", "1") != "0"
+                and not getattr(self.flow, "_is_replica", False) and rows_path.supported(self.flow, x))
+
     def normal_flow(self, x, y_onehot, noise=None):
         """model.py:409-452.  `noise` (U(0, 1/n_bins), same shape as x) may be supplied for parity runs."""
         n_bins = 2 ** self.hps.model.n_bits_x
         if noise is None:
             noise = torch.nn.init.uniform_(torch.empty(*x.shape, device=x.device), 0, 1. / n_bins)
+        if self._fused_head(x):
+            train = torch.is_grad_enabled() and any(p.requires_grad for p in self.flow.parameters())
+            self.flow.prepare_invconvs(need_inverse=train)   # one batched LU kernel (the adjoint needs W^-T)
+            if train:
+                from .autograd import GlowNLLFunction
+                params = [p for p in self.flow.parameters() if p.requires_grad]
+                z, nll, loss = GlowNLLFunction.apply(self.flow, n_bins, x, noise, *params)
+            else:
+                from . import rows_path
+                d_x = x[0].numel()
+                with torch.no_grad():
+                    z, ld = rows_path.encode(self.flow, x.contiguous(), None, add=noise.contiguous(), want_ld=True)
+                    nll, loss = K.nll_head(z, ld, -float(np.log(n_bins)) * d_x, float(np.log(2.)) * d_x)
+            nll._glowk_mean = loss                           # picked up by generative_loss(nll)
+            return z, nll, None
         z = x + noise
         logdet_factor = x.shape[1] * ops.count_pixels(x)
         objective = torch.full((x.shape[0],), float(-np.log(n_bins)) * logdet_factor, device=x.device,
@@ -330,7 +354,10 @@ class Glow(nn.Module):
 
     @staticmethod
     def generative_loss(nll):
-        return torch.mean(nll)
+        """model.py:496-498.  For the nll tensor normal_flow returned from its fused loss head the batch mean was
+        computed by the same kernel."""
+        fused = getattr(nll, "_glowk_mean", None)
+        return fused if fused is not None else torch.mean(nll)
 
     @staticmethod
     def single_class_loss(y_logits, y):

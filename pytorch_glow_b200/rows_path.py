@@ -397,8 +397,8 @@ def _ones_col(net, dt):
     return k if (dt == _C.BF16 and k < net.k1p and net.in_channels % 2 == 0) else -1
 
 
-def _step_forward(step, x, n, c, h, w, ld, ws, save):
-    """FlowStep.normal_flow (network/model.py:82-117) on rows x [P][C]."""
+def _step_forward(step, x, n, c, h, w, ld, ws, save, want_ld=False):
+    """FlowStep.normal_flow (network/model.py:82-117) on rows x [P][C].  want_ld with ld None: the logdet starts at 0."""
     an = step.actnorm
     if an.needs_init:
         an.initialize_from_rows(x)
@@ -415,7 +415,7 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save):
     c3 = net[4]
     affine = step.coupling == 'affine'
     ld_out, hrows = K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), z, n, h, w, affine, False,
-                                    c3.logscale_factor, save_h=save, ld_in=ld, want_ld=ld is not None, an_logs=l,
+                                    c3.logscale_factor, save_h=save, ld_in=ld, want_ld=want_ld or ld is not None, an_logs=l,
                                     an_f=an.logscale_factor, logabsdet=logabsdet, sign=1.0, partials=ws.partials,
                                     tickets=ws.tickets)
     ctx = None
@@ -582,9 +582,11 @@ def _max_nblk(flow, h, w):
     return best
 
 
-def encode(flow, z, ld, tape=None):
+def encode(flow, z, ld, tape=None, add=None, want_ld=False):
     """FlowModel.encode (network/model.py:263-276).  z: NCHW fp32; ld: [N] fp32 or None.
-    With `tape` (a list) every layer records what its adjoint needs.  Returns (z_out NCHW, ld_out)."""
+    With `tape` (a list) every layer records what its adjoint needs.  Returns (z_out NCHW, ld_out).
+    add: NCHW tensor added to z inside the entry squeeze (Glow's dequantisation noise); want_ld with ld None: the
+    logdet is accumulated from zero (Glow's loss head adds the objective's constant start value)."""
     from .model import FlowStep
     z = z.contiguous()
     n, c, h, w = z.shape
@@ -599,14 +601,15 @@ def encode(flow, z, ld, tape=None):
             if h % f or w % f:
                 raise ValueError("Squeeze2d: H, W = %d, %d not divisible by factor %d" % (h, w, f))
             dst = torch.empty(n * (h // f) * (w // f), c * f * f, device=dev, dtype=torch.float32)
-            K.rows_squeeze(cur, layout, pitch, dst, ROWS, c * f * f, n, c, h, w, f, False)
+            K.rows_squeeze(cur, layout, pitch, dst, ROWS, c * f * f, n, c, h, w, f, False, add=add)
+            add = None
             if save:
                 tape.append(("squeeze", layer, (c, h, w, layout, pitch)))
             c, h, w = c * f * f, h // f, w // f
             cur, layout, pitch = dst, ROWS, c
         elif isinstance(layer, FlowStep):
             assert layout == ROWS and pitch == c
-            cur, ld, ctx = _step_forward(layer, cur, n, c, h, w, ld, ws, save)
+            cur, ld, ctx = _step_forward(layer, cur, n, c, h, w, ld, ws, save, want_ld)
             if save:
                 tape.append(("step", layer, ctx))
         else:

@@ -147,6 +147,7 @@ class FusedTrainStep:
         self.exp_avg = torch.zeros_like(self.arena.flat)
         self.exp_avg_sq = torch.zeros_like(self.arena.flat)
         self.ws = K.optim_workspace(dev)
+        self._one = torch.ones((), device=dev, dtype=torch.float32)      # seed of loss.backward
         # [lr, 1-beta1^t, sqrt(1-beta2^t)] are computed ON THE DEVICE from a device step counter inside the
         # (captured) optimizer step: no host memory is read when the GPU gets there, however far the CPU ran ahead
         self.sched_dev = torch.zeros(4, device=dev, dtype=torch.float32)
@@ -252,7 +253,7 @@ class FusedTrainStep:
         try:
             z, nll, _ = self.glow(x=x)
             loss = self.glow.generative_loss(nll)
-            loss.backward()
+            loss.backward(self._one)                 # explicit seed: no ones_like fill kernel in the step
         finally:
             self.glow.flow.__dict__.pop("_level_done_hook", None)
         if self.overlap:

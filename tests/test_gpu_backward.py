@@ -306,3 +306,42 @@ def test_train_steps_follow_oracle(golden_glow, use_graphs):
     worst = max(rel_err(got[k], p[k]) for k in names)
     print("3 train steps (graphs=%s): losses %s, worst param rel err %.2e" % (use_graphs, losses, worst))
     assert worst < 1e-3
+
+
+def test_fused_loss_head_matches_layer_composition(monkeypatch):
+    """Glow.normal_flow's fused loss head (dequantisation inside the entry squeeze, logdet from zero, objective start
+    + top prior + bits/dim + batch mean in glowk_nll_head; network/model.py:419-450, 496-498) against the same model
+    on the layer-by-layer composition (GLOWK_FUSED_HEAD=0), for a loss that uses nll per sample, the mean AND z."""
+    hps = make_hps((16, 16, 3), K=2, L=2, hidden_channels=32, coupling="affine", permutation="invconv", batch=4)
+    np.random.seed(1); torch.manual_seed(1)
+    glow = G.Glow(hps)
+    sd = randomize_({k: v.clone() for k, v in glow.state_dict().items()}, 3, coupling_std=0.02)
+    adopt(glow, sd)
+    glow.flow.set_conv_dtype("fp32")
+    glow = glow.to(DEV).train()
+    g = torch.Generator().manual_seed(2)
+    x = cu(torch.rand(4, 3, 16, 16, generator=g))
+    noise = cu(torch.rand(4, 3, 16, 16, generator=g) / 256)
+    wn = cu(torch.rand(4, generator=g))
+    wz = cu(torch.randn(4, 24, 4, 4, generator=g) * 1e-3)
+    out = {}
+    for fused in ("1", "0"):
+        monkeypatch.setenv("GLOWK_FUSED_HEAD", fused)
+        glow.zero_grad(set_to_none=True)
+        z, nll, _ = glow.normal_flow(x, None, noise=noise)
+        assert (getattr(nll, "_glowk_mean", None) is not None) == (fused == "1")
+        loss = G.Glow.generative_loss(nll) + (nll * wn).sum() + (z * wz).sum()
+        loss.backward()
+        out[fused] = (z.detach().clone(), nll.detach().clone(), float(G.Glow.generative_loss(nll)),
+                      {k: p.grad.clone() for k, p in glow.named_parameters() if p.grad is not None})
+    assert rel_err(out["1"][0], out["0"][0]) < 1e-6 and rel_err(out["1"][1], out["0"][1]) < 1e-6
+    assert abs(out["1"][2] - out["0"][2]) < 1e-6 * abs(out["0"][2])
+    assert out["1"][3].keys() == out["0"][3].keys() and len(out["1"][3]) > 20
+    worst = max(grad_rel(out["1"][3][k], out["0"][3][k]) for k in out["0"][3])
+    print("fused loss head vs composition: worst grad rel err %.2e" % worst)
+    assert worst < 1e-4
+    # eval path (no autograd)
+    monkeypatch.setenv("GLOWK_FUSED_HEAD", "1")
+    with torch.no_grad():
+        z2, nll2, _ = glow.normal_flow(x, None, noise=noise)
+    assert rel_err(nll2, out["0"][1]) < 1e-6 and rel_err(z2, out["0"][0]) < 1e-6
