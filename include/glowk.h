@@ -65,6 +65,13 @@ int glowk_actnorm_init(const void* x, int act_dtype, int64_t N, int64_t C, int64
                        int64_t sN, int64_t sC, int64_t sP, float scale, float logscale_factor,
                        float* bias_out, float* logs_out, void* stream);
 
+/* The init variants the call above does not cover: batch_variance (module.py:112-113: ONE variance, the mean of
+ * (x+bias)^2 over the whole tensor, for all channels) and the first call arriving in the reverse direction
+ * (module.py:143-146 with 44-45, 62-63: logs from the raw second moment mean x^2, then bias = -mean(x * exp(-f*logs))). */
+int glowk_actnorm_init_ex(const float* x, int64_t N, int64_t C, int64_t HW, int64_t sN, int64_t sC, int64_t sP,
+                          float scale, float logscale_factor, int batch_variance, int reverse, float* bias_out,
+                          float* logs_out, void* stream);
+
 /* ---- Invertible 1x1 conv weight prep: module.py:356-357,365 (torch.det / .inverse) -------
  * LU with partial pivoting of the CxC matrix W (one CTA, fp64 internally):
  * logabsdet_out[0] = log|det W|; winv_out (nullable) = W^-1. */

@@ -92,6 +92,20 @@ def actnorm_init(x, scale=1.0, logscale_factor=3.0, batch_variance=False):
     return bias, logs
 
 
+def actnorm_init_reverse(x, scale=1.0, logscale_factor=3.0, batch_variance=False):
+    """Data-dependent init when the first training-mode call comes with reverse=True (network/module.py:143-146:
+    actnorm_scale runs first and initialises logs from the RAW input (62-63, 106-120), then actnorm_center
+    initialises the bias from the scaled tensor (44-45, 93-104)).  Returns (bias, logs) shaped [1,C,1,1]."""
+    if batch_variance:
+        var = torch.mean(x ** 2).reshape(1, 1, 1, 1)
+    else:
+        var = reduce_mean(x ** 2, [0, 2, 3], keepdim=True)
+    logs = torch.log(scale / (torch.sqrt(var) + 1e-6)) / logscale_factor
+    xs = x * torch.exp(-(logs * logscale_factor))
+    bias = -1.0 * reduce_mean(xs, [0, 2, 3], keepdim=True)
+    return bias, logs.expand(1, x.shape[1], 1, 1).clone()
+
+
 def actnorm(x, bias, logs, logdet=None, reverse=False, logscale_factor=3.0):
     """network/module.py:34-84,122-149.  Out-of-place restatement.
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "glowk_invconv_prepare_batched": [_p, _i64, _i64, _p, _p, _p],
     "glowk_invconv_lu_assemble": [_p, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
     "glowk_invconv_lu_grads": [_p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p],
+    "glowk_actnorm_init_ex": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _i32, _i32, _p, _p, _p],
     "glowk_actnorm_mix": [_p, _p, _p, _p, _p, _p, _f32, _i64, _i64, _i64, _i32, _p],
     "glowk_squeeze2d": [_p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p],
     "glowk_im2col": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p],

@@ -129,6 +129,13 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // 
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
   return *reinterpret_cast<float2*>(&ud);
 }
+// two fp32 -> packed bf16 pair with the ReLU folded into the conversion (F2FP.RELU): low half = v.x, high half = v.y.
+// max(round(x), 0) == round-with-relu(x): rounding is monotonic and keeps the sign.
+__device__ __forceinline__ uint32_t cvt_relu_bf16x2(float2 v) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(v.y), "f"(v.x));
+  return d;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // 128-byte row `lane` of a [32 rows][128 B] SWIZZLE_128B box: 16-byte piece j lives at (j ^ (lane & 7)) * 16
@@ -503,21 +510,19 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (tl_rel >= 0) CNET_TS(true, tl_rel);
       const float* sc = (ph ? s_sc2 : s_sc1) + c * NC + g * 64;
       if (!BWD) {
-        // packed arithmetic: one FFMA2 (fma.rn.f32x2) + one F2FP + one HMNMX2 per PAIR of elements.  relu after the
-        // bf16 rounding equals relu before it (rounding is monotonic and keeps the sign), so results stay bit-identical
+        // packed arithmetic: one FFMA2 (fma.rn.f32x2) + one F2FP.RELU per PAIR of elements.  relu inside the bf16
+        // rounding equals relu before it (rounding is monotonic and keeps the sign), so results stay bit-identical
         // to the three-GEMM path.  Scale / shift come as LDS.128 broadcasts (warp-uniform addresses).
         const float4* sc4 = reinterpret_cast<const float4*>(sc);
         const float4* sf4 = reinterpret_cast<const float4*>((ph ? s_x2 : s_x1) + c * NC + g * 64);
-        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 s4 = sc4[j], t4 = sf4[j];
           const uint32_t* r = j < 8 ? &r0[4 * j] : &r1[4 * j - 32];
           const float2 v0 = ffma2(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), make_float2(s4.x, s4.y), make_float2(t4.x, t4.y));
           const float2 v1 = ffma2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
-          const __nv_bfloat162 h0 = __hmax2(__float22bfloat162_rn(v0), zero2), h1 = __hmax2(__float22bfloat162_rn(v1), zero2);
-          pk[2 * j] = *reinterpret_cast<const uint32_t*>(&h0);
-          pk[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+          pk[2 * j] = cvt_relu_bf16x2(v0);
+          pk[2 * j + 1] = cvt_relu_bf16x2(v1);
         }
       } else {
         const uint8_t* yrow = hb + (size_t)(c & 1) * HB_BYTES + my_off + lane * 128;

@@ -80,6 +80,70 @@ __global__ void actnorm_init_kernel(const float* __restrict__ x, int64_t N, int6
   }
 }
 
+// The two variants of the data-dependent init the default kernel above does not cover (network/module.py:44-45,
+// 62-63, 106-120).  Pass 1, one CTA per channel: stats[c] = mean_c, stats[C + c] = second moment of channel c --
+// centred (x - mean_c) in the forward direction; UNcentred in the reverse direction, where the reference initialises
+// logs first, from the raw input (module.py:143-146: scale, then centre).
+__global__ void actnorm_moments_kernel(const float* __restrict__ x, int64_t N, int64_t HW, int64_t sN, int64_t sC,
+                                       int64_t sP, int centred, double* __restrict__ stats, int C) {
+  __shared__ double red[32];
+  __shared__ double s_mean;
+  const int64_t c = blockIdx.x;
+  const int64_t cnt = N * HW;
+  const float* base = x + c * sC;
+  auto block_sum_d = [&](double v) -> double {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x < 32) {
+      r = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+    }
+    return r;
+  };
+  double acc = 0.0;
+  for (int64_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const int64_t n = e / HW, p = e - n * HW;
+    acc += (double)base[n * sN + p * sP];
+  }
+  double tot = block_sum_d(acc);
+  if (threadIdx.x == 0) s_mean = tot / (double)cnt;
+  __syncthreads();
+  const float b = centred ? -(float)s_mean : 0.f;
+  acc = 0.0;
+  for (int64_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const int64_t n = e / HW, p = e - n * HW;
+    const float v = base[n * sN + p * sP] + b;
+    acc += (double)(v * v);
+  }
+  tot = block_sum_d(acc);
+  if (threadIdx.x == 0) { stats[c] = s_mean; stats[C + c] = tot / (double)cnt; }
+}
+
+// Pass 2, one CTA: batch_variance -> one variance for all channels (every channel has the same count, so the mean of
+// the per-channel moments is the reference's mean over the whole tensor, module.py:112-113);
+// forward: bias = -mean;  reverse: bias = -mean(x * exp(-f*logs)) = -mean_c * exp(-f*logs_c) (module.py:143-146).
+__global__ void actnorm_init_finish_kernel(const double* __restrict__ stats, int C, float scale, float f,
+                                           int batch_variance, int reverse, float* __restrict__ bias_out,
+                                           float* __restrict__ logs_out) {
+  __shared__ double s_all;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int c = 0; c < C; ++c) t += stats[C + c];
+    s_all = t / (double)C;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float var = (float)(batch_variance ? s_all : stats[C + c]);
+    const float lg = logf(scale / (sqrtf(var) + 1e-6f)) / f;
+    logs_out[c] = lg;
+    const float m = (float)stats[c];
+    bias_out[c] = reverse ? -(m * expf(-(lg * f))) : -m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Fused ActNorm + channel mix / permutation (model.py:94-103, 142-152; module.py:356-369, 392-397)
 // Tile = TP consecutive global pixels; x tile (post-actnorm in forward) staged in smem as
@@ -712,6 +776,23 @@ extern "C" int glowk_actnorm_init(const void* x, int act_dtype, int64_t N, int64
   actnorm_init_kernel<<<(unsigned)C, 512, 0, (cudaStream_t)stream>>>(
       (const float*)x, N, HW, sN, sC, sP, scale, logscale_factor, bias_out, logs_out);
   GLOWK_CHECK_LAUNCH("glowk_actnorm_init");
+  return GLOWK_OK;
+}
+
+extern "C" int glowk_actnorm_init_ex(const float* x, int64_t N, int64_t C, int64_t HW, int64_t sN, int64_t sC,
+                                     int64_t sP, float scale, float logscale_factor, int batch_variance, int reverse,
+                                     float* bias_out, float* logs_out, void* stream) {
+  GLOWK_CHECK_ARG(x && bias_out && logs_out, "glowk_actnorm_init_ex: null pointer");
+  GLOWK_CHECK_ARG(N > 0 && C > 0 && HW > 0 && C < (1 << 20), "glowk_actnorm_init_ex: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* stats = nullptr;
+  GLOWK_CUDA(cudaMallocAsync((void**)&stats, (size_t)(2 * C) * sizeof(double), st));
+  actnorm_moments_kernel<<<(unsigned)C, 512, 0, st>>>(x, N, HW, sN, sC, sP, reverse ? 0 : 1, stats, (int)C);
+  actnorm_init_finish_kernel<<<1, 256, 0, st>>>(stats, (int)C, scale, logscale_factor, batch_variance, reverse,
+                                                bias_out, logs_out);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(stats, st);
+  if (e != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_actnorm_init_ex: %s", cudaGetErrorString(e));
   return GLOWK_OK;
 }
 

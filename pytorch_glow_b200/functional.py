@@ -33,25 +33,34 @@ def actnorm(x, bias, logs, logscale_factor=3.0, reverse=False, out=None):
     return y
 
 
-def actnorm_init_nchw(x, scale=1.0, logscale_factor=3.0):
-    """(bias, logs) [C] from a [N,C,H,W] fp32 batch.  network/module.py:86-120."""
+def actnorm_init_nchw(x, scale=1.0, logscale_factor=3.0, batch_variance=False, reverse=False):
+    """(bias, logs) [C] from a [N,C,H,W] fp32 batch.  network/module.py:86-120 (+ 44-45, 62-63, 112-113: the
+    batch_variance option and a first call in the reverse direction)."""
     check_cuda(x)
     x = _f32c(x)
     n, c, h, w = x.shape
     bias = torch.empty(c, device=x.device, dtype=torch.float32)
     logs = torch.empty_like(bias)
+    if batch_variance or reverse:
+        call("glowk_actnorm_init_ex", ptr(x), n, c, h * w, c * h * w, h * w, 1, float(scale), float(logscale_factor),
+             int(bool(batch_variance)), int(bool(reverse)), ptr(bias), ptr(logs))
+        return bias, logs
     call("glowk_actnorm_init", ptr(x), F32, n, c, h * w, c * h * w, h * w, 1, float(scale),
          float(logscale_factor), ptr(bias), ptr(logs))
     return bias, logs
 
 
-def actnorm_init_rows(rows, n_cols, scale=1.0, logscale_factor=3.0):
+def actnorm_init_rows(rows, n_cols, scale=1.0, logscale_factor=3.0, batch_variance=False, reverse=False):
     """Same statistics over a pixel-major fp32 matrix [P][ld] (columns 0..n_cols-1)."""
     check_cuda(rows)
     assert rows.dtype == torch.float32 and rows.dim() == 2 and rows.is_contiguous()
     p, ld = rows.shape
     bias = torch.empty(n_cols, device=rows.device, dtype=torch.float32)
     logs = torch.empty_like(bias)
+    if batch_variance or reverse:
+        call("glowk_actnorm_init_ex", ptr(rows), 1, n_cols, p, 0, 1, ld, float(scale), float(logscale_factor),
+             int(bool(batch_variance)), int(bool(reverse)), ptr(bias), ptr(logs))
+        return bias, logs
     call("glowk_actnorm_init", ptr(rows), F32, 1, n_cols, p, 0, 1, ld, float(scale), float(logscale_factor),
          ptr(bias), ptr(logs))
     return bias, logs

@@ -99,8 +99,15 @@ class FlowStep(nn.Module):
         partials, _ = K.coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, affine, True,
                                  c3.logscale_factor)
         wmat, idx, logabsdet = self._mix_args(x.device, True)
-        out_x = K.actnorm_mix(x, wmat, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
-                              an.logscale_factor, reverse=True)
+        if an.needs_init:
+            # first training-mode call in the reverse direction (network/module.py:143-146): un-mix, then let the
+            # ActNorm initialise itself from that tensor (logs from the raw second moment, then the bias)
+            y = K.actnorm_mix(x, wmat, idx, None, None, an.logscale_factor, reverse=True)
+            an.initialize_from_nchw(y, reverse=True)
+            out_x = K.actnorm(y, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1), an.logscale_factor, True)
+        else:
+            out_x = K.actnorm_mix(x, wmat, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
+                                  an.logscale_factor, reverse=True)
         vec, scalar_like = _logdet_in(logdet, n, x.device)
         if vec is None:
             return out_x, None

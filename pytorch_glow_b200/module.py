@@ -106,18 +106,17 @@ class ActNorm(nn.Module):
         """True iff the next training-mode call performs the data-dependent init (module.py:93-94)."""
         return self.training and not (self.bias_inited and self.logs_inited)
 
-    def initialize_from_nchw(self, x):
-        """module.py:86-120 on a [N,C,H,W] batch."""
-        if self.batch_variance:
-            raise NotImplementedError("ActNorm(batch_variance=True) is unused by the reference's callers")
+    def initialize_from_nchw(self, x, reverse=False):
+        """module.py:86-120 on a [N,C,H,W] batch.  reverse: the first training-mode call came in the reverse direction
+        (module.py:143-146: logs from the raw input, then the bias from the scaled input)."""
         with torch.no_grad():
-            b, l = K.actnorm_init_nchw(x, self.scale, self.logscale_factor)
+            b, l = K.actnorm_init_nchw(x, self.scale, self.logscale_factor, self.batch_variance, reverse)
             self._store_init(b, l)
 
     def initialize_from_rows(self, rows):
         """Same, on a pixel-major fp32 matrix [P][>=C] (conv output before the ActNorm)."""
         with torch.no_grad():
-            b, l = K.actnorm_init_rows(rows, self.num_channels, self.scale, self.logscale_factor)
+            b, l = K.actnorm_init_rows(rows, self.num_channels, self.scale, self.logscale_factor, self.batch_variance)
             self._store_init(b, l)
 
     def _store_init(self, b, l):
@@ -141,9 +140,7 @@ class ActNorm(nn.Module):
         assert x.device == self.bias.device and x.device == self.logs.device, \
             'Expect input device {} instead of {}'.format(self.bias.device, x.device)
         if self.needs_init:
-            if reverse:
-                raise NotImplementedError("data-dependent ActNorm init in the reverse direction")
-            self.initialize_from_nchw(x)
+            self.initialize_from_nchw(x, reverse=reverse)
         if torch.is_grad_enabled() and (x.requires_grad or self.bias.requires_grad):
             from .autograd import actnorm_autograd
             return actnorm_autograd(self, x, logdet, reverse)

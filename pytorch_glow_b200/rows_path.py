@@ -432,6 +432,18 @@ def _step_reverse(step, x, n, c, h, w, ws):
     p3 = net.tap_rows_from_rows(x, n, h, w, dt)
     c3 = net[4]
     wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
+    if an.needs_init:
+        # first training-mode call arrives in the reverse direction (network/module.py:143-146 with 44-45, 62-63):
+        # the ActNorm initialises from the un-mixed tensor -- logs from its raw second moment, then the bias
+        K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
+                        c3.logscale_factor)
+        if _is_wide(c):
+            y = K.gemm(x, wm, c, c, _C.EPI_STORE, out_dtype=_C.F32)
+        else:
+            y = K.rows_actnorm_mix(x, wm, idx, None, None, an.logscale_factor, reverse=True)
+        b, l = K.actnorm_init_rows(y, c, an.scale, an.logscale_factor, an.batch_variance, reverse=True)
+        an._store_init(b, l)
+        return K.actnorm(y.view(n * h * w, c, 1, 1), b, l, an.logscale_factor, reverse=True).view(n * h * w, c)
     if not _is_wide(c) and os.environ.get("GLOWK_REV_FUSED", "1") != "0":
         # inverse coupling + W^-1 mix + ActNorm^-1 in ONE launch (the coupled rows never leave shared memory)
         return K.rows_coupling_rev_mix(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w,

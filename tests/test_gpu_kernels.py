@@ -53,6 +53,71 @@ def test_actnorm_init(shape, scale):
     assert_close(l2, l_ref.reshape(-1), 1e-5, 1e-6, "logs(rows)")
 
 
+def test_actnorm_init_variants_match_reference():
+    """ActNorm(batch_variance=True) and the data-dependent init arriving with reverse=True (network/module.py:44-45,
+    62-63, 112-113, 143-146): module outputs and initialised parameters against the reference's (actnorm_init.npz)."""
+    from conftest import Golden
+    G_ = Golden("actnorm_init.npz")
+    import pytorch_glow_b200 as G
+    n = 0
+    for c in (12, 48):
+        for bv in (0, 1):
+            for rev in (0, 1):
+                tag = "c%d_bv%d_rev%d/" % (c, bv, rev)
+                if not G_.has(tag + "x"):
+                    continue
+                an = G.ActNorm(c, scale=1.3, logscale_factor=3., batch_variance=bool(bv)).to("cuda:0").train()
+                with torch.no_grad():
+                    y, ld = an(cu(G_.t(tag + "x")), torch.zeros(6, device="cuda:0"), reverse=bool(rev))
+                assert an.bias_inited and an.logs_inited
+                assert_close(an.bias, G_.t(tag + "bias"), 1e-5, 1e-6, tag + "bias")
+                assert_close(an.logs, G_.t(tag + "logs"), 1e-5, 1e-6, tag + "logs")
+                assert_close(y, G_.t(tag + "y"), 1e-5, 1e-5, tag + "y")
+                assert_close(ld, G_.t(tag + "logdet"), 1e-5, 1e-4, tag + "logdet")
+                if bv:                              # the rows entry point (Conv2d's ActNorm, FlowStep on the rows path)
+                    x = G_.t(tag + "x")
+                    rows = cu(x.permute(0, 2, 3, 1).reshape(-1, c).contiguous())
+                    b2, l2 = K.actnorm_init_rows(rows, c, 1.3, 3.0, batch_variance=True, reverse=bool(rev))
+                    assert_close(b2, G_.t(tag + "bias").reshape(-1), 1e-5, 1e-6, tag + "bias(rows)")
+                    assert_close(l2, G_.t(tag + "logs").reshape(-1), 1e-5, 1e-6, tag + "logs(rows)")
+                n += 1
+    assert n == 6
+
+
+def test_flowstep_reverse_direction_init_matches_oracle():
+    """A training-mode FlowStep whose first call is reverse_flow: the step's ActNorm initialises from the un-mixed tensor
+    (network/model.py:119-154 + module.py:143-146).  NCHW layer call and the rows path of FlowModel.decode."""
+    import pytorch_glow_b200 as G
+    from parity_util import randomize_
+    torch.manual_seed(3); np.random.seed(3)
+    c, hw, n = 12, 8, 4
+    fs = G.FlowStep(c, 32, permutation="invconv", coupling="affine")
+    sd = randomize_({k: v.clone() for k, v in fs.state_dict().items()}, 9, coupling_std=0.02)
+    fs.load_state_dict(sd)
+    for m in fs.modules():
+        if isinstance(m, G.ActNorm):
+            m.bias_inited = m.logs_inited = True
+    fs.actnorm.bias_inited = fs.actnorm.logs_inited = False
+    fs.conv_dtype = "fp32"
+    fs = fs.to("cuda:0").train()
+    z = torch.randn(n, c, hw, hw, generator=g(77)) * 1.5 + 0.3
+    # oracle: coupling^-1, W^-1, then the reverse-direction init and ActNorm^-1
+    z1, z2 = z[:, :c // 2], z[:, c // 2:]
+    h = O.f_net(z1, sd, "f.")
+    shift, sc = O.split_channel(h, "cross")
+    sc = torch.sigmoid(sc + 2.)
+    u = torch.cat([z1, z2 / sc - shift], 1)
+    y, _ = O.invconv(u, sd["invconv.weight"], reverse=True)
+    b, l = O.actnorm_init_reverse(y)
+    x_ref, _ = O.actnorm(y, b, l, reverse=True)
+    with torch.no_grad():
+        x, _ = fs(cu(z).clone(), None, reverse=True)
+    assert fs.actnorm.bias_inited
+    assert_close(fs.actnorm.bias, b, 1e-4, 1e-5, "bias")
+    assert_close(fs.actnorm.logs, l, 1e-4, 1e-5, "logs")
+    assert_close(x, x_ref, 1e-4, 1e-4, "x")
+
+
 # ---------------------------------------------------------------- 1x1 conv weight prep
 @pytest.mark.parametrize("c", [2, 6, 12, 24, 48, 96, 130, 192, 384])
 def test_invconv_prepare(c):

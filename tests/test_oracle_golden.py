@@ -259,3 +259,31 @@ def test_trainer_arithmetic():
         m, v = torch.zeros_like(p0), torch.zeros_like(p0)
         O.adam_step_(p0, g, m, v, 1, 1e-3)
         assert_close(p0, r.data, 1e-5, 1e-7)
+
+
+# ---------------------------------------------------------------- actnorm_init.npz (make_golden_actnorm.py)
+def test_actnorm_init_variants_match_reference():
+    """batch_variance=True and a first training-mode call with reverse=True (network/module.py:44-45, 62-63, 112-113,
+    143-146), against the reference ActNorm's own parameters and outputs."""
+    from conftest import Golden
+    G = Golden("actnorm_init.npz")
+    n = 0
+    for c in (12, 48):
+        for bv in (0, 1):
+            for rev in (0, 1):
+                tag = "c%d_bv%d_rev%d/" % (c, bv, rev)
+                if not G.has(tag + "x"):
+                    continue
+                x = G.t(tag + "x")
+                if rev:
+                    bias, logs = O.actnorm_init_reverse(x, 1.3, 3.0, bool(bv))
+                else:
+                    bias, logs = O.actnorm_init(x, 1.3, 3.0, bool(bv))
+                    logs = logs.expand(1, c, 1, 1)
+                assert_close(bias, G.t(tag + "bias"), 1e-5, 1e-6, tag + "bias")
+                assert_close(logs, G.t(tag + "logs"), 1e-5, 1e-6, tag + "logs")
+                y, ld = O.actnorm(x, bias, logs, torch.zeros(x.shape[0]), reverse=bool(rev))
+                assert_close(y, G.t(tag + "y"), 1e-5, 1e-5, tag + "y")
+                assert_close(ld, G.t(tag + "logdet"), 1e-5, 1e-4, tag + "logdet")
+                n += 1
+    assert n == 6
