@@ -267,7 +267,11 @@ class GlowNLLFunction(torch.autograd.Function):
                                  want_ld=True)
         ctx.denom = math.log(2.) * d_x
         nll, loss = K.nll_head(z, ld, -math.log(n_bins) * d_x, ctx.denom)
-        ctx.flow, ctx.tape, ctx.z = flow, tape, z
+        ctx.flow, ctx.tape = flow, tape
+        # z is an OUTPUT of this node: keeping it as a plain attribute would tie node -> z -> node into a reference
+        # cycle, and a node that outlives its iteration keeps the parameters' AccumulateGrad nodes (and the stream
+        # they were created on) alive -- fatal for the next CUDA-graph capture.  save_for_backward breaks the cycle.
+        ctx.save_for_backward(z)
         ctx.set_materialize_grads(False)
         return z, nll, loss
 
@@ -277,7 +281,8 @@ class GlowNLLFunction(torch.autograd.Function):
         if dz is None and dnll is None and dloss is None:
             return (None,) * len(ctx.needs_input_grad)
         f = lambda t: None if t is None else t.contiguous().float()
-        dz_top, dld = K.nll_head_bwd(ctx.z, ctx.denom, g_loss=f(dloss), g_nll=f(dnll), dz_in=f(dz))
+        (z,) = ctx.saved_tensors
+        dz_top, dld = K.nll_head_bwd(z, ctx.denom, g_loss=f(dloss), g_nll=f(dnll), dz_in=f(dz))
         if dloss is None and dnll is None:
             dld.zero_()                                     # only z took part in the loss
             dz_top = f(dz)

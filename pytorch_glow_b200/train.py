@@ -13,6 +13,8 @@ gradient arena, so that
 import math
 import os
 
+import gc
+
 import torch
 import torch.distributed as dist
 
@@ -326,6 +328,7 @@ class FusedTrainStep:
                 self._optimizer()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        gc.collect()      # no autograd node of the warm-up (created on the side stream) may survive into the capture
         self.arena.flat.copy_(saved[0]); self.exp_avg.copy_(saved[1]); self.exp_avg_sq.copy_(saved[2])
         self.step_dev.copy_(saved[3])
         _module.bump_weight_generation()
