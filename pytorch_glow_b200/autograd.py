@@ -295,15 +295,31 @@ class GlowNLLFunction(torch.autograd.Function):
 
 # ------------------------------------------------------------------ stand-alone layer nodes
 class _StepFunction(torch.autograd.Function):
+    """A FlowStep called as a layer: on the pixel-major kernels (fused coupling net, packed weight gradients) behind a
+    layout change when the step's shape allows it, else on the per-layer NCHW kernels."""
+
     @staticmethod
     def forward(ctx, step, x, logdet, *params):
-        y, ld, c = flowstep_forward_save(step, x.detach().contiguous(), None if logdet is None else logdet.detach().contiguous())
+        from . import rows_path
+        x = x.detach().contiguous()
+        ld = None if logdet is None else logdet.detach().contiguous()
+        ctx.rows = step._rows_route(x)
+        if ctx.rows:
+            y, ld, c = rows_path.step_forward_nchw(step, x, ld, save=True)
+        else:
+            y, ld, c = flowstep_forward_save(step, x, ld)
         ctx.step, ctx.c = step, c
         return (y, ld) if ld is not None else y
 
     @staticmethod
     def backward(ctx, dy, dld=None):
-        dx = flowstep_backward(ctx.step, ctx.c, dy.contiguous(), None if dld is None else dld.contiguous())
+        from . import rows_path
+        dld_c = None if dld is None else dld.contiguous()
+        if ctx.rows:
+            dx = rows_path.step_backward_nchw(ctx.step, ctx.c, dy.contiguous(), dld_c)
+        else:
+            dx = flowstep_backward(ctx.step, ctx.c, dy.contiguous(), dld_c)
+        ctx.c = None
         return (None, dx, dld) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 

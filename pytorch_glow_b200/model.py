@@ -56,6 +56,24 @@ class FlowStep(nn.Module):
             return (winv if reverse else w), None, ld
         return None, self.perm_module.device_indices(device, reverse), None
 
+    def _rows_route(self, x):
+        """A stand-alone call (the reference's FlowModel driving this package's FlowStep) runs on the pixel-major
+        kernels -- fused coupling net included -- behind a layout change in and out.  GLOWK_LAYER_ROWS=0: the
+        per-layer NCHW kernels (csrc/flow_kernels.cu), also the path of channel counts the rows kernels do not take."""
+        return os.environ.get("GLOWK_LAYER_ROWS", "1") != "0" and rows_path.step_supported(self, x)
+
+    def _rows_logdet_in(self, logdet, n, device):
+        vec, scalar_like = _logdet_in(logdet, n, device)
+        if vec is not None and vec.shape[0] == 1 and n != 1:
+            vec = vec.expand(n).contiguous()
+        return vec, scalar_like
+
+    def _rows_logdet_out(self, ld, scalar_like):
+        if ld is None:
+            return None
+        keep_scalar = scalar_like and self.coupling != 'affine'      # (reference broadcasting semantics)
+        return _logdet_out(ld[:1] if keep_scalar else ld, keep_scalar)
+
     # -- forward (model.py:82-117) ------------------------------------------------------------------
     def normal_flow(self, x, logdet=None):
         _C.check_cuda(x)
@@ -64,6 +82,10 @@ class FlowStep(nn.Module):
             return flowstep_autograd(self, x, logdet)
         x = x.contiguous()
         n, c, h, w = x.shape
+        if self._rows_route(x):
+            vec, scalar_like = self._rows_logdet_in(logdet, n, x.device)
+            z, ld, _ = rows_path.step_forward_nchw(self, x, vec)
+            return z, self._rows_logdet_out(ld, scalar_like)
         an = self.actnorm
         if an.needs_init:
             an.initialize_from_nchw(x)
@@ -93,6 +115,10 @@ class FlowStep(nn.Module):
         x = x.contiguous()
         n, c, h, w = x.shape
         an = self.actnorm
+        if self._rows_route(x) and not (an.needs_init and logdet is not None):
+            vec, scalar_like = self._rows_logdet_in(logdet, n, x.device)
+            out, ld = rows_path.step_reverse_nchw(self, x, vec)
+            return out, self._rows_logdet_out(ld, scalar_like)
         c3 = self.f[4]
         affine = self.coupling == 'affine'
         p3 = self.f.tap_rows(x, self.conv_dtype)

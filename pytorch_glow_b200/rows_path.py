@@ -424,19 +424,32 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save, want_ld=False):
     return z, ld_out, ctx
 
 
-def _step_reverse(step, x, n, c, h, w, ws):
-    """FlowStep.reverse_flow (network/model.py:119-154) on rows; x is clobbered."""
+def _step_reverse(step, x, n, c, h, w, ws, ld=None, want_ld=False):
+    """FlowStep.reverse_flow (network/model.py:119-154) on rows; x is clobbered.  Returns the new rows, or
+    (rows, ld_out) when the reverse direction's logdet is asked for (ld given or want_ld)."""
     an = step.actnorm
     net = step.f
     dt = net.dtype(step.conv_dtype)
     p3 = net.tap_rows_from_rows(x, n, h, w, dt)
     c3 = net[4]
-    wm, idx, _, _, _ = _mix_params(step, x.device, True, False)
+    wm, idx, logabsdet, _, _ = _mix_params(step, x.device, True, False)
+    want_ld = want_ld or ld is not None
+    affine = step.coupling == 'affine'
+    b3, l3 = c3.bias.detach(), c3.logs.detach().reshape(-1)
+
+    def coupling_inverse():
+        # in place on x; with the logdet: -(HW * (sum f*logs + log|det W|) + sum log scale)   (model.py:131-152)
+        ld_out, _ = K.rows_coupling(p3, b3, l3, x, n, h, w, affine, True, c3.logscale_factor, ld_in=ld, want_ld=want_ld,
+                                    an_logs=an.logs.detach().reshape(-1) if want_ld else None, an_f=an.logscale_factor,
+                                    logabsdet=logabsdet if want_ld else None, sign=-1.0,
+                                    partials=ws.partials if want_ld else None, tickets=ws.tickets if want_ld else None)
+        return ld_out
+
     if an.needs_init:
         # first training-mode call arrives in the reverse direction (network/module.py:143-146 with 44-45, 62-63):
         # the ActNorm initialises from the un-mixed tensor -- logs from its raw second moment, then the bias
-        K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
-                        c3.logscale_factor)
+        assert not want_ld, "the logdet of an uninitialised ActNorm is not defined before its init"
+        coupling_inverse()
         if _is_wide(c):
             y = K.gemm(x, wm, c, c, _C.EPI_STORE, out_dtype=_C.F32)
         else:
@@ -444,18 +457,17 @@ def _step_reverse(step, x, n, c, h, w, ws):
         b, l = K.actnorm_init_rows(y, c, an.scale, an.logscale_factor, an.batch_variance, reverse=True)
         an._store_init(b, l)
         return K.actnorm(y.view(n * h * w, c, 1, 1), b, l, an.logscale_factor, reverse=True).view(n * h * w, c)
-    if not _is_wide(c) and os.environ.get("GLOWK_REV_FUSED", "1") != "0":
+    ab, al = an.bias.detach().reshape(-1), an.logs.detach().reshape(-1)
+    if not want_ld and not _is_wide(c) and os.environ.get("GLOWK_REV_FUSED", "1") != "0":
         # inverse coupling + W^-1 mix + ActNorm^-1 in ONE launch (the coupled rows never leave shared memory)
-        return K.rows_coupling_rev_mix(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w,
-                                       step.coupling == 'affine', c3.logscale_factor, wm, idx,
-                                       an.bias.detach().reshape(-1), an.logs.detach().reshape(-1), an.logscale_factor)
-    K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), x, n, h, w, step.coupling == 'affine', True,
-                    c3.logscale_factor)
+        return K.rows_coupling_rev_mix(p3, b3, l3, x, n, h, w, affine, c3.logscale_factor, wm, idx, ab, al,
+                                       an.logscale_factor)
+    ld_out = coupling_inverse()
     if _is_wide(c):
-        return _mix_wide_forward(x, wm, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
-                                 an.logscale_factor, True)
-    return K.rows_actnorm_mix(x, wm, idx, an.bias.detach().reshape(-1), an.logs.detach().reshape(-1),
-                              an.logscale_factor, reverse=True)
+        out = _mix_wide_forward(x, wm, ab, al, an.logscale_factor, True)
+    else:
+        out = K.rows_actnorm_mix(x, wm, idx, ab, al, an.logscale_factor, reverse=True)
+    return (out, ld_out) if want_ld else out
 
 
 def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
@@ -580,6 +592,70 @@ def _split_backward(sp, ctx, dx, dld, n, c, h, w, plan):
     da = K.gemm(duc, wt, kp, cp, _C.EPI_STORE, out_dtype=_C.F32)
     K.rows_tapsum(da, dx, 0, ch, n, h, w, flip=True, accumulate=True)
     return dx
+
+
+# ------------------------------------------------------------------ one FlowStep called as a layer (NCHW in / out)
+def _layer_view(layer):
+    """A one-layer flow around `layer`: owner of its pack / gradient plans and workspaces."""
+    v = layer.__dict__.get("_rows_view")
+    if v is None or v.layers[0] is not layer:          # (DataParallel replicas share __dict__ copies)
+        v = layer.__dict__["_rows_view"] = _FlowView([layer])
+    return v
+
+
+def step_supported(step, x):
+    """True iff a stand-alone FlowStep call on the NCHW tensor x can run on the pixel-major kernels (a layout change
+    on the way in and out: the reference's FlowStep/FlowModel classes calling this package's layers, INTEGRATION.md
+    section 1, second patch line)."""
+    return (config.use_rows_path and torch.is_tensor(x) and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and 0 < x.shape[0] <= 65535 and x.shape[1] == step.in_channels and _step_ok(step)
+            and x.numel() < (1 << 31))
+
+
+def _to_rows(x):
+    n, c, h, w = x.shape
+    rows = torch.empty(n * h * w, c, device=x.device, dtype=torch.float32)
+    K.rows_squeeze(x.contiguous(), NCHW, c * h * w, rows, ROWS, c, n, c, h, w, 1, False)
+    return rows
+
+
+def _to_nchw(rows, n, c, h, w):
+    out = torch.empty(n, c, h, w, device=rows.device, dtype=torch.float32)
+    K.rows_squeeze(rows, ROWS, c, out, NCHW, c * h * w, n, c, h, w, 1, False)
+    return out
+
+
+def step_forward_nchw(step, x, ld, save=False, want_ld=False):
+    """FlowStep.normal_flow on an NCHW tensor through the rows kernels -> (z NCHW, ld_out, ctx | None)."""
+    n, c, h, w = x.shape
+    view = _layer_view(step)
+    prepare_packs(view, save, x.device)
+    ws = _workspace(view, x.device, n, K.rows_coupling_nblk(h * w, c))
+    z, ld_out, ctx = _step_forward(step, _to_rows(x), n, c, h, w, ld, ws, save, want_ld)
+    return _to_nchw(z, n, c, h, w), ld_out, ctx
+
+
+def step_reverse_nchw(step, z, ld=None):
+    """FlowStep.reverse_flow on an NCHW tensor through the rows kernels -> (x NCHW, ld_out | None)."""
+    n, c, h, w = z.shape
+    view = _layer_view(step)
+    prepare_packs(view, False, z.device)
+    ws = _workspace(view, z.device, n, K.rows_coupling_nblk(h * w, c))
+    out = _step_reverse(step, _to_rows(z), n, c, h, w, ws, ld)
+    ld_out = None
+    if ld is not None:
+        out, ld_out = out
+    return _to_nchw(out, n, c, h, w), ld_out
+
+
+def step_backward_nchw(step, ctx, dy, dld):
+    """Adjoint of step_forward_nchw: accumulates the step's parameter gradients into .grad, returns dx NCHW."""
+    n, c, h, w = dy.shape
+    plan = grad_plan(_layer_view(step), dy.device)
+    plan.begin()
+    dx = _step_backward(step, ctx, _to_rows(dy), dld, n, c, h, w, plan)
+    plan.finish()
+    return _to_nchw(dx, n, c, h, w)
 
 
 # ------------------------------------------------------------------ whole model

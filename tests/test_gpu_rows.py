@@ -515,3 +515,57 @@ def test_rows_coupling_rev_mix_matches_two_launches(c, h, w, affine, perm):
     torch.cuda.synchronize()
     assert torch.equal(x, x0)                       # the input rows are not modified
     assert torch.equal(got, ref), (got - ref).abs().max().item()
+
+
+# ---------------------------------------------------------------- a FlowStep called as a layer
+@pytest.mark.parametrize("perm,coup,c,hw,hidden,lu", [("invconv", "affine", 12, 16, 32, False),
+                                                      ("shuffle", "additive", 24, 8, 32, False),
+                                                      ("invconv", "affine", 48, 4, 64, True)])
+def test_standalone_flowstep_rows_route_matches_nchw_route_and_oracle(monkeypatch, perm, coup, c, hw, hidden, lu):
+    """FlowStep.forward called as a layer (the reference's FlowModel driving this package's layers, INTEGRATION.md
+    section 1) runs on the pixel-major kernels behind a layout change: forward, reverse (with the reference's
+    logdet conventions: None / number / [N] tensor) and all gradients against the per-layer NCHW route
+    (GLOWK_LAYER_ROWS=0) and, for the dense 1x1 conv, the oracle."""
+    np.random.seed(c); torch.manual_seed(c)
+    fs = G.FlowStep(c, hidden, permutation=perm, coupling=coup, lu_decomposition=lu)
+    sd = randomize_({k: v.clone() for k, v in fs.state_dict().items()}, 31, coupling_std=0.02)
+    fs.load_state_dict(sd)
+    for m in fs.modules():
+        if isinstance(m, G.ActNorm):
+            m.bias_inited = m.logs_inited = True
+    fs.conv_dtype = "fp32"
+    fs = fs.to(DEV).train()
+    n = 3
+    x = torch.randn(n, c, hw, hw, generator=g(5))
+    ld0 = torch.randn(n, generator=g(6))
+    wz = cu(torch.randn(n, c, hw, hw, generator=g(7)))
+    wl = cu(torch.randn(n, generator=g(8)))
+    res = {}
+    for route in ("1", "0"):
+        monkeypatch.setenv("GLOWK_LAYER_ROWS", route)
+        assert fs._rows_route(cu(x)) == (route == "1")
+        with torch.no_grad():
+            z, ld = fs(cu(x), cu(ld0))
+            z_none, ld_none = fs(cu(x), None)
+            z_s, ld_s = fs(cu(x), 0.5)
+            xr, ldr = fs(z.clone(), ld.clone(), reverse=True)
+            xr_none, _ = fs(z.clone(), None, reverse=True)
+        assert ld_none is None and torch.equal(z_none, z) and torch.equal(z_s, z)
+        assert ld_s.dim() == (1 if coup == "affine" else 0)           # reference broadcasting semantics
+        fs.zero_grad(set_to_none=True)
+        xg = cu(x).requires_grad_(True)
+        zz, ll = fs(xg, cu(ld0))
+        ((zz * wz).sum() + (ll * wl).sum()).backward()
+        res[route] = dict(z=z, ld=ld, ld_s=ld_s.reshape(-1)[:1], xr=xr, ldr=ldr, xr_none=xr_none, dx=xg.grad.clone(),
+                          grads={k: p.grad.clone() for k, p in fs.named_parameters() if p.grad is not None})
+    a, b = res["1"], res["0"]
+    for k in ("z", "ld", "ld_s", "xr", "ldr", "xr_none", "dx"):
+        assert rel_err(a[k], b[k]) < 2e-5, k
+    assert rel_err(a["xr"], x) < 1e-4 and rel_err(a["ldr"], ld0) < 1e-4      # round trip
+    assert a["grads"].keys() == b["grads"].keys() and len(a["grads"]) >= 9
+    for k in a["grads"]:
+        ga, gb = a["grads"][k].double().cpu(), b["grads"][k].double().cpu()
+        assert float((ga - gb).abs().max()) <= 2e-4 * max(float(gb.abs().max()), 1e-6), k
+    if not lu and perm == "invconv":
+        z_ref, ld_ref = O.flowstep(x, ld0.clone(), sd, "", perm, coup)
+        assert rel_err(a["z"], z_ref) < 1e-4 and rel_err(a["ld"], ld_ref) < 1e-4
