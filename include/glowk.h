@@ -223,6 +223,27 @@ int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int
                                  const void* h1, void* d2, void* d1, int64_t ldh, void* da1, int64_t ldda1,
                                  float* dbias2, float* dbias1, void* stream);
 
+/* The same two calls with the ReLU masks of the hidden activations as BITS.  The training forward writes, next to
+ * h1 / h2 (still needed by the weight-gradient GEMMs), one bit per element; the backward chain then reads 1/16 of the
+ * bytes for its two ReLU' masks (the kernel is bound by its HBM traffic, of which the bf16 masks were 45 %).
+ * mask1 / mask2: glowk_cnet_relu_mask_bytes(M) bytes each, 8-byte aligned, opaque layout
+ * ([tile of 128 rows][8 column groups of 64][128 rows] x 64 bits).  Results are bit-identical to the unmasked calls. */
+int64_t glowk_cnet_relu_mask_bytes(int64_t M);
+int glowk_cnet_forward_implicit_masked(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
+                                       int64_t W, int64_t ones_col, void* a1_save, int64_t lda, const void* w1,
+                                       int64_t ldw1, const void* w2, int64_t ldw2, const void* w3, int64_t ldw3,
+                                       int64_t K1, int64_t hidden, int64_t N3, const float* bias1, const float* logs1,
+                                       float f1, const float* bias2, const float* logs2, float f2, float* p3,
+                                       int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* mask1, void* mask2,
+                                       void* stream);
+int glowk_cnet_backward_implicit_masked(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
+                                        void* d3col_save, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
+                                        int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t K3, int64_t hidden,
+                                        int64_t K1p, const float* logs2, float f2, const float* logs1, float f1,
+                                        const void* h2, const void* h1, void* d2, void* d1, int64_t ldh, void* da1,
+                                        int64_t ldda1, float* dbias2, float* dbias1, const void* mask2,
+                                        const void* mask1, void* stream);
+
 /* ---- Coupling: model.py:105-115 (fwd) / 131-140 (rev) --------------------------------------
  * h[n,co,y,x] = (u + bias3[co]) * exp(f*logs3[co]),  u = 3x3 tap gather-sum of P (ldp floats/row,
  * column tap*Cout+co), i.e. Conv2dZeros (module.py:295-296).

@@ -52,6 +52,9 @@ SIGNATURES = {
                            _p, _i64, _p, _p, _i64, _p],
     "glowk_cnet_forward_implicit": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
                                     _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p],
+    "glowk_cnet_relu_mask_bytes": [_i64],
+    "glowk_cnet_forward_implicit_masked": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p, _p, _p],
+    "glowk_cnet_backward_implicit_masked": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _p, _f32, _p, _f32, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _p, _p, _p],
     "glowk_cnet_backward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _f32, _p, _f32, _p, _p,
                             _p, _p, _i64, _p, _i64, _p, _p, _p],
     "glowk_cnet_backward_implicit": [_p, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64,
@@ -97,7 +100,7 @@ SIGNATURES = {
     "glowk_conv_actnorm_finish_batched": [_p, _i64, _i64, _p],
 }
 _RESTYPES = {"glowk_last_error": _c.c_char_p, "glowk_coupling_nblk": _i64, "glowk_optim_workspace_floats": _i64,
-             "glowk_rows_coupling_nblk": _i64}
+             "glowk_rows_coupling_nblk": _i64, "glowk_cnet_relu_mask_bytes": _i64}
 
 _lib = None
 launch_count = 0  # kernels-launching C-ABI calls made by this process (bench.py's gpu_launches claim)

@@ -62,6 +62,9 @@ struct Shared {
 struct Params {
   int M, K1B, N3, NH, nhb, c3_col, deferred, nstages, bps;
   int save1, save2, dbg;
+  // ReLU bit masks of the two hidden activations, one uint2 (64 columns) per (tile, chunk half, row): written by the
+  // training forward (mk[ph] = mask of the activation EPI(ph) produces), read by the backward (mask EPI(ph) applies)
+  uint2* mk[2];
   const float *bias1, *logs1, *bias2, *logs2;
   float f1, f2;
   float *dbias1, *dbias2;     // backward: column sums of the stored d2 (EPI1) / d1 (EPI2), nullable
@@ -128,6 +131,17 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {      // 
                      uc = *reinterpret_cast<unsigned long long*>(&c), ud;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
   return *reinterpret_cast<float2*>(&ud);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {                // two fp32 multiplies in one instruction
+  unsigned long long ua = *reinterpret_cast<unsigned long long*>(&a), ub = *reinterpret_cast<unsigned long long*>(&b), ud;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+  return *reinterpret_cast<float2*>(&ud);
+}
+// per-half bit mask of a packed bf16 pair: 0xffff where the half is > 0, else 0 (HSET2.BM)
+__device__ __forceinline__ uint32_t gt0_mask_bf16x2(uint32_t y) {
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(y), "r"(0u));
+  return m;
 }
 // two fp32 -> packed bf16 pair with the ReLU folded into the conversion (F2FP.RELU): low half = v.x, high half = v.y.
 // max(round(x), 0) == round-with-relu(x): rounding is monotonic and keeps the sign.
@@ -471,7 +485,35 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const uint32_t lane_taddr = tmem_base + ((uint32_t)row0 << 16);
     const size_t my_off = (size_t)g * BOX_BYTES + (size_t)quarter * 4096;   // this warp's [32 rows][64 k] slice of a chunk buffer
     const bool no_epi = (p.dbg & 4) != 0;
-    // Backward: the ReLU masks (the saved forward activations, [32 rows][64 columns] bf16 per warp and chunk) are
+    // Backward with bit masks (written by the training forward, 8 bytes per row and chunk half instead of a 128-byte
+    // row of the bf16 activation): each lane copies its own row's four words of a phase into shared memory with
+    // cp.async one whole phase ahead (no register waits on HBM latency), and reads them back per chunk.
+    const bool bitmask = BWD && p.mk[0] != nullptr;
+    const bool want_mask = !BWD && p.mk[0] != nullptr;
+    uint8_t* s_mask = reinterpret_cast<uint8_t*>(sh + 1);         // [2 phases][EPI_WARPS][NCHUNK][32 lanes] x 8 B (BWD only)
+    auto mask_slot = [&](int ph, int c) -> uint32_t {
+      return smem_u32(s_mask) + (uint32_t)((((ph * EPI_WARPS + ew) * NCHUNK + c) * 32 + lane) * 8);
+    };
+    auto issue_masks = [&](int t, int ph) {                       // phase ph of tile t -> buffer ph; one commit group
+      if (bitmask && t < num_tiles) {
+#pragma unroll
+        for (int c = 0; c < NCHUNK; ++c) {
+          const uint2* src = p.mk[ph] + (uint32_t)(t * 8 + c * 2 + g) * (uint32_t)BLOCK_M + (uint32_t)(row0 + lane);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mask_slot(ph, c)), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto read_mask = [&](int ph, int c) -> uint2 {
+      uint2 v;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(mask_slot(ph, c)) : "memory");
+      return v;
+    };
+    if (bitmask) issue_masks(blockIdx.x, 0);
+    // every chunk of EPI1 / EPI2 issues one TMA store from alternating staging slices: the slice about to be rewritten
+    // was read by the store before last, so one store may stay in flight
+    const bool chain_stores = BWD ? bitmask : (p.save1 && p.save2);
+    // Backward without them: the ReLU masks (the saved forward activations, [32 rows][64 columns] bf16 per warp and chunk) are
     // TMA-loaded straight into this warp's slice of chunk buffer (c & 1) -- the slice the gradient of the same chunk
     // is then written to in place -- so two mask boxes are in flight per warp (they come from HBM: ~1500 cycles)
     // without any extra shared memory.  A slice may be refilled once the TMA store / GEMM3 partial that last read it
@@ -483,10 +525,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         tma_load_2d(ph ? &tm_y2 : &tm_y1, bar, hb + (size_t)(c & 1) * HB_BYTES + my_off, c * NC + g * 64, tile * BLOCK_M + row0);
       }
     };
-    if (BWD && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, 0);
+    if (BWD && !bitmask && (int)blockIdx.x < num_tiles) issue_y(blockIdx.x, 0, 0);
 
     // this warp's 32 rows x 64 columns of a chunk accumulator -> bf16 pairs; releases the accumulator
-    auto epilogue_chunk = [&](int c, int ph, uint32_t acc_col, uint64_t* rel_bar, uint32_t (&pk)[32], int tl_rel, uint32_t tcnt) {
+    auto epilogue_chunk = [&](int c, int ph, uint32_t acc_col, uint64_t* rel_bar, uint32_t (&pk)[32], int tl_rel, uint32_t tcnt, int tile, uint2 mbits) {
       if (no_epi) {                                                // profiling: barrier protocol only
         tcgen05_fence_before();
         __syncwarp();
@@ -498,7 +540,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       uint32_t r0[32], r1[32];
       tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64), r0);
       tmem_ld32_async(lane_taddr + acc_col + (uint32_t)(g * 64 + 32), r1);
-      if (BWD) mbar_wait(&sh->y_bar[ew * 2 + (c & 1)], (tcnt * 4u + (uint32_t)(ph * 2 + (c >> 1))) & 1);
+      if (BWD && !bitmask) mbar_wait(&sh->y_bar[ew * 2 + (c & 1)], (tcnt * 4u + (uint32_t)(ph * 2 + (c >> 1))) & 1);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
@@ -515,6 +557,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // to the three-GEMM path.  Scale / shift come as LDS.128 broadcasts (warp-uniform addresses).
         const float4* sc4 = reinterpret_cast<const float4*>(sc);
         const float4* sf4 = reinterpret_cast<const float4*>((ph ? s_x2 : s_x1) + c * NC + g * 64);
+        // Training: the ReLU mask for the backward pass as 1 bit per element (instead of the backward re-reading the
+        // bf16 activation): pair jp (columns 2jp, 2jp+1) -> word jp/16, bits 15 - jp%16 (even column) and
+        // 31 - jp%16 (odd column); one HSET2.BM + one LOP3 per pair.
+        uint32_t u0 = 0u, u1 = 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float4 s4 = sc4[j], t4 = sf4[j];
@@ -523,25 +569,54 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           const float2 v1 = ffma2(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), make_float2(s4.z, s4.w), make_float2(t4.z, t4.w));
           pk[2 * j] = cvt_relu_bf16x2(v0);
           pk[2 * j + 1] = cvt_relu_bf16x2(v1);
+          if (want_mask) {
+            const uint32_t m0 = gt0_mask_bf16x2(pk[2 * j]) & (0x00010001u << (15 - ((2 * j) & 15)));
+            const uint32_t m1 = gt0_mask_bf16x2(pk[2 * j + 1]) & (0x00010001u << (15 - ((2 * j + 1) & 15)));
+            if (j < 8) u0 |= m0 | m1; else u1 |= m0 | m1;
+          }
         }
+        if (want_mask)
+          p.mk[ph][(uint32_t)(tile * 8 + c * 2 + g) * (uint32_t)BLOCK_M + (uint32_t)(row0 + lane)] = make_uint2(u0, u1);
       } else {
+        // d = [y > 0] * acc * s, rounded to bf16: the product is rounded first and the ReLU mask applied to the packed
+        // pair as a bit mask (one FMUL2 + F2FP + HSET2.BM + LOP3 per PAIR) -- same bits as select-then-multiply, since
+        // 0 * s rounds to +0 as well.
+        const float4* sc4 = reinterpret_cast<const float4*>(sc);
+        if (bitmask) {
+          // masks as bits (see the forward): halfword mask of pair jp = ((word >> (15 - jp%16)) & 0x00010001) * 0xffff
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 sa = sc4[2 * j4], sb = sc4[2 * j4 + 1];
+            const float2 s2[4] = {make_float2(sa.x, sa.y), make_float2(sa.z, sa.w), make_float2(sb.x, sb.y), make_float2(sb.z, sb.w)};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j4 * 8 + u * 2, jp = j >> 1;
+              const float ra = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
+              const float rb = __uint_as_float(j < 32 ? r0[j + 1] : r1[j - 31]);
+              const float2 v = fmul2(make_float2(ra, rb), s2[u]);
+              const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+              const uint32_t m = (((jp < 16 ? mbits.x : mbits.y) >> (15 - (jp & 15))) & 0x00010001u) * 0xffffu;
+              pk[jp] = *reinterpret_cast<const uint32_t*>(&h) & m;
+            }
+          }
+        } else {
         const uint8_t* yrow = hb + (size_t)(c & 1) * HB_BYTES + my_off + lane * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const uint4 yraw = *reinterpret_cast<const uint4*>(yrow + ((j4 ^ (lane & 7)) * 16));
-          const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&yraw);
+          const uint32_t yw[4] = {yraw.x, yraw.y, yraw.z, yraw.w};
+          const float4 sa = sc4[2 * j4], sb = sc4[2 * j4 + 1];
+          const float2 s2[4] = {make_float2(sa.x, sa.y), make_float2(sa.z, sa.w), make_float2(sb.x, sb.y), make_float2(sb.z, sb.w)};
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float2 yv = __bfloat1622float2(yp[u]);
             const int j = j4 * 8 + u * 2;                          // column within this warp's 64
             const float ra = __uint_as_float(j < 32 ? r0[j] : r1[j - 32]);
             const float rb = __uint_as_float(j < 32 ? r0[j + 1] : r1[j - 31]);
-            const float2 s2 = *reinterpret_cast<const float2*>(sc + j);
-            const float a = (yv.x > 0.f ? ra : 0.f) * s2.x;
-            const float b = (yv.y > 0.f ? rb : 0.f) * s2.y;
-            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h);
+            const float2 v = fmul2(make_float2(ra, rb), s2[u]);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+            pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&h) & gt0_mask_bf16x2(yw[u]);
           }
+        }
         }
         __syncwarp();                                              // every lane has read its row of the mask box
       }
@@ -554,11 +629,15 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
       const int grow = tile * BLOCK_M + row0;
       const bool tl = (p.dbg & 16) && blockIdx.x == 0 && tcount == 5 && ew == 0 && lane == 0;
+      if (bitmask) {                                               // EPI2's masks on their way; EPI1's have landed
+        issue_masks(tile, 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      }
       // ---- EPI1: chunk accumulators -> bf16 -> TMEM (A operand of GEMM2)
       for (int c = 0; c < NCHUNK; ++c) {
         const int buf = c & 1;
         const uint32_t idx = tcount * (buf ? uses1 : uses0) + (uint32_t)(c >> 1);
-        if (BWD) {                                                 // next mask box -> the other slice
+        if (BWD && !bitmask) {                                     // next mask box -> the other slice
           if (lane == 0) tma_store_wait_read<0>();                 // (my TMA store that last read it has retired)
           __syncwarp();
           if (c + 1 < NCHUNK) issue_y(tile, 0, c + 1); else issue_y(tile, 1, 0);
@@ -567,7 +646,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         CNET_TS(tl, 32 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 0, buf ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf], pk, tl ? 33 + 3 * c : -1, tcount);
+        epilogue_chunk(c, 0, buf ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf], pk, tl ? 33 + 3 * c : -1, tcount, tile, bitmask ? read_mask(0, c) : make_uint2(0u, 0u));
         if (p.deferred && c == 0) {                                // GEMM3's accumulator of the previous tile aliases h1
           mbar_wait(&sh->c3_empty, (tcount & 1) ^ 1);
           tcgen05_fence_after();
@@ -576,7 +655,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         if (!no_epi) tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2) + g * 32), pk);
         if (BWD || p.save1) {
           uint8_t* stg = hb + (size_t)buf * HB_BYTES + my_off;     // chunk buffers are idle until EPI2
-          if (lane == 0) tma_store_wait_read<0>();                 // my previous store out of this staging box
+          if (lane == 0) {                                         // my previous store out of this staging box
+            if (chain_stores && (BWD || c >= 1)) tma_store_wait_read<1>();   // (FWD c = 0: EPI3 stored from both slices)
+            else tma_store_wait_read<0>();
+          }
           __syncwarp();
           store_row_sw128(stg, lane, pk);
           fence_proxy_async();
@@ -591,6 +673,10 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         if (lane == 0) mbar_arrive(&sh->h1_full);
         CNET_TS(tl, 34 + 3 * c);
       }
+      if (bitmask) {                                               // my next tile's EPI1 masks on their way
+        issue_masks(tile + (int)gridDim.x, 0);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      }
       // ---- EPI2: chunk accumulators -> bf16 -> shared-memory chunk (A operand of GEMM3)
       for (int c = 0; c < NCHUNK; ++c) {
         const int buf2 = p.deferred ? (c & 1) : 0;
@@ -599,12 +685,14 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         CNET_TS(tl, 44 + 3 * c);
         tcgen05_fence_after();
         uint32_t pk[32];
-        epilogue_chunk(c, 1, buf2 ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf2], pk, tl ? 45 + 3 * c : -1, tcount);
+        epilogue_chunk(c, 1, buf2 ? COL_ACC1 : COL_ACC0, &sh->acc_empty[buf2], pk, tl ? 45 + 3 * c : -1, tcount, tile, bitmask ? read_mask(1, c) : make_uint2(0u, 0u));
         CNET_TS(tl && c == 1, 60);
         const int b = c % p.nhb;
         const uint32_t hidx = tcount * (uint32_t)upt + (uint32_t)(c / p.nhb);
         mbar_wait(&sh->h2_empty[b], (hidx & 1) ^ 1);               // GEMM3 partial that last read this buffer retired
-        if (lane == 0) tma_store_wait_read<0>();                   // ... and so has my TMA store out of it
+        if (lane == 0) {                                           // ... and so has my TMA store out of it
+          if (chain_stores) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
         __syncwarp();
         CNET_TS(tl && c == 1, 61);
         uint8_t* slice = hb + (size_t)b * HB_BYTES + my_off;
@@ -618,7 +706,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           mbar_arrive(&sh->h2_full[b]);
         }
         if (BWD && p.dbias1) box_colsum_bf16(slice, lane, s_x1 + c * NC + g * 64);
-        if (BWD && c + 1 < NCHUNK) {
+        if (BWD && !bitmask && c + 1 < NCHUNK) {
           // mask box of chunk c+1 -> slice (c+1)&1: GEMM3's partial sum for chunk c-1 read it last
           if (c >= 1) mbar_wait(&sh->h2_empty[(c + 1) & 1], (tcount * (uint32_t)upt + (uint32_t)((c - 1) / p.nhb)) & 1);
           if (lane == 0) tma_store_wait_read<0>();
@@ -672,7 +760,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (lane == 0) mbar_arrive(&sh->c3_empty);
         }
       } else {
-        if ((int)(tile + gridDim.x) < num_tiles) {
+        if (!bitmask && (int)(tile + gridDim.x) < num_tiles) {
           if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
           issue_y(tile + gridDim.x, 0, 0);                          // first mask box of my next tile -> slice 0
@@ -740,8 +828,9 @@ static bool pick_variant(int mode, int64_t K1, int64_t n3tot, Variant* v) {
   else if (n3tot <= 128) { v->NH = 1; v->N3 = (int)n3tot; v->nhb = 2; v->c3_col = COL_C3; v->deferred = 0; }
   else if (n3tot <= 256 && n3tot % 32 == 0) { v->NH = 2; v->N3 = (int)(n3tot / 2); v->nhb = 4; v->c3_col = COL_H; v->deferred = 1; }
   else return false;
-  const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES + 
-                       4 * HID * sizeof(float) + sizeof(Shared) + 64;
+  const size_t mask_stage = mode == MODE_BWD ? (size_t)2 * EPI_WARPS * NCHUNK * 32 * 8 : 0;     // bit masks via cp.async
+  const size_t fixed = (size_t)(K1 / 64) * BOX_BYTES + (size_t)v->nhb * HB_BYTES +
+                       4 * HID * sizeof(float) + sizeof(Shared) + 64 + mask_stage;
   const size_t budget = 227 * 1024;
   if (fixed + 3 * (size_t)BOX_BYTES > budget) return false;
   // two boxes per stage (8 MMAs = 512 tensor cycles per barrier round trip) when at least three such stages fit
@@ -778,7 +867,7 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
                  const void* W3, int64_t ldw3, int64_t M, int64_t K1, int64_t n3tot, const float* bias1,
                  const float* logs1, float f1, const float* bias2, const float* logs2, float f2, void* o1, void* o2,
                  int64_t ldh, const void* y1, const void* y2, void* o3, int64_t ldo3, float* dbias1, float* dbias2,
-                 cudaStream_t st) {
+                 void* mask_a, void* mask_b, cudaStream_t st) {
   const int mode = backward ? MODE_BWD : MODE_FWD;
   Variant v;
   if (!pick_variant(mode, K1, n3tot, &v))
@@ -825,6 +914,9 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
   { const char* e = getenv("GLOWK_CNET_DEBUG"); p.dbg = e ? atoi(e) : 0; }
   p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
   p.dbias1 = dbias1; p.dbias2 = dbias2;
+  GLOWK_CHECK_ARG((mask_a != nullptr) == (mask_b != nullptr) && (((uintptr_t)mask_a | (uintptr_t)mask_b) % 8) == 0,
+                  "glowk_cnet: the two ReLU bit masks go together (8-byte aligned)");
+  p.mk[0] = (uint2*)mask_a; p.mk[1] = (uint2*)mask_b;
   p.z = gth ? gth->z : nullptr; p.gather = gth ? 1 : 0;
   if (gth) { p.ld_z = (int)gth->ld_z; p.c0 = (int)gth->c0; p.Cin = (int)gth->Cin; p.H = (int)gth->H; p.W = (int)gth->W; p.ones_col = (int)gth->ones_col; p.flip = gth->flip; }
   else { p.ld_z = p.c0 = p.Cin = p.H = p.W = 0; p.ones_col = -1; p.flip = 0; }
@@ -868,15 +960,20 @@ extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, i
   GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward: ldh too small");
   return cnet::chain_launch(0, nullptr, a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1, bias2, logs2, f2,
                             h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr, nullptr,
-                            (cudaStream_t)stream);
+                            nullptr, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
+extern "C" int64_t glowk_cnet_relu_mask_bytes(int64_t M) {
+  return ((M + glowk::tc::BLOCK_M - 1) / glowk::tc::BLOCK_M) * 8 * glowk::tc::BLOCK_M * 8;
+}
+
+extern "C" int glowk_cnet_forward_implicit_masked(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
                                            int64_t W, int64_t ones_col, void* a1_save, int64_t lda, const void* w1,
                                            int64_t ldw1, const void* w2, int64_t ldw2, const void* w3, int64_t ldw3,
                                            int64_t K1, int64_t hidden, int64_t N3, const float* bias1, const float* logs1,
                                            float f1, const float* bias2, const float* logs2, float f2, float* p3,
-                                           int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* stream) {
+                                           int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* mask1, void* mask2,
+                                                  void* stream) {
   const int64_t M = N * H * W;
   if (M == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(z && w1 && w2 && w3 && p3 && bias1 && logs1 && bias2 && logs2, "glowk_cnet_forward_implicit: null pointer");
@@ -887,7 +984,18 @@ extern "C" int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t
   cnet::Gather g{z, ld_z, c0, Cin, H, W, ones_col, 0};
   return cnet::chain_launch(0, &g, a1_save, a1_save ? lda : K1, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1,
                             bias2, logs2, f2, h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr,
-                            nullptr, (cudaStream_t)stream);
+                            nullptr, mask1, mask2, (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_forward_implicit(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
+                                           int64_t W, int64_t ones_col, void* a1_save, int64_t lda, const void* w1,
+                                           int64_t ldw1, const void* w2, int64_t ldw2, const void* w3, int64_t ldw3,
+                                           int64_t K1, int64_t hidden, int64_t N3, const float* bias1, const float* logs1,
+                                           float f1, const float* bias2, const float* logs2, float f2, float* p3,
+                                           int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* stream) {
+  return glowk_cnet_forward_implicit_masked(z, ld_z, c0, Cin, N, H, W, ones_col, a1_save, lda, w1, ldw1, w2, ldw2, w3, ldw3,
+                                            K1, hidden, N3, bias1, logs1, f1, bias2, logs2, f2, p3, ldp3, h1_save,
+                                            h2_save, ldh, nullptr, nullptr, stream);
 }
 
 extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* w3t, int64_t ldw3t, const void* w2t,
@@ -902,15 +1010,16 @@ extern "C" int glowk_cnet_backward(const void* d3col, int64_t ldd3, const void* 
                   "glowk_cnet_backward: leading dimensions too small");
   // chain order: GEMM1 uses (w3t, logs2 / h2 mask), GEMM2 (w2t, logs1 / h1 mask), GEMM3 w1t
   return cnet::chain_launch(1, nullptr, d3col, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2, nullptr,
-                            logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
+                            logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, nullptr, nullptr, (cudaStream_t)stream);
 }
 
-extern "C" int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
+extern "C" int glowk_cnet_backward_implicit_masked(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
                                             void* d3col_save, int64_t ldd3, const void* w3t, int64_t ldw3t,
                                             const void* w2t, int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t K3,
                                             int64_t hidden, int64_t K1p, const float* logs2, float f2, const float* logs1,
                                             float f1, const void* h2, const void* h1, void* d2, void* d1, int64_t ldh,
-                                            void* da1, int64_t ldda1, float* dbias2, float* dbias1, void* stream) {
+                                            void* da1, int64_t ldda1, float* dbias2, float* dbias1, const void* mask2,
+                                                   const void* mask1, void* stream) {
   const int64_t M = N * H * W;
   if (M == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(du && d3col_save && w3t && w2t && w1t && logs2 && logs1 && h2 && h1 && d2 && d1 && da1,
@@ -920,5 +1029,17 @@ extern "C" int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_
                   "glowk_cnet_backward_implicit: leading dimensions too small");
   cnet::Gather g{du, ldu, 0, Cout, H, W, -1, 1};
   return cnet::chain_launch(1, &g, d3col_save, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, M, K3, K1p, nullptr, logs2, f2,
-                            nullptr, logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (cudaStream_t)stream);
+                            nullptr, logs1, f1, d2, d1, ldh, h2, h1, da1, ldda1, dbias1, dbias2, (void*)mask2, (void*)mask1,
+                            (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int64_t N, int64_t H, int64_t W,
+                                            void* d3col_save, int64_t ldd3, const void* w3t, int64_t ldw3t,
+                                            const void* w2t, int64_t ldw2t, const void* w1t, int64_t ldw1t, int64_t K3,
+                                            int64_t hidden, int64_t K1p, const float* logs2, float f2, const float* logs1,
+                                            float f1, const void* h2, const void* h1, void* d2, void* d1, int64_t ldh,
+                                            void* da1, int64_t ldda1, float* dbias2, float* dbias1, void* stream) {
+  return glowk_cnet_backward_implicit_masked(du, ldu, Cout, N, H, W, d3col_save, ldd3, w3t, ldw3t, w2t, ldw2t, w1t, ldw1t, K3,
+                                             hidden, K1p, logs2, f2, logs1, f1, h2, h1, d2, d1, ldh, da1, ldda1, dbias2,
+                                             dbias1, nullptr, nullptr, stream);
 }

@@ -248,10 +248,18 @@ def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2,
     return p3, h1, h2
 
 
+def cnet_relu_masks(m, device):
+    """Two buffers for the ReLU bit masks of h1 / h2 over m pixels (glowk_cnet_*_implicit_masked)."""
+    nbytes = int(_C.lib().glowk_cnet_relu_mask_bytes(m))
+    return (torch.empty(nbytes // 8, dtype=torch.int64, device=device),
+            torch.empty(nbytes // 8, dtype=torch.int64, device=device))
+
+
 def cnet_forward_implicit(z, n, h, w, c0, cin, k1p, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2, ldp3=None,
-                          save=False, ldh=None, ones_col=-1):
+                          save=False, ldh=None, ones_col=-1, masks=None):
     """glowk_cnet_forward_implicit: conv1's im2col operand is gathered in-kernel from the rows z [n*h*w][ld] fp32.
-    Returns (p3, a1, h1, h2); a1 / h1 / h2 are None unless `save` (training)."""
+    Returns (p3, a1, h1, h2); a1 / h1 / h2 are None unless `save` (training).  masks = (m1, m2) from cnet_relu_masks:
+    also write the ReLU masks of h1 / h2 as bits for cnet_backward_implicit."""
     check_cuda(z, w1, w2, w3)
     assert z.dtype == torch.float32 and z.dim() == 2 and w1.dtype == torch.bfloat16
     m = n * h * w
@@ -263,9 +271,14 @@ def cnet_forward_implicit(z, n, h, w, c0, cin, k1p, w1, w2, w3, hidden, n3, bias
     a1 = torch.empty(m, k1p, device=dev, dtype=torch.bfloat16) if save else None
     h1 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16) if save else None
     h2 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16) if save else None
-    call("glowk_cnet_forward_implicit", ptr(z), z.shape[1], c0, cin, n, h, w, int(ones_col), ptr(a1), k1p, ptr(w1),
-         w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], k1p, hidden, n3, ptr(bias1), ptr(logs1), float(f1),
-         ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1), ptr(h2), ldh)
+    args = (ptr(z), z.shape[1], c0, cin, n, h, w, int(ones_col), ptr(a1), k1p, ptr(w1),
+            w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], k1p, hidden, n3, ptr(bias1), ptr(logs1), float(f1),
+            ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1), ptr(h2), ldh)
+    if masks is not None:
+        assert save, "the bit masks are a by-product of the training forward"
+        call("glowk_cnet_forward_implicit_masked", *args, ptr(masks[0]), ptr(masks[1]))
+    else:
+        call("glowk_cnet_forward_implicit", *args)
     return p3, a1, h1, h2
 
 
@@ -286,7 +299,7 @@ def cnet_backward(d3col, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h
 
 
 def cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, hidden, k1p, logs2, f2, logs1, f1, h2, h1, dbias2=None,
-                           dbias1=None):
+                           dbias1=None, masks=None):
     """glowk_cnet_backward_implicit: the dgrad chain with its first operand (flipped im2col of du) gathered in-kernel.
     Returns (d3col [M][k3p] bf16 -- the conv3 wgrad operand --, d2, d1 [M][ldh] bf16, da1 [M][k1p] bf16)."""
     check_cuda(du, w3t, w2t, w1t, h2, h1)
@@ -299,9 +312,13 @@ def cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, hidden, k1p, l
     d2 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16)
     d1 = torch.empty(m, ldh, device=dev, dtype=torch.bfloat16)
     da1 = torch.empty(m, k1p, device=dev, dtype=torch.bfloat16)
-    call("glowk_cnet_backward_implicit", ptr(du), du.shape[1], cout, n, h, w, ptr(d3col), k3p, ptr(w3t), w3t.shape[1],
-         ptr(w2t), w2t.shape[1], ptr(w1t), w1t.shape[1], k3p, hidden, k1p, ptr(logs2), float(f2), ptr(logs1), float(f1),
-         ptr(h2), ptr(h1), ptr(d2), ptr(d1), ldh, ptr(da1), k1p, ptr(dbias2), ptr(dbias1))
+    args = (ptr(du), du.shape[1], cout, n, h, w, ptr(d3col), k3p, ptr(w3t), w3t.shape[1],
+            ptr(w2t), w2t.shape[1], ptr(w1t), w1t.shape[1], k3p, hidden, k1p, ptr(logs2), float(f2), ptr(logs1), float(f1),
+            ptr(h2), ptr(h1), ptr(d2), ptr(d1), ldh, ptr(da1), k1p, ptr(dbias2), ptr(dbias1))
+    if masks is not None:          # (m1, m2) as written by cnet_forward_implicit: the chain applies m2 first, then m1
+        call("glowk_cnet_backward_implicit_masked", *args, ptr(masks[1]), ptr(masks[0]))
+    else:
+        call("glowk_cnet_backward_implicit", *args)
     return d3col, d2, d1, da1
 
 

@@ -357,14 +357,19 @@ class CouplingNet(nn.Sequential):
         an1, an2 = self[0].actnorm, self[2].actnorm
         if (dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False)
                 and self.in_channels % 2 == 0 and os.environ.get("GLOWK_CNET_IMPLICIT", "1") != "0"):
+            # training: the ReLU masks of h1 / h2 also leave as bits -- the backward chain reads those instead of the
+            # bf16 activations (cnet_backward_implicit; GLOWK_CNET_BITMASK=0: bf16 masks)
+            masks = None
+            if save is not None and self.fused(True) and os.environ.get("GLOWK_CNET_BITMASK", "1") != "0":
+                masks = K.cnet_relu_masks(n * h * w, z.device)
             p3, a1, h1, h2 = K.cnet_forward_implicit(
                 z, n, h, w, 0, self.in_channels, self.k1p, self.packed("w1", dt), self.packed("w2", dt),
                 self.packed("w3", dt), self.hidden_channels, self.n3p, an1.bias.detach().reshape(-1),
                 an1.logs.detach().reshape(-1), an1.logscale_factor, an2.bias.detach().reshape(-1),
                 an2.logs.detach().reshape(-1), an2.logscale_factor, ldp3=self.n3p, save=save is not None,
-                ldh=round_up(self.hidden_channels, 64), ones_col=ones_col)
+                ldh=round_up(self.hidden_channels, 64), ones_col=ones_col, masks=masks)
             if save is not None:
-                save.update(a1=a1, h1=h1, h2=h2)
+                save.update(a1=a1, h1=h1, h2=h2, masks=masks)
             return p3
         a1 = K.im2col_rows(z, n, h, w, 0, self.in_channels, 3, dt, self.k1p, ones_col=ones_col)
         return self.tap_rows_from_a1(a1, dt, save)

@@ -420,7 +420,8 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save, want_ld=False):
                                     tickets=ws.tickets)
     ctx = None
     if save:
-        ctx = dict(x=x, y=z, hrows=hrows, a1=sv["a1"], h1=sv["h1"], h2=sv["h2"], wmat=wmat, winv=winv, idx=idx)
+        ctx = dict(x=x, y=z, hrows=hrows, a1=sv["a1"], h1=sv["h1"], h2=sv["h2"], masks=sv.get("masks"), wmat=wmat,
+                   winv=winv, idx=idx)
     return z, ld_out, ctx
 
 
@@ -507,7 +508,7 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
         d3col, d2, d1, da1 = K.cnet_backward_implicit(
             du, n, h, w, cout, k3p, net.packed("w3t", dt), net.packed("w2t", dt), net.packed("w1t", dt), hid, k1p,
             an2.logs.detach().reshape(-1), an2.logscale_factor, an1.logs.detach().reshape(-1), an1.logscale_factor,
-            h2, h1, dbias2=db2, dbias1=db1)
+            h2, h1, dbias2=db2, dbias1=db1, masks=ctx.get("masks"))
     elif fused:
         d2, d1, da1 = K.cnet_backward(d3col, net.packed("w3t", dt), net.packed("w2t", dt), net.packed("w1t", dt), hid,
                                       k1p, an2.logs.detach().reshape(-1), an2.logscale_factor,

@@ -159,3 +159,61 @@ def test_cnet_backward_implicit_matches_explicit_im2col(n, h, w, c):
     torch.cuda.synchronize()
     assert torch.equal(d3, d3r) and torch.equal(d2, d2r) and torch.equal(d1, d1r) and torch.equal(da1, da1r)
     assert torch.allclose(db2, db2r, rtol=1e-4, atol=1e-4)
+
+
+def _encode_relu_bits(hact, m):
+    """Host restatement of the bit-mask layout of glowk_cnet_*_implicit_masked (include/glowk.h): one 64-bit word per
+    (tile of 128 rows, group of 64 columns, row); column pair jp of the group -> 32-bit word jp // 16, bit
+    15 - jp % 16 (even column) / 31 - jp % 16 (odd column)."""
+    tiles = (m + 127) // 128
+    pos = torch.zeros(tiles * 128, 512, dtype=torch.bool)
+    pos[:m] = hact[:m, :512].float().cpu() > 0
+    pos = pos.view(tiles, 128, 8, 2, 16, 2)                    # tile, row, group, word, jp % 16, parity
+    sh_even = torch.tensor([15 - j for j in range(16)], dtype=torch.int64)
+    words = (pos[..., 0].long() << sh_even).sum(-1) + (pos[..., 1].long() << (sh_even + 16)).sum(-1)   # tile,row,group,word
+    full = words[..., 0] + (words[..., 1] << 32)               # u0 = low half of the 64-bit word
+    return full.permute(0, 2, 1).contiguous().view(-1)         # [tile][group][row]
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 32, 32, 12), (3, 16, 16, 24), (1, 10, 6, 12)])
+def test_cnet_relu_bit_masks(n, h, w, c):
+    """Training forward writes the ReLU masks of h1 / h2 as bits (documented layout); the backward chain fed with them is
+    bit-identical to the chain fed with the bf16 activations."""
+    if not _C.has_tcgen05():
+        pytest.skip("needs sm_100")
+    cin, cout = c // 2, c
+    k1p, n3 = K.round_up(9 * cin, 64), K.round_up(9 * c, 16)
+    k3p = K.round_up(9 * cout, 64)
+    if not (K.cnet_fused_supported(False, k1p, HID, n3) and K.cnet_fused_supported(True, k3p, HID, k1p)):
+        pytest.skip("shape not served by the fused kernels")
+    m = n * h * w
+    g = torch.Generator().manual_seed(n * 31 + h)
+    z = torch.randn(m, c, generator=g).cuda()
+    _, w1, w2, w3, b1, l1, b2, l2 = _mk(8, k1p, n3, 3)
+    w1[:, 9 * cin:] = 0
+    masks = K.cnet_relu_masks(m, z.device)
+    for t in masks:
+        t.fill_(-1)
+    p3, a1, h1, h2 = K.cnet_forward_implicit(z, n, h, w, 0, cin, k1p, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0,
+                                             save=True, masks=masks)
+    p3r, _, h1r, h2r = K.cnet_forward_implicit(z, n, h, w, 0, cin, k1p, w1, w2, w3, HID, n3, b1, l1, 3.0, b2, l2, 3.0,
+                                               save=True)
+    torch.cuda.synchronize()
+    assert torch.equal(p3, p3r) and torch.equal(h1, h1r) and torch.equal(h2, h2r)
+    tiles = (m + 127) // 128
+    rows_ok = (torch.arange(tiles * 128) < m).view(tiles, 1, 128).expand(tiles, 8, 128).reshape(-1)
+    for got, act in ((masks[0], h1), (masks[1], h2)):
+        ref = _encode_relu_bits(act, m)
+        assert torch.equal(got.cpu()[rows_ok], ref[rows_ok])
+    # backward: bits vs bf16 masks
+    du = (torch.randn(m, cout, generator=g) * 0.5).cuda()
+    _, w3t, w2t, w1t, _, _, lb2, lb1 = _mk_bwd(m, k3p, k1p, 5)
+    w3t[:, 9 * cout:] = 0
+    db2r, db2 = torch.zeros(HID, device="cuda"), torch.zeros(HID, device="cuda")
+    ref = K.cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, HID, k1p, lb2, 3.0, lb1, 3.0, h2, h1, dbias2=db2r)
+    got = K.cnet_backward_implicit(du, n, h, w, cout, k3p, w3t, w2t, w1t, HID, k1p, lb2, 3.0, lb1, 3.0, h2, h1, dbias2=db2,
+                                   masks=masks)
+    torch.cuda.synchronize()
+    for a, b, name in zip(got, ref, ("d3col", "d2", "d1", "da1")):
+        assert torch.equal(a, b), name
+    assert torch.allclose(db2, db2r, rtol=1e-5, atol=1e-5)

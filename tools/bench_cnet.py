@@ -119,6 +119,27 @@ def main():
             trace("bwd")
             if int(os.environ["GLOWK_CNET_DEBUG"]) & 16:
                 timeline("bwd")
+        # the path the training step runs: operands gathered in-kernel, ReLU masks as bits or as the bf16 activations
+        n_img, hh = m // 1024, 32
+        if m % 1024 == 0 and k1 == 64 and k3 == 128:
+            c = 12
+            zz = rn(m, c)
+            w1i = (rn(HID, 64) * 0.05).bfloat16(); w1i[:, 54:] = 0
+            w2i, w3i = (rn(HID, HID) * 0.05).bfloat16(), (rn(112, HID) * 0.05).bfloat16()
+            bz = torch.zeros(HID, device=dev)
+            masks = K.cnet_relu_masks(m, dev)
+            for label, mk in (("bf16 masks", None), ("bit masks ", masks)):
+                tfw = timeit(lambda: K.cnet_forward_implicit(zz, n_img, hh, hh, 0, c // 2, 64, w1i, w2i, w3i, HID, 112, bz, l1, 3.0,
+                                                             bz, l2, 3.0, save=True, ones_col=54, masks=mk), a.iters)
+                du = rn(m, c) * 0.5
+                w3ti = w3t.clone(); w3ti[:, 108:] = 0
+                tbw = timeit(lambda: K.cnet_backward_implicit(du, n_img, hh, hh, c, 128, w3ti, w2t, w1t, HID, 64, l2, 3.0, l1, 3.0,
+                                                              h2, h1, dbias2=db2, masks=mk), a.iters)
+                print("implicit, %s : fwd(train) %8.1f us   bwd %8.1f us" % (label, tfw, tbw))
+            if os.environ.get("GLOWK_CNET_DEBUG"):
+                trace("bwd bit masks")
+                if int(os.environ["GLOWK_CNET_DEBUG"]) & 16:
+                    timeline("bwd bit masks")
     else:
         print("bwd fused: shape not supported")
 
