@@ -229,6 +229,11 @@ int glowk_cnet_backward_implicit(const float* du, int64_t ldu, int64_t Cout, int
  * mask1 / mask2: glowk_cnet_relu_mask_bytes(M) bytes each, 8-byte aligned, opaque layout
  * ([tile of 128 rows][8 column groups of 64][128 rows] x 64 bits).  Results are bit-identical to the unmasked calls. */
 int64_t glowk_cnet_relu_mask_bytes(int64_t M);
+int glowk_cnet_forward_masked(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2, int64_t ldw2,
+                              const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden, int64_t N3,
+                              const float* bias1, const float* logs1, float f1, const float* bias2, const float* logs2,
+                              float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save, int64_t ldh, void* mask1,
+                              void* mask2, void* stream);
 int glowk_cnet_forward_implicit_masked(const float* z, int64_t ld_z, int64_t c0, int64_t Cin, int64_t N, int64_t H,
                                        int64_t W, int64_t ones_col, void* a1_save, int64_t lda, const void* w1,
                                        int64_t ldw1, const void* w2, int64_t ldw2, const void* w3, int64_t ldw3,

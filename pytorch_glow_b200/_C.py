@@ -50,6 +50,7 @@ SIGNATURES = {
     "glowk_cnet_fused_supported": [_i32, _i64, _i64, _i64],
     "glowk_cnet_forward": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32,
                            _p, _i64, _p, _p, _i64, _p],
+    "glowk_cnet_forward_masked": [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p, _p, _p],
     "glowk_cnet_forward_implicit": [_p, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64,
                                     _i64, _i64, _i64, _p, _p, _f32, _p, _p, _f32, _p, _i64, _p, _p, _i64, _p],
     "glowk_cnet_relu_mask_bytes": [_i64],

@@ -174,7 +174,7 @@ __device__ __forceinline__ void box_colsum_bf16(const uint8_t* box, int lane, fl
   atomicAdd(acc + 2 * lane + 1, s1);
 }
 
-template <int MODE, int BPS>
+template <int MODE, int BPS, bool MASKS>
 __global__ void __launch_bounds__(THREADS, 1)
 cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w1,
                   const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_w3,
@@ -488,8 +488,8 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     // Backward with bit masks (written by the training forward, 8 bytes per row and chunk half instead of a 128-byte
     // row of the bf16 activation): each lane copies its own row's four words of a phase into shared memory with
     // cp.async one whole phase ahead (no register waits on HBM latency), and reads them back per chunk.
-    const bool bitmask = BWD && p.mk[0] != nullptr;
-    const bool want_mask = !BWD && p.mk[0] != nullptr;
+    constexpr bool bitmask = BWD && MASKS;        // (template parameter: every instance carries one mask path only)
+    constexpr bool want_mask = !BWD && MASKS;
     uint8_t* s_mask = reinterpret_cast<uint8_t*>(sh + 1);         // [2 phases][EPI_WARPS][NCHUNK][32 lanes] x 8 B (BWD only)
     auto mask_slot = [&](int ph, int c) -> uint32_t {
       return smem_u32(s_mask) + (uint32_t)((((ph * EPI_WARPS + ew) * NCHUNK + c) * 32 + lane) * 8);
@@ -848,9 +848,9 @@ bool chain_supported(int backward, int64_t K1, int64_t hidden, int64_t n3tot) {
   return hidden == HID && tc_available() && pick_variant(backward ? MODE_BWD : MODE_FWD, K1, n3tot, &v);
 }
 
-template <int MODE, int BPS>
+template <int MODE, int BPS, bool MASKS>
 static int launch_chain(const CUtensorMap* tm, const Params& p, size_t smem, cudaStream_t st) {
-  auto kern = cnet_chain_kernel<MODE, BPS>;
+  auto kern = cnet_chain_kernel<MODE, BPS, MASKS>;
   GLOWK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -921,8 +921,13 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
   if (gth) { p.ld_z = (int)gth->ld_z; p.c0 = (int)gth->c0; p.Cin = (int)gth->Cin; p.H = (int)gth->H; p.W = (int)gth->W; p.ones_col = (int)gth->ones_col; p.flip = gth->flip; }
   else { p.ld_z = p.c0 = p.Cin = p.H = p.W = 0; p.ones_col = -1; p.flip = 0; }
   p.save_a = gth_save_a;
-  if (v.bps == 2) return backward ? launch_chain<MODE_BWD, 2>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 2>(tm, p, v.smem, st);
-  return backward ? launch_chain<MODE_BWD, 1>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 1>(tm, p, v.smem, st);
+  const bool mk = mask_a != nullptr;
+  if (v.bps == 2) {
+    if (backward) return mk ? launch_chain<MODE_BWD, 2, true>(tm, p, v.smem, st) : launch_chain<MODE_BWD, 2, false>(tm, p, v.smem, st);
+    return mk ? launch_chain<MODE_FWD, 2, true>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 2, false>(tm, p, v.smem, st);
+  }
+  if (backward) return mk ? launch_chain<MODE_BWD, 1, true>(tm, p, v.smem, st) : launch_chain<MODE_BWD, 1, false>(tm, p, v.smem, st);
+  return mk ? launch_chain<MODE_FWD, 1, true>(tm, p, v.smem, st) : launch_chain<MODE_FWD, 1, false>(tm, p, v.smem, st);
 }
 
 int debug_trace(unsigned long long* out16) {
@@ -948,11 +953,11 @@ extern "C" int glowk_cnet_fused_supported(int backward, int64_t K1, int64_t hidd
   return cnet::chain_supported(backward, K1, hidden, N3) ? 1 : 0;
 }
 
-extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2,
+extern "C" int glowk_cnet_forward_masked(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2,
                                   int64_t ldw2, const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden,
                                   int64_t N3, const float* bias1, const float* logs1, float f1, const float* bias2,
                                   const float* logs2, float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save,
-                                  int64_t ldh, void* stream) {
+                                  int64_t ldh, void* mask1, void* mask2, void* stream) {
   if (M == 0) return GLOWK_OK;
   GLOWK_CHECK_ARG(a1 && w1 && w2 && w3 && p3 && bias1 && logs1 && bias2 && logs2, "glowk_cnet_forward: null pointer");
   GLOWK_CHECK_ARG(hidden == cnet::HID, "glowk_cnet_forward: hidden must be %d", cnet::HID);
@@ -960,7 +965,16 @@ extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, i
   GLOWK_CHECK_ARG((!h1_save && !h2_save) || ldh >= hidden, "glowk_cnet_forward: ldh too small");
   return cnet::chain_launch(0, nullptr, a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, N3, bias1, logs1, f1, bias2, logs2, f2,
                             h1_save, h2_save, ldh ? ldh : hidden, nullptr, nullptr, p3, ldp3, nullptr, nullptr,
-                            nullptr, nullptr, (cudaStream_t)stream);
+                            mask1, mask2, (cudaStream_t)stream);
+}
+
+extern "C" int glowk_cnet_forward(const void* a1, int64_t lda, const void* w1, int64_t ldw1, const void* w2,
+                                  int64_t ldw2, const void* w3, int64_t ldw3, int64_t M, int64_t K1, int64_t hidden,
+                                  int64_t N3, const float* bias1, const float* logs1, float f1, const float* bias2,
+                                  const float* logs2, float f2, float* p3, int64_t ldp3, void* h1_save, void* h2_save,
+                                  int64_t ldh, void* stream) {
+  return glowk_cnet_forward_masked(a1, lda, w1, ldw1, w2, ldw2, w3, ldw3, M, K1, hidden, N3, bias1, logs1, f1, bias2, logs2,
+                                   f2, p3, ldp3, h1_save, h2_save, ldh, nullptr, nullptr, stream);
 }
 
 extern "C" int64_t glowk_cnet_relu_mask_bytes(int64_t M) {

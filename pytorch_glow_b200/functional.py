@@ -231,9 +231,11 @@ def cnet_fused_supported(backward, k1, hidden, n3):
     return bool(_C.lib().glowk_cnet_fused_supported(int(bool(backward)), int(k1), int(hidden), int(n3)))
 
 
-def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2, ldp3=None, save=False, ldh=None):
+def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2, ldp3=None, save=False, ldh=None,
+                 masks=None):
     """The coupling net's three convs in one tcgen05 kernel (glowk_cnet_forward).  a1: [M][k1p] bf16 im2col rows.
-    Returns (p3 [M][ldp3] fp32, h1, h2) with h1/h2 [M][ldh] bf16 when `save`, else None."""
+    Returns (p3 [M][ldp3] fp32, h1, h2) with h1/h2 [M][ldh] bf16 when `save`, else None.  masks: see
+    cnet_forward_implicit."""
     check_cuda(a1, w1, w2, w3)
     assert a1.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16
     m, k1 = a1.shape
@@ -242,9 +244,14 @@ def cnet_forward(a1, w1, w2, w3, hidden, n3, bias1, logs1, f1, bias2, logs2, f2,
     p3 = torch.empty(m, ldp3, device=a1.device, dtype=torch.float32)
     h1 = torch.empty(m, ldh, device=a1.device, dtype=torch.bfloat16) if save else None
     h2 = torch.empty(m, ldh, device=a1.device, dtype=torch.bfloat16) if save else None
-    call("glowk_cnet_forward", ptr(a1), k1, ptr(w1), w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], m, k1,
-         hidden, n3, ptr(bias1), ptr(logs1), float(f1), ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1),
-         ptr(h2), ldh)
+    args = (ptr(a1), k1, ptr(w1), w1.shape[1], ptr(w2), w2.shape[1], ptr(w3), w3.shape[1], m, k1,
+            hidden, n3, ptr(bias1), ptr(logs1), float(f1), ptr(bias2), ptr(logs2), float(f2), ptr(p3), ldp3, ptr(h1),
+            ptr(h2), ldh)
+    if masks is not None:
+        assert save, "the bit masks are a by-product of the training forward"
+        call("glowk_cnet_forward_masked", *args, ptr(masks[0]), ptr(masks[1]))
+    else:
+        call("glowk_cnet_forward", *args)
     return p3, h1, h2
 
 

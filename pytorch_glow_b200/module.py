@@ -355,7 +355,9 @@ class CouplingNet(nn.Sequential):
         bf16 path conv1 is an implicit GEMM: the kernel gathers its im2col operand itself (no glowk_im2col_rows, no
         a1 in HBM when sampling).  `save`, if a dict, receives a1 / h1 / h2 for the backward pass."""
         an1, an2 = self[0].actnorm, self[2].actnorm
-        if (dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False)
+        # (A/B switch GLOWK_CNET_IMPLICIT_TRAIN=0: the training forward takes its conv1 operand from glowk_im2col_rows)
+        implicit_ok = save is None or os.environ.get("GLOWK_CNET_IMPLICIT_TRAIN", "1") != "0"
+        if (dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False) and implicit_ok
                 and self.in_channels % 2 == 0 and os.environ.get("GLOWK_CNET_IMPLICIT", "1") != "0"):
             # training: the ReLU masks of h1 / h2 also leave as bits -- the backward chain reads those instead of the
             # bf16 activations (cnet_backward_implicit; GLOWK_CNET_BITMASK=0: bf16 masks)
@@ -372,9 +374,9 @@ class CouplingNet(nn.Sequential):
                 save.update(a1=a1, h1=h1, h2=h2, masks=masks)
             return p3
         a1 = K.im2col_rows(z, n, h, w, 0, self.in_channels, 3, dt, self.k1p, ones_col=ones_col)
-        return self.tap_rows_from_a1(a1, dt, save)
+        return self.tap_rows_from_a1(a1, dt, save, want_masks=True)
 
-    def tap_rows_from_a1(self, a1, dt, save=None):
+    def tap_rows_from_a1(self, a1, dt, save=None, want_masks=False):
         """The three GEMMs of the coupling net on a1 = im2col(z1) ([P][k1p]); returns P3 rows [P][n3p] fp32.
 
         Performs the data-dependent ActNorm init of the two hidden ActNorms on the first training
@@ -387,13 +389,17 @@ class CouplingNet(nn.Sequential):
         if dt == _C.BF16 and not (an1.needs_init or an2.needs_init) and self.fused(False):
             # one tcgen05 kernel for the three convs: h1 stays in tensor memory, h2 in shared memory
             # (csrc/cnet_fused_sm100.cu); bit-identical to the three GEMMs below
+            masks = None
+            if (want_masks and save is not None and self.fused(True) and self.out_channels % 2 == 0
+                    and os.environ.get("GLOWK_CNET_IMPLICIT", "1") != "0" and os.environ.get("GLOWK_CNET_BITMASK", "1") != "0"):
+                masks = K.cnet_relu_masks(a1.shape[0], a1.device)          # read by cnet_backward_implicit (rows path)
             p3, h1, h2 = K.cnet_forward(a1, w1, self.packed("w2", dt), self.packed("w3", dt), hid, self.n3p,
                                         an1.bias.detach().reshape(-1), an1.logs.detach().reshape(-1),
                                         an1.logscale_factor, an2.bias.detach().reshape(-1),
                                         an2.logs.detach().reshape(-1), an2.logscale_factor, ldp3=self.n3p,
-                                        save=save is not None, ldh=kh)
+                                        save=save is not None, ldh=kh, masks=masks)
             if save is not None:
-                save.update(a1=a1, h1=h1, h2=h2)
+                save.update(a1=a1, h1=h1, h2=h2, masks=masks)
             return p3
         if an1.needs_init:
             an1.initialize_from_rows(K.gemm(a1, w1, hid, self.k1p, _C.EPI_STORE, out_dtype=_C.F32))
