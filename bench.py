@@ -330,20 +330,21 @@ def kernel_rooflines(device, B, shape, hidden, peaks):
     fwd_flops = 2.0 * M * (9 * cin * hidden + hidden * hidden + hidden * 9 * C)
     bwd_flops = 2.0 * M * (k3p * hidden + hidden * hidden + hidden * k1p)
     fused = KF.cnet_fused_supported(False, k1p, hidden, n3p) and KF.cnet_fused_supported(True, k3p, hidden, k1p)
+    masks = KF.cnet_relu_masks(M, device) if fused else None        # ReLU masks of h1 / h2 as bits (128 B per pixel)
     # (id, description, launch, algorithmic bytes, algorithmic flops or None)
     cases = []
     if fused:
         cases += [
             ("cnet_bwd", "cnet_chain_kernel<BWD>: dgrad3 -> ReLU'/ActNorm -> dgrad2 -> ReLU'/ActNorm -> dgrad1 fused (M=%d, "
-             "K3=%d, hidden=%d, K1p=%d); reads du (in-kernel flipped im2col) + the two saved activations (masks), writes d3col, d2, d1, dA1" % (M, k3p, hidden, k1p),
+             "K3=%d, hidden=%d, K1p=%d); reads du (in-kernel flipped im2col) + the two ReLU masks as bits, writes d3col, d2, d1, dA1" % (M, k3p, hidden, k1p),
              lambda i: KF.cnet_backward_implicit(dus[i % 2], B, H, W, C, k3p, w3t, w2t, w1t, hidden, k1p, logs, 3.0, logs, 3.0,
-                                                 hs[i], hs[(i + 1) % R], dbias2=dbias),
-             4.0 * M * C + 2.0 * M * (k3p + 4 * hidden + k1p), bwd_flops),
+                                                 hs[i], hs[(i + 1) % R], dbias2=dbias, masks=masks),
+             4.0 * M * C + 128.0 * M + 2.0 * M * (k3p + 2 * hidden + k1p), bwd_flops),
             ("cnet_fwd_train", "cnet_chain_kernel<FWD>, training: implicit conv1 -> conv2 -> conv3 fused, a1 / h1 / h2 stored "
-             "once for the backward pass (M=%d)" % M,
+             "once for the backward pass (+ their ReLU masks as bits) (M=%d)" % M,
              lambda i: KF.cnet_forward_implicit(zs[i], B, H, W, 0, cin, k1p, w1, w2, w3, hidden, n3p, bias, logs, 3.0, bias, logs,
-                                                3.0, save=True, ones_col=9 * cin),
-             M * (4.0 * cin + 4.0 * n3p + 2.0 * k1p + 4.0 * hidden), fwd_flops),
+                                                3.0, save=True, ones_col=9 * cin, masks=masks),
+             M * (4.0 * cin + 4.0 * n3p + 2.0 * k1p + 4.0 * hidden + 128.0), fwd_flops),
             ("cnet_fwd_sample", "cnet_chain_kernel<FWD>, sampling: implicit conv1 -> conv2 -> conv3 fused, hidden activations "
              "never leave the SM (M=%d)" % M,
              lambda i: KF.cnet_forward_implicit(zs[i], B, H, W, 0, cin, k1p, w1, w2, w3, hidden, n3p, bias, logs, 3.0, bias, logs, 3.0),

@@ -129,10 +129,21 @@ def lib():
 
 
 def check_cuda(*tensors):
+    """Every tensor must live on the CURRENT CUDA device: `call` launches on torch's current stream of that device
+    (one process per GPU sets it once; under torch.nn.DataParallel each replica thread has its own)."""
+    cur = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise GlowkError("pytorch_glow_b200 runs on CUDA tensors only (got a %s tensor); "
                              "there is no CPU fallback" % t.device)
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            raise GlowkError("tensor on cuda:%d but the current device is cuda:%d: wrap the call in "
+                             "torch.cuda.device(tensor.device) (kernels launch on the current device's stream)"
+                             % (t.device.index, cur))
 
 
 def ptr(t):
