@@ -653,6 +653,16 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
         CNET_TS(tl && c == 1, 58);
         if (!no_epi) tmem_st32(lane_taddr + (uint32_t)(COL_H + c * (NC / 2) + g * 32), pk);
+        // GEMM2 starts when the LAST chunk of every warp is in tensor memory: that chunk is published before its copy
+        // for the backward pass / the weight gradient leaves (the earlier chunks hide the tcgen05.st behind that copy)
+        auto publish = [&]() {
+          tmem_st_wait();
+          CNET_TS(tl && c == 1, 59);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh->h1_full);
+        };
+        if (c == NCHUNK - 1) publish();
         if (BWD || p.save1) {
           uint8_t* stg = hb + (size_t)buf * HB_BYTES + my_off;     // chunk buffers are idle until EPI2
           if (lane == 0) {                                         // my previous store out of this staging box
@@ -666,11 +676,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           if (lane == 0) { tma_store_2d(&tm_o1, stg, c * NC + g * 64, grow); tma_store_commit(); }
           if (BWD && p.dbias2) box_colsum_bf16(stg, lane, s_x2 + c * NC + g * 64);
         }
-        tmem_st_wait();
-        CNET_TS(tl && c == 1, 59);
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->h1_full);
+        if (c != NCHUNK - 1) publish();
         CNET_TS(tl, 34 + 3 * c);
       }
       if (bitmask) {                                               // my next tile's EPI1 masks on their way
