@@ -52,7 +52,7 @@ struct Shared {
   uint64_t ring_full[MAX_STAGES], ring_empty[MAX_STAGES];
   uint64_t a_full, a_empty;
   uint64_t acc_full[2], acc_empty[2];
-  uint64_t h1_full;
+  uint64_t h1_full[NCHUNK];     // chunk c of h1 / d2 is in tensor memory (all epilogue warps)
   uint64_t h2_full[MAX_HB], h2_empty[MAX_HB];
   uint64_t c3_full, c3_empty;
   uint64_t y_bar[2 * EPI_WARPS];   // backward: two mask boxes in flight per epilogue warp
@@ -61,7 +61,7 @@ struct Shared {
 
 struct Params {
   int M, K1B, N3, NH, nhb, c3_col, deferred, nstages, bps;
-  int save1, save2, dbg;
+  int save1, save2, dbg, pipe2;
   // ReLU bit masks of the two hidden activations, one uint2 (64 columns) per (tile, chunk half, row): written by the
   // training forward (mk[ph] = mask of the activation EPI(ph) produces), read by the backward (mask EPI(ph) applies)
   uint2* mk[2];
@@ -89,13 +89,22 @@ __device__ unsigned long long g_cnet_trace[16];
 //             [44+3c] EPI2 chunk c: acc_full seen  [45+3c] released  [46+3c] h2 chunk published
 //             [56] c3_full seen  [57] c3 drained
 __device__ unsigned long long g_cnet_timeline[64];
+// Profiling aids are compiled in only with -DGLOWK_CNET_TRACE=1 (GLOWK_CNET_TRACE=1 python __graft_entry__.py --force):
+// the time stamps and wait counters of ~80 sites cost instruction-cache space in every role's hot loop.
+#ifndef GLOWK_CNET_TRACE
+#define GLOWK_CNET_TRACE 0
+#endif
+#if GLOWK_CNET_TRACE
 #define CNET_TS(on, id) do { if (on) g_cnet_timeline[id] = (unsigned long long)clock64(); } while (0)
 __device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, bool on, unsigned long long& acc) {
-  if (!on) { mbar_wait(bar, parity); return; }
-  const long long t0 = clock64();
+  const long long t0 = on ? clock64() : 0;
   mbar_wait(bar, parity);
-  acc += (unsigned long long)(clock64() - t0);
+  if (on) acc += (unsigned long long)(clock64() - t0);
 }
+#else
+#define CNET_TS(on, id) do { (void)(on); } while (0)
+__device__ __forceinline__ void wait_t(uint64_t* bar, uint32_t parity, bool, unsigned long long&) { mbar_wait(bar, parity); }
+#endif
 // non-blocking probe: lets the issuing warp start a barrier read a stage ahead of needing its answer
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -210,7 +219,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     for (int s = 0; s < p.nstages; ++s) { mbar_init(&sh->ring_full[s], 1); mbar_init(&sh->ring_empty[s], 1); }
     mbar_init(&sh->a_full, p.gather ? GATHER_WARPS : 1); mbar_init(&sh->a_empty, 1);
     for (int g = 0; g < 2; ++g) { mbar_init(&sh->acc_full[g], 1); mbar_init(&sh->acc_empty[g], EPI_WARPS); }
-    mbar_init(&sh->h1_full, EPI_WARPS * NCHUNK);
+    for (int c = 0; c < NCHUNK; ++c) mbar_init(&sh->h1_full[c], EPI_WARPS);
     for (int b = 0; b < p.nhb; ++b) { mbar_init(&sh->h2_full[b], EPI_WARPS); mbar_init(&sh->h2_empty[b], 1); }
     mbar_init(&sh->c3_full, 1); mbar_init(&sh->c3_empty, EPI_WARPS);
     for (int q = 0; q < 2 * EPI_WARPS; ++q) mbar_init(&sh->y_bar[q], 1);
@@ -374,8 +383,26 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
       if (elect_one_sync()) tcgen05_commit(&sh->a_empty);
       __syncwarp();
       // ---- GEMM2: A = h1 / d2 in TMEM (bf16 pairs: 16 k = 8 columns); GEMM3 partial sums interleaved
-      wait_t(&sh->h1_full, tcount & 1, tr, w3);
-      CNET_TS(tl, 10);
+      // One stage of a column chunk: BPS k-blocks of W2 against the matching h1 / d2 columns.  (Kept free of anything
+      // else: every extra instruction in this loop shows up in the tensor pipe's duty cycle.)
+      auto gemm2_stage = [&](uint32_t d, int kb) {
+        acquire(w5);
+        const uint64_t bdesc0 = ring_desc + (uint64_t)((uint32_t)stage * stage16);
+        const uint32_t ta = tmem_base + (uint32_t)(COL_H + kb * 32);
+        if (elect_one_sync()) {
+          if (!no_mma) {
+#pragma unroll
+            for (int bb = 0; bb < BPS; ++bb) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+                tcgen05_mma_bf16_ts(d, ta + (uint32_t)(bb * 32 + k * 8), bdesc0 + (uint64_t)(bb * (BOX_BYTES / 16) + k * 2),
+                                    idesc_c, (kb | bb | k) != 0);
+            }
+          }
+          tcgen05_commit(&sh->ring_empty[stage]);
+        }
+        advance();
+      };
       for (int c = 0; c < NCHUNK; ++c) {
         // deferred layout: [384,512) is free while GEMM2 runs -> ping-pong, EPI2 of chunk c overlaps GEMM2 of chunk c+1
         const int buf2 = p.deferred ? (c & 1) : 0;
@@ -383,24 +410,24 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         wait_t(&sh->acc_empty[buf2], (idx & 1) ^ 1, tr, w4);
         CNET_TS(tl, 11 + 3 * c);
         const uint32_t d = tmem_base + (uint32_t)(buf2 ? COL_ACC1 : COL_ACC0);
+        if (c == 0 && p.pipe2) {
+          // The first column chunk starts as soon as its accumulator is free (EPI1 has drained GEMM1's third chunk) and
+          // consumes h1 / d2 chunk by chunk as the epilogue publishes it: three quarters of it run under EPI1's last
+          // chunk instead of after it.  (Its own loop: the other chunks' issue loop stays as it was.)
+#pragma unroll 1
+          for (int q = 0; q < NCHUNK; ++q) {
+            wait_t(&sh->h1_full[q], tcount & 1, tr, w3);
 #pragma unroll
-        for (int kb = 0; kb < HID / BLOCK_K; kb += BPS) {
-          acquire(w5);
-          const uint64_t bdesc0 = ring_desc + (uint64_t)((uint32_t)stage * stage16);
-          const uint32_t ta = tmem_base + (uint32_t)(COL_H + kb * 32);
-          if (elect_one_sync()) {
-            if (!no_mma) {
-#pragma unroll
-              for (int bb = 0; bb < BPS; ++bb) {
-#pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-                  tcgen05_mma_bf16_ts(d, ta + (uint32_t)(bb * 32 + k * 8), bdesc0 + (uint64_t)(bb * (BOX_BYTES / 16) + k * 2),
-                                      idesc_c, (kb | bb | k) != 0);
-              }
-            }
-            tcgen05_commit(&sh->ring_empty[stage]);
+            for (int kb = 0; kb < NC / BLOCK_K; kb += BPS) gemm2_stage(d, q * (NC / BLOCK_K) + kb);
           }
-          advance();
+          CNET_TS(tl, 10);
+        } else {
+          if (c == 0) {
+            for (int q = 0; q < NCHUNK; ++q) wait_t(&sh->h1_full[q], tcount & 1, tr, w3);
+            CNET_TS(tl, 10);
+          }
+#pragma unroll
+          for (int kb = 0; kb < HID / BLOCK_K; kb += BPS) gemm2_stage(d, kb);
         }
         if (elect_one_sync()) tcgen05_commit(&sh->acc_full[buf2]);
         __syncwarp();
@@ -660,7 +687,7 @@ cnet_chain_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
           CNET_TS(tl && c == 1, 59);
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh->h1_full);
+          if (lane == 0) mbar_arrive(&sh->h1_full[c]);
         };
         if (c == NCHUNK - 1) publish();
         if (BWD || p.save1) {
@@ -918,6 +945,10 @@ int chain_launch(int backward, const Gather* gth, const void* A, int64_t lda, co
   p.deferred = v.deferred; p.nstages = v.nstages; p.bps = v.bps;
   p.save1 = o1 != nullptr; p.save2 = o2 != nullptr;
   { const char* e = getenv("GLOWK_CNET_DEBUG"); p.dbg = e ? atoi(e) : 0; }
+  // GEMM2's first column chunk consumes h1 / d2 chunk by chunk as EPI1 publishes it (bit 0: backward, bit 1: forward)
+  // Measured (profiles/r2_cnet_experiments_session3.log): backward -5 %; forward in the deferred layout (level 2) -10 %,
+  // forward otherwise within the noise -> on for those two.  GLOWK_CNET_PIPE2 = bit mask {1: backward, 2: forward}.
+  { const char* e = getenv("GLOWK_CNET_PIPE2"); p.pipe2 = e ? ((atoi(e) >> (backward ? 0 : 1)) & 1) : (backward || v.deferred); }
   p.bias1 = bias1; p.logs1 = logs1; p.bias2 = bias2; p.logs2 = logs2; p.f1 = f1; p.f2 = f2;
   p.dbias1 = dbias1; p.dbias2 = dbias2;
   GLOWK_CHECK_ARG((mask_a != nullptr) == (mask_b != nullptr) && (((uintptr_t)mask_a | (uintptr_t)mask_b) % 8) == 0,
