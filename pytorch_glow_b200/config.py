@@ -11,6 +11,15 @@ conv_dtype = "auto"
 # (rows_path.py) whenever the model fits those kernels; False forces the per-layer NCHW kernels.
 use_rows_path = True
 
+# Activation recompute for training (the exact inverse network/model.py:119-154 is what makes it
+# possible in a flow).  False: every FlowStep keeps a1 / h1 / h2 / their ReLU masks / the coupling's (shift, scale) for
+# its backward pass (~2.4 KB per pixel at 12 channels: ~100 MB per 64x64 image).  True: a step keeps only its input
+# and output rows (96 B per pixel; the output is the next step's input anyway) and its backward pass re-runs the fused
+# coupling-net forward on z1 -- which the coupling leaves untouched in the output -- to rebuild the rest, bit for bit:
+# ~20x less activation memory for one more fused forward per step (~ +20 % step time).  GLOWK_RECOMPUTE=1 sets it.
+import os as _os
+recompute_activations = _os.environ.get("GLOWK_RECOMPUTE", "0") == "1"
+
 
 def resolve_conv_dtype(hidden_channels, override=None):
     mode = override or conv_dtype

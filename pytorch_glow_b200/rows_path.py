@@ -410,19 +410,42 @@ def _step_forward(step, x, n, c, h, w, ld, ws, save, want_ld=False):
         z = K.rows_actnorm_mix(x, wm, idx, b, l, an.logscale_factor, reverse=False)
     net = step.f
     dt = net.dtype(step.conv_dtype)
-    sv = {} if save else None
-    p3 = net.tap_rows_from_rows(z, n, h, w, dt, sv, ones_col=_ones_col(net, dt) if save else -1)
+    # activation recompute (config.recompute_activations): nothing of the coupling net is kept, see _recompute
+    keep = save and not (config.recompute_activations and not an.needs_init
+                         and not (net[0].actnorm.needs_init or net[2].actnorm.needs_init))
+    sv = {} if keep else None
+    p3 = net.tap_rows_from_rows(z, n, h, w, dt, sv, ones_col=_ones_col(net, dt) if keep else -1)
     c3 = net[4]
     affine = step.coupling == 'affine'
     ld_out, hrows = K.rows_coupling(p3, c3.bias.detach(), c3.logs.detach().reshape(-1), z, n, h, w, affine, False,
-                                    c3.logscale_factor, save_h=save, ld_in=ld, want_ld=want_ld or ld is not None, an_logs=l,
+                                    c3.logscale_factor, save_h=keep, ld_in=ld, want_ld=want_ld or ld is not None, an_logs=l,
                                     an_f=an.logscale_factor, logabsdet=logabsdet, sign=1.0, partials=ws.partials,
                                     tickets=ws.tickets)
     ctx = None
-    if save:
+    if keep:
         ctx = dict(x=x, y=z, hrows=hrows, a1=sv["a1"], h1=sv["h1"], h2=sv["h2"], masks=sv.get("masks"), wmat=wmat,
                    winv=winv, idx=idx)
+    elif save:
+        ctx = dict(x=x, y=z, recompute=dt, wmat=wmat, winv=winv, idx=idx)
     return z, ld_out, ctx
+
+
+def _recompute(step, ctx, n, h, w):
+    """Rebuild what _step_forward did not keep (config.recompute_activations) from the step's OUTPUT rows: the coupling
+    leaves z1 -- the coupling net's input -- untouched, so the fused forward on y[:, :C/2] reproduces a1 / h1 / h2 / the
+    ReLU masks bit for bit, and the tap sum of its P3 rows + the Conv2dZeros scale reproduce the coupling's (shift, scale)
+    pre-activations with the coupling kernel's own arithmetic."""
+    net = step.f
+    dt = ctx.pop("recompute")
+    sv = {}
+    p3 = net.tap_rows_from_rows(ctx["y"], n, h, w, dt, sv, ones_col=_ones_col(net, dt))
+    c3 = net[4]
+    cout = net.out_channels
+    u = torch.empty(n * h * w, cout, device=p3.device, dtype=torch.float32)
+    K.rows_tapsum(p3, u, 0, cout, n, h, w)
+    hrows = K.actnorm(u.view(n * h * w, cout, 1, 1), c3.bias.detach().reshape(-1), c3.logs.detach().reshape(-1),
+                      c3.logscale_factor, False, out=u.view(n * h * w, cout, 1, 1)).view(n * h * w, cout)
+    ctx.update(hrows=hrows, a1=sv["a1"], h1=sv["h1"], h2=sv["h2"], masks=sv.get("masks"))
 
 
 def _step_reverse(step, x, n, c, h, w, ws, ld=None, want_ld=False):
@@ -480,6 +503,8 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
     kh = round_up(hid, 64)
     affine = step.coupling == 'affine'
     cout = net.out_channels
+    if "recompute" in ctx:
+        _recompute(step, ctx, n, h, w)
     h1, h2, a1 = ctx["h1"], ctx["h2"], ctx["a1"]
     dt = _C.BF16 if h1.dtype == torch.bfloat16 else _C.F32
     dev = dy.device

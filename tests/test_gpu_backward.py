@@ -345,3 +345,44 @@ def test_fused_loss_head_matches_layer_composition(monkeypatch):
     with torch.no_grad():
         z2, nll2, _ = glow.normal_flow(x, None, noise=noise)
     assert rel_err(nll2, out["0"][1]) < 1e-6 and rel_err(z2, out["0"][0]) < 1e-6
+
+
+def test_activation_recompute_same_gradients_less_memory():
+    """config.recompute_activations: a FlowStep keeps only its input / output rows and its backward pass re-runs the
+    fused coupling-net forward on z1 (untouched by the coupling, network/model.py:105-115) -- same loss, same gradients
+    (the recomputed tensors are bit-identical; the column-sum atomics are the only run-to-run difference), a fraction of
+    the activation memory."""
+    from pytorch_glow_b200 import config
+    hps = make_hps((32, 32, 3), K=4, L=2, hidden_channels=512, coupling="affine", permutation="invconv", batch=8)
+    np.random.seed(5); torch.manual_seed(5)
+    glow = G.Glow(hps)
+    sd = randomize_({k: v.clone() for k, v in glow.state_dict().items()}, 7, coupling_std=0.01)
+    adopt(glow, sd)
+    glow.flow.set_conv_dtype("bf16")
+    glow = glow.to(DEV).train()
+    g = torch.Generator().manual_seed(3)
+    x = cu(torch.rand(8, 3, 32, 32, generator=g))
+    noise = cu(torch.rand(8, 3, 32, 32, generator=g) / 256)
+    out = {}
+    old = config.recompute_activations
+    try:
+        for rec in (False, True):
+            config.recompute_activations = rec
+            glow.zero_grad(set_to_none=True)
+            torch.cuda.synchronize(); torch.cuda.reset_peak_memory_stats()
+            base = torch.cuda.memory_allocated()
+            z, nll, _ = glow.normal_flow(x, None, noise=noise)
+            loss = G.Glow.generative_loss(nll)
+            held = torch.cuda.memory_allocated() - base          # what the autograd node keeps for the backward pass
+            loss.backward()
+            torch.cuda.synchronize()
+            out[rec] = (float(loss), held, {k: p.grad.clone() for k, p in glow.named_parameters() if p.grad is not None})
+    finally:
+        config.recompute_activations = old
+    assert out[True][0] == out[False][0]
+    assert out[True][2].keys() == out[False][2].keys() and len(out[True][2]) > 40
+    worst = max(grad_rel(out[True][2][k], out[False][2][k]) for k in out[False][2])
+    print("recompute: loss %.6f, kept %.1f MB vs %.1f MB, worst grad rel diff %.2e"
+          % (out[True][0], out[True][1] / 2 ** 20, out[False][1] / 2 ** 20, worst))
+    assert worst < 1e-4
+    assert out[True][1] < 0.25 * out[False][1]
