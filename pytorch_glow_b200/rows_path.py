@@ -548,7 +548,7 @@ def _step_backward(step, ctx, dy, dld, n, c, h, w, plan):
                     an1.logscale_factor, y=h1, dlogs=dl1, dbias=db1, out_dtype=dt, ldo=kh)
     # (4) the three weight gradients (conv3 tap form, conv2, conv1 im2col form): side stream, see GradPlan.wgrads
     plan.wgrads([(d3col, h2, k3p, hid, plan.view(step, "w3")), (d2, h1, hid, hid, dw2),
-                 (d1, a1, hid, k1p, plan.view(step, "w1"))], (d3col, d2, d1))
+                 (d1, a1, hid, k1p, plan.view(step, "w1"))], (d3col, d2, d1, h1, h2, a1))
     if defer:
         plan.defer_dlogs(step, net.packed("w2", dt), dw2, an2, db2, hid, hid)
         plan.defer_dlogs(step, net.packed("w1", dt), plan.view(step, "w1"), an1, db1, hid, k1p, ones_col=ones)
@@ -680,6 +680,7 @@ def step_backward_nchw(step, ctx, dy, dld):
     plan = grad_plan(_layer_view(step), dy.device)
     plan.begin()
     dx = _step_backward(step, ctx, _to_rows(dy), dld, n, c, h, w, plan)
+    ctx.clear()
     plan.finish()
     return _to_nchw(dx, n, c, h, w)
 
@@ -754,9 +755,11 @@ def backward(flow, tape, dz, dld):
     for kind, layer, ctx in reversed(tape):
         if kind == "step":
             cur = _step_backward(layer, ctx, cur, dld, n, c, h, w, plan)
+            ctx.clear()                     # saved (or recomputed) activations of this step go back to the allocator now
         elif kind == "split":
             c = c * 2                       # `cur` is the [P][C] buffer the squeeze adjoint below left half-filled
             cur = _split_backward(layer, ctx, cur, dld, n, c, h, w, plan)
+            ctx.clear()
         else:
             lv = plan.level_of.get(id(layer))
             if lv is not None:              # the level that starts at this Squeeze2d is fully differentiated
