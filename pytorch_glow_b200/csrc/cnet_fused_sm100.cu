@@ -2,7 +2,8 @@
 //
 // Forward, per 128-pixel tile (hidden = 512):
 //   GEMM1  acc[128][512] = a1[128][K1] . W1[512][K1]^T        conv1 3x3 in im2col form, SS-mode MMA, four 128-column chunks
-//   EPI1   h1 = relu(acc*s1 + t1) -> bf16 -> TMEM (tcgen05.st)  (+ optional TMA store of h1 for the backward pass)
+//   EPI1   h1 = relu(acc*s1 + t1) -> bf16 -> TMEM (tcgen05.st)  (+ optional TMA store of h1 for the backward pass, + its
+//          ReLU mask as bits: template parameter MASKS)
 //   GEMM2  acc[128][512] = h1 . W2[512][512]^T                 conv2 1x1, **A operand read from TMEM** (TS-mode MMA)
 //   EPI2   h2 = relu(acc*s2 + t2) -> bf16 -> 32 KB shared-memory chunk (K-major, SWIZZLE_128B) (+ optional TMA store)
 //   GEMM3  P3[128][N3] += h2 chunk . W3[N3][chunk]^T           conv3 as nine pointwise GEMMs folded into N (tap form)
@@ -13,12 +14,17 @@
 //   GEMM1  d_h2 = dP3[128][K3] . W3t[512][K3]^T ; EPI1: d2 = [h2 > 0] * d_h2 * s2 -> TMEM + TMA store (wgrad operand)
 //   GEMM2  d_h1 = d2 . W2t^T                    ; EPI2: d1 = [h1 > 0] * d_h1 * s1 -> smem chunk + TMA store
 //   GEMM3  dA1[128][K1p] += d1 chunk . W1t[K1p][chunk]^T ; EPI3: bf16 store
+// The two ReLU masks come either as the bf16 activations themselves (TMA boxes loaded in place into the staging slices)
+// or, MASKS = true, as the bits the training forward wrote (cp.async into shared memory one phase ahead).  GEMM2's first
+// column chunk starts under EPI1's last chunk (per-chunk h1_full barriers).
 //
-// Roles (320 threads, one CTA per SM, persistent over tiles):
+// Roles (384 threads, one CTA per SM, persistent over tiles):
 //   warp 0      TMA producer: the tile's A operand (resident for the whole tile) + every weight box, in issue order,
 //               through a ring of stages (one or two 16 KB boxes each)
 //   warp 1      MMA issuer: the warp runs warp-uniform, one elected lane issues (see elect_one_sync)
 //   warps 2..9  epilogue: warp (g, q) owns TMEM lane quarter q and the column half g of every 128-column chunk
+//   warps 10,11 operand gather (implicit GEMM): build the im2col tile of conv1 / dgrad3 in shared memory from the
+//               fp32 flow state, one tile ahead of GEMM1
 // TMEM (512 columns): [0,256) h1 / d2 as bf16 pairs; [256,384) chunk accumulator; [384,512) GEMM3's accumulator,
 //   which doubles as the second chunk accumulator of GEMM1 (ping-pong while EPI1 is the bottleneck).  GEMM2 runs on
 //   the single accumulator: while EPI2 drains chunk c the tensor pipe works on GEMM3's partial sum for chunk c-1.
