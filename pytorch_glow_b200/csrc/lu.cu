@@ -312,7 +312,8 @@ __global__ void lu_assemble_kernel(const float* __restrict__ p, const float* __r
 __global__ void lu_grads_kernel(const float* __restrict__ dw, const float* __restrict__ p, const float* __restrict__ l,
                                 const float* __restrict__ u, const float* __restrict__ sign_s,
                                 const float* __restrict__ log_s, int C, float* __restrict__ dl, float* __restrict__ du,
-                                float* __restrict__ dlog_s, int* __restrict__ rowsrc) {
+                                float* __restrict__ dlog_s) {
+  __shared__ int rowsrc[1024];                      // (C <= 1024, checked by the entry point; no allocation: graph-safe)
   const int tid = threadIdx.x, nthr = blockDim.x;
   // rowsrc[r] = i with P[i][r] = 1  (G[r][:] = dW[i][:])
   for (int r = tid; r < C; r += nthr) {
@@ -423,13 +424,8 @@ extern "C" int glowk_invconv_lu_grads(const float* dw, const float* p, const flo
                                       float* dlog_s, void* stream) {
   GLOWK_CHECK_ARG(dw && p && l && u && sign_s && log_s && dl && du && dlog_s, "glowk_invconv_lu_grads: null pointer");
   GLOWK_CHECK_ARG(C > 0 && C <= 1024, "glowk_invconv_lu_grads: C out of range");
-  cudaStream_t st = (cudaStream_t)stream;
-  int* rowsrc = nullptr;
-  GLOWK_CUDA(cudaMallocAsync((void**)&rowsrc, (size_t)C * sizeof(int), st));
   const int threads = C <= 16 ? 64 : (C <= 48 ? 256 : 1024);
-  lu_grads_kernel<<<1, threads, 0, st>>>(dw, p, l, u, sign_s, log_s, (int)C, dl, du, dlog_s, rowsrc);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(rowsrc, st);
-  if (e != cudaSuccess) return fail(GLOWK_ECUDA, "glowk_invconv_lu_grads: %s", cudaGetErrorString(e));
+  lu_grads_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(dw, p, l, u, sign_s, log_s, (int)C, dl, du, dlog_s);
+  GLOWK_CHECK_LAUNCH("glowk_invconv_lu_grads");
   return GLOWK_OK;
 }
