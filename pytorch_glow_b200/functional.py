@@ -374,6 +374,9 @@ _tickets = {}
 
 
 def _ticket(device):
+    """One zero-initialised counter per device for glowk_nll_head's last-CTA reduction (the kernel leaves it at zero).
+    Launches that use it must be stream-ordered per device: one loss head at a time per GPU, which is what a training
+    / evaluation process does; two models driven concurrently on different streams of ONE device need their own."""
     t = _tickets.get(device)
     if t is None:
         t = _tickets[device] = torch.zeros(4, device=device, dtype=torch.int32)
