@@ -156,3 +156,28 @@ def test_flowmodel_training_under_dataparallel_replica_raises():
     fm._is_replica = True                             # what torch.nn.parallel.replicate sets on replicas
     with pytest.raises(RuntimeError, match="DataParallel"):
         fm.encode(torch.zeros(1, 3, 8, 8))
+
+
+def test_layer_route_logdet_conventions_and_recompute_switch(monkeypatch):
+    """Host logic of the stand-alone FlowStep route: the reference's logdet conventions (None / number / 0-dim / [N]
+    tensor; an additive step keeps a scalar logdet scalar, an affine one returns one value per sample) and the
+    activation-recompute switch read from the environment."""
+    import importlib
+    import pytorch_glow_b200 as G
+    from pytorch_glow_b200 import config
+    np.random.seed(0)
+    add = G.FlowStep(4, 8, permutation="reverse", coupling="additive")
+    aff = G.FlowStep(4, 8, permutation="reverse", coupling="affine")
+    cpu = torch.device("cpu")
+    vec, scalar_like = add._rows_logdet_in(0.5, 3, cpu)
+    assert scalar_like and vec.shape == (3,) and torch.all(vec == 0.5)
+    assert add._rows_logdet_out(vec + 1.0, scalar_like).dim() == 0            # additive: stays a scalar
+    assert aff._rows_logdet_out(vec + 1.0, scalar_like).shape == (3,)         # affine: one value per sample
+    vec, scalar_like = add._rows_logdet_in(torch.arange(3.), 3, cpu)
+    assert not scalar_like and add._rows_logdet_out(vec, scalar_like).shape == (3,)
+    assert add._rows_logdet_in(None, 3, cpu) == (None, False) and add._rows_logdet_out(None, False) is None
+    assert not add._rows_route(torch.zeros(3, 4, 2, 2))                       # CPU tensors never take the rows route
+    monkeypatch.setenv("GLOWK_RECOMPUTE", "1")
+    assert importlib.reload(config).recompute_activations is True
+    monkeypatch.setenv("GLOWK_RECOMPUTE", "0")
+    assert importlib.reload(config).recompute_activations is False
